@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE — stand-in for leap/lml/io.h (see vector.h in this directory).
+#pragma once
+#include "vector.h"
