@@ -1,0 +1,699 @@
+// datum_b200 — C ABI of libdatum_ibl_cuda (see include/datum_ibl_cuda.h).
+//
+// Owns the device context: stream, cached per-level sample tables, grow-only
+// device scratch (payload chain, quad records, SH9 weight table and partials).
+// No CPU fallback exists anywhere in this library: every entry point either runs
+// the CUDA kernels or fails with an error string.
+
+#include "../../include/datum_ibl_cuda.h"
+
+#include "ibl_math.cuh"
+#include "ibl_tables.h"
+#include "prefilter.h"
+#include "sh9.h"
+#include "luts.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace
+{
+  thread_local std::string g_last_error;
+
+  int fail(std::string const &what)
+  {
+    g_last_error = what;
+    return 1;
+  }
+
+  int fail_cuda(const char *where, cudaError_t err)
+  {
+    g_last_error = std::string(where) + ": " + cudaGetErrorString(err);
+    return 1;
+  }
+
+  struct DeviceTable
+  {
+    float4 *d_entries = nullptr;
+    int count = 0;
+    float norm = 0; // kAccScale / total weight
+  };
+
+  template<typename T>
+  struct DeviceBuffer
+  {
+    T *ptr = nullptr;
+    size_t capacity = 0;
+
+    cudaError_t reserve(size_t count)
+    {
+      if (count <= capacity)
+        return cudaSuccess;
+
+      if (ptr)
+        cudaFree(ptr);
+
+      ptr = nullptr;
+      capacity = 0;
+
+      cudaError_t err = cudaMalloc(&ptr, count * sizeof(T));
+      if (err == cudaSuccess)
+        capacity = count;
+
+      return err;
+    }
+
+    void release()
+    {
+      if (ptr)
+        cudaFree(ptr);
+      ptr = nullptr;
+      capacity = 0;
+    }
+  };
+}
+
+struct datum_ibl_ctx
+{
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  bool timed = false;
+
+  uint64_t launches = 0;
+  int prefilter_variant = 0;
+
+  ibl::Quatf quats[6];
+
+  std::map<std::pair<int, int>, std::vector<DeviceTable>> tables; // (levels, samples) -> per level
+
+  DeviceBuffer<uint32_t> chain;   // staged payload for the host entry point
+  DeviceBuffer<uint4> records;    // quad records of the current source level
+  DeviceBuffer<float> sh_weights; // solid angle table
+  int sh_weights_w = 0, sh_weights_h = 0;
+  DeviceBuffer<double> sh_partials; // block partials + 28 result doubles
+  DeviceBuffer<unsigned char> staging; // generic device staging for host entry points
+  DeviceBuffer<float> sink;
+};
+
+namespace
+{
+  struct DeviceGuard
+  {
+    int previous = -1;
+    explicit DeviceGuard(int device)
+    {
+      cudaGetDevice(&previous);
+      if (previous != device)
+        cudaSetDevice(device);
+    }
+    ~DeviceGuard()
+    {
+      if (previous >= 0)
+        cudaSetDevice(previous);
+    }
+  };
+
+  bool valid_chain(int width, int height, int levels)
+  {
+    if (width < 1 || height < 1 || levels < 1 || levels > 16)
+      return false;
+
+    // every level of the chain must have at least one texel, and a level that is
+    // convolved needs a source of at least 2x2 (the bilinear footprint of ibl.cpp:40)
+    if ((width >> (levels - 1)) < 1 || (height >> (levels - 1)) < 1)
+      return false;
+
+    return true;
+  }
+
+  int get_tables(datum_ibl_ctx *ctx, int levels, int samples, std::vector<DeviceTable> **out)
+  {
+    auto key = std::make_pair(levels, samples);
+    auto it = ctx->tables.find(key);
+    if (it == ctx->tables.end())
+    {
+      std::vector<DeviceTable> built(levels);
+
+      for(int level = 1; level < levels; ++level)
+      {
+        ibl::LevelSamples host = ibl::build_level_samples(level, levels, samples);
+
+        DeviceTable &t = built[level];
+        t.count = host.accepted;
+        t.norm = (float)((double)ibl::kAccScale / host.total_weight);
+
+        cudaError_t err = cudaMalloc(&t.d_entries, sizeof(float4) * (size_t)(t.count > 0 ? t.count : 1));
+        if (err != cudaSuccess)
+          return fail_cuda("cudaMalloc(sample table)", err);
+
+        static_assert(sizeof(ibl::SampleEntry) == sizeof(float4), "table entry layout");
+
+        err = cudaMemcpyAsync(t.d_entries, host.entries.data(), sizeof(float4) * (size_t)t.count, cudaMemcpyHostToDevice, ctx->stream);
+        if (err == cudaSuccess)
+          err = cudaStreamSynchronize(ctx->stream); // `host` dies at the end of this iteration
+        if (err != cudaSuccess)
+          return fail_cuda("upload(sample table)", err);
+      }
+
+      it = ctx->tables.emplace(key, std::move(built)).first;
+    }
+
+    *out = &it->second;
+    return 0;
+  }
+
+  // one level on the context's stream: records of the source level, then the prefilter slab
+  int run_level(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32)
+  {
+    int wd = ws >> 1, hd = hs >> 1;
+
+    if (ws < 2 || hs < 2)
+      return fail("prefilter: source level must be at least 2x2");
+
+    if (row_begin < 0 || row_end > 6 * hd || row_begin > row_end)
+      return fail("prefilter: row range outside the destination level");
+
+    if (row_begin == row_end)
+      return 0;
+
+    cudaError_t err = ctx->records.reserve((size_t)6 * ws * hs);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(quad records)", err);
+
+    err = ibl::launch_build_quad_records(d_src, ctx->records.ptr, ws, hs, ctx->sm_count, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("build_quad_records", err);
+    ctx->launches += 1;
+
+    ibl::PrefilterParams p = {};
+    p.records = ctx->records.ptr;
+    p.table = table.d_entries;
+    p.table_count = table.count;
+    p.dst_words = d_dst_words;
+    p.dst_f32 = d_dst_f32;
+    p.wd = wd;
+    p.hd = hd;
+    p.row_begin = row_begin;
+    p.row_end = row_end;
+    p.geom = ibl::make_level_geom(ws, hs);
+    for(int f = 0; f < 6; ++f)
+      p.quats[f] = ctx->quats[f];
+    p.norm = table.norm;
+
+    err = ibl::launch_prefilter_level(p, ctx->prefilter_variant, ctx->sm_count, ctx->stream, nullptr);
+    if (err != cudaSuccess)
+      return fail_cuda("prefilter_level", err);
+    ctx->launches += 1;
+
+    return 0;
+  }
+
+  int run_chain(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, uint32_t *d_bits, float *d_f32)
+  {
+    std::vector<DeviceTable> *tables = nullptr;
+    if (get_tables(ctx, levels, samples, &tables))
+      return 1;
+
+    cudaEventRecord(ctx->ev_begin, ctx->stream);
+
+    uint32_t *src = d_bits;
+    uint32_t *dst = src + (size_t)width * height * 6;
+
+    // tools/ibl.cpp:247-278
+    for(int level = 1; level < levels; ++level)
+    {
+      int hd = height >> 1;
+
+      if (run_level(ctx, src, width, height, (*tables)[level], 0, 6 * hd, dst, d_f32))
+        return 1;
+
+      size_t outcount = (size_t)(width >> 1) * hd * 6;
+
+      src += (size_t)width * height * 6;
+      dst += outcount;
+      if (d_f32)
+        d_f32 += 3 * outcount;
+
+      width /= 2;
+      height /= 2;
+    }
+
+    cudaEventRecord(ctx->ev_end, ctx->stream);
+    ctx->timed = true;
+
+    return 0;
+  }
+}
+
+extern "C"
+{
+  const char *datum_ibl_last_error(void) { return g_last_error.c_str(); }
+
+  int datum_ibl_create(int device, datum_ibl_ctx **out)
+  {
+    if (!out)
+      return fail("datum_ibl_create: null out pointer");
+
+    *out = nullptr;
+
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+      return fail(std::string("datum_ibl_create: no CUDA device (") + cudaGetErrorString(err) + "); libdatum_ibl_cuda has no CPU fallback");
+
+    if (device < 0 || device >= count)
+      return fail("datum_ibl_create: device index out of range");
+
+    DeviceGuard guard(device);
+
+    cudaDeviceProp prop;
+    err = cudaGetDeviceProperties(&prop, device);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaGetDeviceProperties", err);
+
+    if (prop.major < 10)
+      return fail(std::string("datum_ibl_create: kernels are built for sm_100a only, device is ") + prop.name);
+
+    datum_ibl_ctx *ctx = new datum_ibl_ctx;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+
+    err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess)
+      err = cudaEventCreate(&ctx->ev_begin);
+    if (err == cudaSuccess)
+      err = cudaEventCreate(&ctx->ev_end);
+    if (err != cudaSuccess)
+    {
+      delete ctx;
+      return fail_cuda("datum_ibl_create", err);
+    }
+
+    // tools/ibl.cpp:253-261: Quaternion(axis, angle) = (cos(angle/2), axis*sin(angle/2)) in fp32
+    const float pi = 3.14159265358979323846f;
+    const float angles[6] = { -pi/2, pi/2, -pi/2, pi/2, 0.0f, pi };
+    const int axes[6] = { 1, 1, 0, 0, 1, 1 };
+    for(int f = 0; f < 6; ++f)
+    {
+      float c = std::cos(angles[f]/2), s = std::sin(angles[f]/2);
+      ctx->quats[f] = ibl::Quatf{ c, axes[f] == 0 ? s : 0.0f, axes[f] == 1 ? s : 0.0f, 0.0f };
+    }
+
+    *out = ctx;
+    return 0;
+  }
+
+  void datum_ibl_destroy(datum_ibl_ctx *ctx)
+  {
+    if (!ctx)
+      return;
+
+    DeviceGuard guard(ctx->device);
+
+    cudaStreamSynchronize(ctx->stream);
+
+    for(auto &entry : ctx->tables)
+      for(auto &t : entry.second)
+        if (t.d_entries)
+          cudaFree(t.d_entries);
+
+    ctx->chain.release();
+    ctx->records.release();
+    ctx->sh_weights.release();
+    ctx->sh_partials.release();
+    ctx->staging.release();
+    ctx->sink.release();
+
+    cudaEventDestroy(ctx->ev_begin);
+    cudaEventDestroy(ctx->ev_end);
+    cudaStreamDestroy(ctx->stream);
+
+    delete ctx;
+  }
+
+  void *datum_ibl_stream(datum_ibl_ctx *ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+  int datum_ibl_synchronize(datum_ibl_ctx *ctx)
+  {
+    if (!ctx)
+      return fail("null context");
+
+    DeviceGuard guard(ctx->device);
+    cudaError_t err = cudaStreamSynchronize(ctx->stream);
+    return err == cudaSuccess ? 0 : fail_cuda("cudaStreamSynchronize", err);
+  }
+
+  uint64_t datum_ibl_launch_count(datum_ibl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+  int datum_ibl_set_prefilter_variant(datum_ibl_ctx *ctx, int variant)
+  {
+    if (!ctx || variant < 0 || variant > 7)
+      return fail("datum_ibl_set_prefilter_variant: bad argument");
+
+    ctx->prefilter_variant = variant;
+    return 0;
+  }
+
+  size_t datum_ibl_chain_bytes(int width, int height, int levels)
+  {
+    size_t size = 0;
+    for(int i = 0; i < levels; ++i)
+      size += (size_t)(width >> i) * (size_t)(height >> i) * 6 * sizeof(uint32_t);
+    return size;
+  }
+
+  int datum_ibl_buildmips_cube_ibl_device(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, uint32_t *d_bits, float *d_f32)
+  {
+    if (!ctx || !d_bits)
+      return fail("datum_ibl_buildmips_cube_ibl_device: null argument");
+    if (!valid_chain(width, height, levels) || samples < 1)
+      return fail("datum_ibl_buildmips_cube_ibl_device: bad width/height/levels/samples");
+
+    DeviceGuard guard(ctx->device);
+    return run_chain(ctx, width, height, levels, samples, d_bits, d_f32);
+  }
+
+  int datum_ibl_buildmips_cube_ibl(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, void *bits)
+  {
+    if (!ctx || !bits)
+      return fail("datum_ibl_buildmips_cube_ibl: null argument");
+    if (!valid_chain(width, height, levels) || samples < 1)
+      return fail("datum_ibl_buildmips_cube_ibl: bad width/height/levels/samples");
+
+    DeviceGuard guard(ctx->device);
+
+    size_t words = datum_ibl_chain_bytes(width, height, levels) / sizeof(uint32_t);
+    size_t level0 = (size_t)width * height * 6;
+
+    cudaError_t err = ctx->chain.reserve(words);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(chain)", err);
+
+    err = cudaMemcpyAsync(ctx->chain.ptr, bits, level0 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMemcpyAsync(level 0)", err);
+
+    if (run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr))
+      return 1;
+
+    if (words > level0)
+    {
+      err = cudaMemcpyAsync((uint32_t*)bits + level0, ctx->chain.ptr + level0, (words - level0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+      if (err != cudaSuccess)
+        return fail_cuda("cudaMemcpyAsync(levels)", err);
+    }
+
+    err = cudaStreamSynchronize(ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("datum_ibl_buildmips_cube_ibl", err);
+
+    return 0;
+  }
+
+  int datum_ibl_prefilter_level_device(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, int level, int levels, int samples, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32)
+  {
+    if (!ctx || !d_src)
+      return fail("datum_ibl_prefilter_level_device: null argument");
+    if (levels < 2 || levels > 16 || level < 1 || level >= levels || samples < 1)
+      return fail("datum_ibl_prefilter_level_device: bad level/levels/samples");
+
+    DeviceGuard guard(ctx->device);
+
+    std::vector<DeviceTable> *tables = nullptr;
+    if (get_tables(ctx, levels, samples, &tables))
+      return 1;
+
+    return run_level(ctx, d_src, ws, hs, (*tables)[level], row_begin, row_end, d_dst_words, d_dst_f32);
+  }
+
+  int datum_ibl_last_prefilter_ms(datum_ibl_ctx *ctx, float *ms)
+  {
+    if (!ctx || !ms)
+      return fail("datum_ibl_last_prefilter_ms: null argument");
+    if (!ctx->timed)
+      return fail("datum_ibl_last_prefilter_ms: no chain has run yet");
+
+    DeviceGuard guard(ctx->device);
+
+    cudaError_t err = cudaEventSynchronize(ctx->ev_end);
+    if (err == cudaSuccess)
+      err = cudaEventElapsedTime(ms, ctx->ev_begin, ctx->ev_end);
+
+    return err == cudaSuccess ? 0 : fail_cuda("cudaEventElapsedTime", err);
+  }
+
+  // ---- SH9 ----------------------------------------------------------------------
+
+  int datum_ibl_sh9_partial_device(datum_ibl_ctx *ctx, void const *d_level0, int format, int width, int height, int row_begin, int row_end, double *d_partial)
+  {
+    if (!ctx || !d_level0 || !d_partial)
+      return fail("datum_ibl_sh9_partial_device: null argument");
+    if (width < 1 || height < 1 || (format != DATUM_IBL_FORMAT_RGBE && format != DATUM_IBL_FORMAT_F32))
+      return fail("datum_ibl_sh9_partial_device: bad width/height/format");
+    if (row_begin < 0 || row_end > 6 * height || row_begin > row_end)
+      return fail("datum_ibl_sh9_partial_device: row range outside the cube");
+
+    DeviceGuard guard(ctx->device);
+
+    if (ctx->sh_weights_w != width || ctx->sh_weights_h != height)
+    {
+      cudaError_t err = ctx->sh_weights.reserve((size_t)width * height);
+      if (err != cudaSuccess)
+        return fail_cuda("cudaMalloc(sh9 weights)", err);
+
+      err = ibl::launch_sh9_weights(ctx->sh_weights.ptr, width, height, ctx->stream);
+      if (err != cudaSuccess)
+        return fail_cuda("sh9_weights", err);
+      ctx->launches += 1;
+
+      ctx->sh_weights_w = width;
+      ctx->sh_weights_h = height;
+    }
+
+    int blocks = ibl::sh9_partial_blocks(width, height, ctx->sm_count);
+
+    cudaError_t err = ctx->sh_partials.reserve((size_t)blocks * 28 + 28);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(sh9 partials)", err);
+
+    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, d_partial, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("sh9_partial", err);
+    ctx->launches += 2;
+
+    return 0;
+  }
+
+  void datum_ibl_sh9_finish(double const *partial, float *sh)
+  {
+    const double pi = 3.1415926535897932384626433832795;
+    double scale = 4 * pi / partial[27];
+    for(int k = 0; k < 27; ++k)
+      sh[k] = (float)(partial[k] * scale);
+  }
+
+  int datum_ibl_project_sh9(datum_ibl_ctx *ctx, void const *level0, int format, int width, int height, float *sh)
+  {
+    if (!ctx || !level0 || !sh)
+      return fail("datum_ibl_project_sh9: null argument");
+    if (width < 1 || height < 1 || (format != DATUM_IBL_FORMAT_RGBE && format != DATUM_IBL_FORMAT_F32))
+      return fail("datum_ibl_project_sh9: bad width/height/format");
+
+    DeviceGuard guard(ctx->device);
+
+    size_t bytes = (size_t)6 * width * height * (format == DATUM_IBL_FORMAT_RGBE ? 4 : 16);
+
+    cudaError_t err = ctx->staging.reserve(bytes + 28 * sizeof(double));
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(staging)", err);
+
+    // result slot first so that it stays 8-byte aligned
+    double *d_partial = reinterpret_cast<double*>(ctx->staging.ptr);
+    unsigned char *d_level0 = ctx->staging.ptr + 28 * sizeof(double);
+
+    err = cudaMemcpyAsync(d_level0, level0, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMemcpyAsync(level 0)", err);
+
+    if (datum_ibl_sh9_partial_device(ctx, d_level0, format, width, height, 0, 6 * height, d_partial))
+      return 1;
+
+    double partial[28];
+    err = cudaMemcpyAsync(partial, d_partial, sizeof(partial), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess)
+      err = cudaStreamSynchronize(ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("datum_ibl_project_sh9", err);
+
+    datum_ibl_sh9_finish(partial, sh);
+    return 0;
+  }
+
+  int datum_ibl_sh9_irradiance_cube(datum_ibl_ctx *ctx, float const *sh, int width, int height, uint32_t *words, float *f32)
+  {
+    if (!ctx || !sh || (!words && !f32))
+      return fail("datum_ibl_sh9_irradiance_cube: null argument");
+    if (width < 1 || height < 1)
+      return fail("datum_ibl_sh9_irradiance_cube: bad width/height");
+
+    DeviceGuard guard(ctx->device);
+
+    size_t texels = (size_t)6 * width * height;
+
+    cudaError_t err = ctx->staging.reserve(texels * 16);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(staging)", err);
+
+    float *d_f32 = reinterpret_cast<float*>(ctx->staging.ptr);
+    uint32_t *d_words = reinterpret_cast<uint32_t*>(ctx->staging.ptr + texels * 12);
+
+    ibl::Sh9Coefficients coeffs;
+    memcpy(coeffs.v, sh, sizeof(coeffs.v));
+
+    err = ibl::launch_sh9_irradiance(coeffs, width, height, words ? d_words : nullptr, f32 ? d_f32 : nullptr, ctx->sm_count, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("sh9_irradiance", err);
+    ctx->launches += 1;
+
+    if (words)
+      err = cudaMemcpyAsync(words, d_words, texels * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess && f32)
+      err = cudaMemcpyAsync(f32, d_f32, texels * 12, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess)
+      err = cudaStreamSynchronize(ctx->stream);
+
+    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_sh9_irradiance_cube", err);
+  }
+
+  // ---- LUTs -----------------------------------------------------------------------
+
+  int datum_ibl_pack_envbrdf(datum_ibl_ctx *ctx, int width, int height, int samples, void *bits)
+  {
+    if (!ctx || !bits)
+      return fail("datum_ibl_pack_envbrdf: null argument");
+    if (width < 1 || height < 1 || samples < 1)
+      return fail("datum_ibl_pack_envbrdf: bad width/height/samples");
+
+    DeviceGuard guard(ctx->device);
+
+    size_t texels = (size_t)width * height;
+
+    cudaError_t err = ctx->staging.reserve(texels * 4);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(staging)", err);
+
+    uint32_t *d_words = reinterpret_cast<uint32_t*>(ctx->staging.ptr);
+
+    err = ibl::launch_envbrdf(width, height, samples, d_words, nullptr, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("envbrdf", err);
+    ctx->launches += 1;
+
+    err = cudaMemcpyAsync(bits, d_words, texels * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess)
+      err = cudaStreamSynchronize(ctx->stream);
+
+    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_pack_envbrdf", err);
+  }
+
+  int datum_ibl_pack_watercolor(datum_ibl_ctx *ctx, float const *deepcolor, float const *shallowcolor, float depthscale, float const *fresnelcolor, float fresnelbias, float fresnelpower, int width, int height, void *bits)
+  {
+    if (!ctx || !bits || !deepcolor || !shallowcolor || !fresnelcolor)
+      return fail("datum_ibl_pack_watercolor: null argument");
+    if (width < 1 || height < 1)
+      return fail("datum_ibl_pack_watercolor: bad width/height");
+
+    DeviceGuard guard(ctx->device);
+
+    size_t texels = (size_t)width * height;
+
+    cudaError_t err = ctx->staging.reserve(texels * 4);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(staging)", err);
+
+    uint32_t *d_words = reinterpret_cast<uint32_t*>(ctx->staging.ptr);
+
+    ibl::WaterColorParams params;
+    for(int c = 0; c < 3; ++c)
+    {
+      params.deep[c] = deepcolor[c];
+      params.shallow[c] = shallowcolor[c];
+      params.fresnel[c] = fresnelcolor[c];
+    }
+    params.depthscale = depthscale;
+    params.fresnelbias = fresnelbias;
+    params.fresnelpower = fresnelpower;
+
+    err = ibl::launch_watercolor(params, width, height, d_words, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("watercolor", err);
+    ctx->launches += 1;
+
+    err = cudaMemcpyAsync(bits, d_words, texels * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess)
+      err = cudaStreamSynchronize(ctx->stream);
+
+    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_pack_watercolor", err);
+  }
+
+  // ---- measurement ------------------------------------------------------------------
+
+  int datum_ibl_measure_fp32_peak(datum_ibl_ctx *ctx, double *tflops)
+  {
+    if (!ctx || !tflops)
+      return fail("datum_ibl_measure_fp32_peak: null argument");
+
+    DeviceGuard guard(ctx->device);
+
+    const int threads = 256, blocks = ctx->sm_count * 8, iters = 1 << 15;
+
+    cudaError_t err = ctx->sink.reserve((size_t)threads * blocks);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(sink)", err);
+
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+
+    double best = 0;
+
+    for(int rep = 0; rep < 5 && err == cudaSuccess; ++rep)
+    {
+      cudaEventRecord(e0, ctx->stream);
+      err = ibl::launch_fma_peak(ctx->sink.ptr, blocks, threads, iters, ctx->stream);
+      cudaEventRecord(e1, ctx->stream);
+      ctx->launches += 1;
+
+      if (err == cudaSuccess)
+        err = cudaEventSynchronize(e1);
+
+      float ms = 0;
+      if (err == cudaSuccess)
+        err = cudaEventElapsedTime(&ms, e0, e1);
+
+      if (err == cudaSuccess && rep > 0 && ms > 0) // rep 0 warms up
+      {
+        double flops = 2.0 * 16.0 * (double)iters * threads * blocks;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+      }
+    }
+
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+
+    if (err != cudaSuccess)
+      return fail_cuda("datum_ibl_measure_fp32_peak", err);
+
+    *tflops = best;
+    return 0;
+  }
+}

@@ -1,0 +1,65 @@
+// datum_b200 — per-level GGX sample tables (host side); see ibl_tables.h.
+
+#include "ibl_tables.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace ibl
+{
+  float radicalinverse_VdC(uint32_t bits)
+  {
+    uint32_t r = 0;
+    for(int k = 0; k < 32; ++k, bits >>= 1)
+      r = (r << 1) | (bits & 1u);
+
+    return float(r) * 2.3283064365386963e-10f; // 2^-32, rounded to fp32 like ibl.cpp:103
+  }
+
+  LevelSamples build_level_samples(int level, int levels, int samples)
+  {
+    LevelSamples out;
+
+    // ibl.cpp:251, 173: roughness = level/(levels-1), alpha = roughness^2 — in fp32 like the reference
+    float roughness = (float)level / (float)(levels - 1);
+    float alpha = roughness * roughness;
+    float a2m1 = alpha * alpha - 1;
+
+    out.roughness = roughness;
+    out.entries.reserve(samples);
+
+    for(int i = 0; i < samples; ++i)
+    {
+      // ibl.cpp:106-109, 119-121 in fp32 so that (phi, theta) are the reference's values
+      float ux = float(i) / float(samples);
+      float uy = radicalinverse_VdC((uint32_t)i);
+      float phi = 2 * 3.14159265358979323846f * ux;
+      float costheta = std::sqrt((1 - uy) / (1 + a2m1 * uy));
+      float sintheta = std::sqrt(1 - costheta * costheta);
+
+      double hx = (double)sintheta * std::cos((double)phi);
+      double hy = (double)sintheta * std::sin((double)phi);
+      double hz = (double)costheta;
+
+      double lz = 2 * hz * hz - 1;
+
+      if (!(lz > 0))
+        continue; // ibl.cpp:178
+
+      SampleEntry e;
+      e.lx = (float)(2 * hz * hx);
+      e.ly = (float)(2 * hz * hy);
+      e.lz = (float)std::min(lz, 1.0);
+      e.wh = 0.5f * e.lz;
+
+      out.total_weight += (double)e.lz;
+      out.entries.push_back(e);
+    }
+
+    out.accepted = (int)out.entries.size();
+
+    std::stable_sort(out.entries.begin(), out.entries.end(), [](SampleEntry const &a, SampleEntry const &b) { return a.lz > b.lz; });
+
+    return out;
+  }
+}

@@ -1,0 +1,30 @@
+// datum_b200 — launch interface of the prefilter kernels (internal to libdatum_ibl_cuda).
+#pragma once
+
+#include "ibl_math.cuh"
+
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ibl
+{
+  struct PrefilterParams
+  {
+    uint4 const *records;    // quad records of the SOURCE level (6*ws*hs)
+    float4 const *table;     // sample table of this level: (lx, ly, lz, 0.5*lz), decreasing lz
+    int table_count;
+    uint32_t *dst_words;     // destination level base, rgbe words (may be null)
+    float *dst_f32;          // destination level base, fp32 rgb triples before quantisation (may be null)
+    int wd, hd;              // destination level size
+    int row_begin, row_end;  // slab of the 6*hd face-major rows to compute
+    LevelGeom geom;          // source level addressing constants
+    Quatf quats[6];          // face rotations, tools/ibl.cpp:253-261
+    float norm;              // kAccScale / total weight
+    int tiles_x, tiles;      // filled by the launcher
+  };
+
+  // variant 0 = pick by slab size; 1..7 = fixed <tile width, texels per lane, warps per tile>
+  cudaError_t launch_prefilter_level(PrefilterParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid);
+
+  cudaError_t launch_build_quad_records(uint32_t const *src, uint4 *records, int ws, int hs, int sm_count, cudaStream_t stream);
+}

@@ -1,0 +1,288 @@
+// datum_b200 — SH9 irradiance projection of a cube map and its evaluation (sm_100a).
+//
+// Replaces the single-thread GLSL loop of data/project.comp:23-106 (reference
+// paths relative to /root/reference).  The texel solid angle (project.comp:56-60)
+// depends only on (x, y), not on the face, and its four-atan form cancels
+// catastrophically in fp32 once faces exceed a few hundred texels, so it is
+// evaluated ONCE per (x, y) in fp64 into a table that the context caches per
+// face size.  The projection itself is HBM-bound (16 B/texel RGBA32F, 100 B per
+// (x, y) column of six faces): one thread per (x, y) reads the six face texels
+// with coalesced 16-byte loads, shares the normalisation across the six
+// signed-permutation rays, accumulates 27 sums + the weight sum in registers,
+// then warp-shuffle and block-reduce in fp64.  Block partials are summed in a
+// fixed order by a second kernel, so the result is run-to-run deterministic.
+
+#include "sh9.h"
+#include "ibl_math.cuh"
+
+#include <cuda_runtime.h>
+
+namespace ibl
+{
+  // ---- solid angle table -------------------------------------------------------
+
+  __device__ __forceinline__ double corner_angle(double x, double y) { return atan2(x * y, sqrt(x * x + y * y + 1.0)); }
+
+  __global__ void __launch_bounds__(256) sh9_weights_kernel(float *__restrict__ weights, int w, int h)
+  {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= w * h)
+      return;
+
+    int x = idx % w, y = idx / w;
+
+    // project.comp:53, 56-60
+    double u = 2 * (x + 0.5) / w - 1;
+    double v = 2 * (y + 0.5) / h - 1;
+    double x0 = u - 1.0 / w, x1 = u + 1.0 / w;
+    double y0 = v - 1.0 / h, y1 = v + 1.0 / h;
+
+    weights[idx] = (float)(corner_angle(x0, y0) - corner_angle(x0, y1) - corner_angle(x1, y0) + corner_angle(x1, y1));
+  }
+
+  // ---- projection ----------------------------------------------------------------
+
+  template<int FORMAT>
+  __device__ __forceinline__ void load_texel(void const *__restrict__ level0, size_t idx, float &r, float &g, float &b)
+  {
+    if (FORMAT == 0)
+    {
+      // color.h:164-172 with the 1/511 folded into the scale (<= 1 ulp from the reference decode)
+      uint32_t c = __ldg(reinterpret_cast<uint32_t const *>(level0) + idx);
+      float s = u2f((((c >> 27) & 0x1Fu) + 112u) << 23) * (1.0f / 511.0f);
+      r = (float)((c >> 0) & 0x1FFu) * s;
+      g = (float)((c >> 9) & 0x1FFu) * s;
+      b = (float)((c >> 18) & 0x1FFu) * s;
+    }
+    else
+    {
+      float4 c = __ldg(reinterpret_cast<float4 const *>(level0) + idx);
+      r = c.x; g = c.y; b = c.z;
+    }
+  }
+
+  // acc[3*k + c] += weight * color[c] * Y_k(ray), project.comp:64-92
+  __device__ __forceinline__ void sh9_accumulate(float acc[28], float wr, float wg, float wb, float rx, float ry, float rz)
+  {
+    float basis[9];
+    basis[0] = 0.282095f;
+    basis[1] = 0.488603f * ry;
+    basis[2] = 0.488603f * rz;
+    basis[3] = 0.488603f * rx;
+    basis[4] = 1.092548f * rx * ry;
+    basis[5] = 1.092548f * ry * rz;
+    basis[6] = 0.315392f * (3.0f * rz * rz - 1.0f);
+    basis[7] = 1.092548f * rz * rx;
+    basis[8] = 0.546274f * (rx * rx - ry * ry);
+
+    #pragma unroll
+    for(int k = 0; k < 9; ++k)
+    {
+      acc[3*k + 0] = fmaf(wr, basis[k], acc[3*k + 0]);
+      acc[3*k + 1] = fmaf(wg, basis[k], acc[3*k + 1]);
+      acc[3*k + 2] = fmaf(wb, basis[k], acc[3*k + 2]);
+    }
+  }
+
+  constexpr int kSh9Threads = 256;
+
+  template<int FORMAT>
+  __global__ void __launch_bounds__(kSh9Threads) sh9_partial_kernel(void const *__restrict__ level0, float const *__restrict__ weights, int w, int h, int row_begin, int row_end, double *__restrict__ block_partials)
+  {
+    float acc[28];
+    #pragma unroll
+    for(int k = 0; k < 28; ++k)
+      acc[k] = 0.0f;
+
+    const int pixels = w * h;
+    const float inv_w = 1.0f / (float)w, inv_h = 1.0f / (float)h;
+
+    for(int p = blockIdx.x * kSh9Threads + threadIdx.x; p < pixels; p += gridDim.x * kSh9Threads)
+    {
+      int x = p % w, y = p / w;
+
+      // project.comp:53-54: uv, and the shared 1/|(+-u, +-v, +-1)| of the six face rays
+      float u = 2.0f * ((float)x + 0.5f) * inv_w - 1.0f;
+      float v = 2.0f * ((float)y + 0.5f) * inv_h - 1.0f;
+      float inv = rsqrtf(fmaf(u, u, fmaf(v, v, 1.0f)));
+      float a = u * inv, b = v * inv, c = inv;
+
+      float weight = __ldg(weights + p);
+
+      #pragma unroll
+      for(int face = 0; face < 6; ++face)
+      {
+        int row = face * h + y;
+        if (row < row_begin || row >= row_end)
+          continue;
+
+        float r, g, bl;
+        load_texel<FORMAT>(level0, (size_t)row * w + x, r, g, bl);
+
+        // face rays as in data/convolve.comp:85-100 (equal to project.comp:27-32's quaternions)
+        float rx, ry, rz;
+        switch (face)
+        {
+          case 0: rx = c;  ry = b;  rz = a;  break;
+          case 1: rx = -c; ry = b;  rz = -a; break;
+          case 2: rx = a;  ry = -c; rz = -b; break;
+          case 3: rx = a;  ry = c;  rz = b;  break;
+          case 4: rx = a;  ry = b;  rz = -c; break;
+          default: rx = -a; ry = b; rz = c;  break;
+        }
+
+        sh9_accumulate(acc, weight * r, weight * g, weight * bl, rx, ry, rz);
+        acc[27] += weight;
+      }
+    }
+
+    // ---- warp shuffle reduction in fp64, then across the block's warps ----
+    __shared__ double s_partial[kSh9Threads / 32][28];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    #pragma unroll
+    for(int k = 0; k < 28; ++k)
+    {
+      double v = (double)acc[k];
+      #pragma unroll
+      for(int offset = 16; offset > 0; offset >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, offset);
+
+      if (lane == 0)
+        s_partial[warp][k] = v;
+    }
+
+    __syncthreads();
+
+    if (threadIdx.x < 28)
+    {
+      double v = 0;
+      #pragma unroll
+      for(int wi = 0; wi < kSh9Threads / 32; ++wi)
+        v += s_partial[wi][threadIdx.x];
+
+      block_partials[(size_t)blockIdx.x * 28 + threadIdx.x] = v;
+    }
+  }
+
+  // fixed-order sum of the block partials: deterministic
+  __global__ void __launch_bounds__(32) sh9_combine_kernel(double const *__restrict__ block_partials, int blocks, double *__restrict__ partial)
+  {
+    int k = threadIdx.x;
+    if (k >= 28)
+      return;
+
+    double v = 0;
+    for(int i = 0; i < blocks; ++i)
+      v += block_partials[(size_t)i * 28 + k];
+
+    partial[k] = v;
+  }
+
+  // ---- irradiance cube from SH9: data/lighting.inc:351-366, 371 ---------------------
+
+  __global__ void __launch_bounds__(256) sh9_irradiance_kernel(Sh9Coefficients sh, int w, int h, uint32_t *__restrict__ words, float *__restrict__ f32)
+  {
+    size_t total = (size_t)6 * w * h;
+    for(size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    {
+      int x = (int)(idx % w);
+      int y = (int)((idx / w) % h);
+      int face = (int)(idx / ((size_t)w * h));
+
+      float u = 2.0f * ((float)x + 0.5f) / (float)w - 1.0f;
+      float v = 2.0f * ((float)y + 0.5f) / (float)h - 1.0f;
+      float inv = rsqrtf(fmaf(u, u, fmaf(v, v, 1.0f)));
+      float a = u * inv, b = v * inv, c = inv;
+
+      float nx, ny, nz;
+      switch (face)
+      {
+        case 0: nx = c;  ny = b;  nz = a;  break;
+        case 1: nx = -c; ny = b;  nz = -a; break;
+        case 2: nx = a;  ny = -c; nz = -b; break;
+        case 3: nx = a;  ny = c;  nz = b;  break;
+        case 4: nx = a;  ny = b;  nz = -c; break;
+        default: nx = -a; ny = b; nz = c;  break;
+      }
+
+      float L[9];
+      L[0] = 3.141593f * 0.282095f;
+      L[1] = 2.094395f * 0.488603f * ny;
+      L[2] = 2.094395f * 0.488603f * nz;
+      L[3] = 2.094395f * 0.488603f * nx;
+      L[4] = 0.785398f * 1.092548f * nx * ny;
+      L[5] = 0.785398f * 1.092548f * ny * nz;
+      L[6] = 0.785398f * 0.315392f * (3.0f * nz * nz - 1.0f);
+      L[7] = 0.785398f * 1.092548f * nz * nx;
+      L[8] = 0.785398f * 0.546274f * (nx * nx - ny * ny);
+
+      float rgb[3] = { 0.0f, 0.0f, 0.0f };
+      #pragma unroll
+      for(int k = 0; k < 9; ++k)
+      {
+        rgb[0] = fmaf(L[k], sh.v[3*k + 0], rgb[0]);
+        rgb[1] = fmaf(L[k], sh.v[3*k + 1], rgb[1]);
+        rgb[2] = fmaf(L[k], sh.v[3*k + 2], rgb[2]);
+      }
+
+      rgb[0] = fmaxf(rgb[0], 0.0f); rgb[1] = fmaxf(rgb[1], 0.0f); rgb[2] = fmaxf(rgb[2], 0.0f);
+
+      if (words)
+        words[idx] = rgbe_encode(rgb[0], rgb[1], rgb[2]);
+
+      if (f32)
+      {
+        f32[3*idx + 0] = rgb[0]; f32[3*idx + 1] = rgb[1]; f32[3*idx + 2] = rgb[2];
+      }
+    }
+  }
+
+  // ---- launchers ----------------------------------------------------------------------
+
+  cudaError_t launch_sh9_weights(float *weights, int w, int h, cudaStream_t stream)
+  {
+    int total = w * h;
+    sh9_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(weights, w, h);
+    return cudaGetLastError();
+  }
+
+  int sh9_partial_blocks(int w, int h, int sm_count)
+  {
+    int pixels = w * h;
+    int blocks = (pixels + kSh9Threads - 1) / kSh9Threads;
+    int cap = sm_count * 8;
+    return blocks < cap ? (blocks < 1 ? 1 : blocks) : cap;
+  }
+
+  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, double *partial, cudaStream_t stream)
+  {
+    if (format == 0)
+      sh9_partial_kernel<0><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials);
+    else
+      sh9_partial_kernel<1><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials);
+
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess)
+      return err;
+
+    sh9_combine_kernel<<<1, 32, 0, stream>>>(block_partials, blocks, partial);
+
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_sh9_irradiance(Sh9Coefficients const &sh, int w, int h, uint32_t *words, float *f32, int sm_count, cudaStream_t stream)
+  {
+    size_t total = (size_t)6 * w * h;
+    size_t blocks = (total + 255) / 256;
+    size_t cap = (size_t)sm_count * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    if (grid < 1)
+      grid = 1;
+
+    sh9_irradiance_kernel<<<grid, 256, 0, stream>>>(sh, w, h, words, f32);
+
+    return cudaGetLastError();
+  }
+}

@@ -1,0 +1,142 @@
+/*
+ * libdatum_ibl_cuda — C ABI of the B200 (sm_100a) image-based-lighting bake.
+ *
+ * Drop-in boundary for the hot path of pniekamp/datum's tools/ibl.cpp.  The
+ * reference exposes four C++ free functions in tools/ibl.h:9-15; they take
+ * lml/std types, so they cannot be bound directly.  The host shim under
+ * datum_b200/host/ keeps those four signatures and forwards plain pointers and
+ * sizes to the entry points declared here.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     datum_ibl_last_error() then describes the failure (thread-local).
+ *     The reference functions return void and never fail; the C++ shim turns a
+ *     non-zero status into std::runtime_error, which assetbuilder's main()
+ *     already catches (tools/assetbuilder.cpp:968-982).
+ *   - there is NO CPU fallback: without a CUDA device datum_ibl_create fails.
+ *   - image layout is the reference's: level-major, then face (0 right, 1 left,
+ *     2 down, 3 up, 4 forward, 5 back — tools/ibl.cpp:21-26), then rows of
+ *     32-bit E5B9G9R9 "rgbe" words (src/math/color.h:154-172);
+ *     payload size = sum_i (w>>i)*(h>>i)*6*4 bytes (tools/assetpacker.cpp:488-497).
+ *   - a "row" below is a row of the 6*h face-major image of a level; row ranges
+ *     let several GPUs split one level.
+ *   - host pointers may be pageable; `*_device` entry points take device
+ *     pointers and are asynchronous on the context's stream unless stated.
+ *   - a context is bound to one device and must be used from one thread at a time.
+ */
+#ifndef DATUM_IBL_CUDA_H
+#define DATUM_IBL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct datum_ibl_ctx datum_ibl_ctx;
+
+/* texel formats of a level-0 image handed to the SH9 projection */
+#define DATUM_IBL_FORMAT_RGBE 0 /* uint32 E5B9G9R9 words, src/math/color.h:154-172 */
+#define DATUM_IBL_FORMAT_F32 1  /* RGBA fp32, the layout of HDRImage::bits (tools/hdr.h:24) */
+
+/* ---- lifetime ------------------------------------------------------------ */
+
+int datum_ibl_create(int device, datum_ibl_ctx **out);
+void datum_ibl_destroy(datum_ibl_ctx *ctx);
+const char *datum_ibl_last_error(void);
+
+/* the CUDA stream all asynchronous work of the context is issued on (cudaStream_t) */
+void *datum_ibl_stream(datum_ibl_ctx *ctx);
+int datum_ibl_synchronize(datum_ibl_ctx *ctx);
+
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t datum_ibl_launch_count(datum_ibl_ctx *ctx);
+
+/* prefilter kernel variant: 0 = automatic (default), 1.. = fixed tile shape (tuning/benchmarks) */
+int datum_ibl_set_prefilter_variant(datum_ibl_ctx *ctx, int variant);
+
+/* bytes of a `levels`-deep cube chain; tools/assetpacker.cpp:488-497 with layers = 6 */
+size_t datum_ibl_chain_bytes(int width, int height, int levels);
+
+/* ---- GGX prefilter chain: tools/ibl.cpp:242-279 ----------------------------- */
+
+/*
+ * Replaces image_buildmips_cube_ibl(width, height, levels, bits) (tools/ibl.h:9,
+ * tools/ibl.cpp:242).  `bits` is the caller's payload (tools/assetbuilder.cpp:439,
+ * 484): level 0 pre-filled, levels 1..levels-1 written in place.  Synchronous;
+ * includes the host->device copy of level 0 and the device->host copy of the
+ * computed levels.  `samples` is the reference's kSamples (tools/ibl.cpp:162: 1024).
+ */
+int datum_ibl_buildmips_cube_ibl(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, void *bits);
+
+/*
+ * Same chain on a device-resident payload.  `d_f32` (optional, may be NULL)
+ * receives the fp32 rgb triples handed to rgbe() at tools/ibl.cpp:269 for levels
+ * >= 1, level-major starting at level 1 (3 floats per texel).  Asynchronous.
+ */
+int datum_ibl_buildmips_cube_ibl_device(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, uint32_t *d_bits, float *d_f32);
+
+/*
+ * One level of the chain, for a slab of rows: the body of the level loop at
+ * tools/ibl.cpp:247-278.  `d_src` is the full (ws x hs x 6) source level, the
+ * destination level is (ws/2 x hs/2 x 6); rows [row_begin,row_end) of its
+ * 6*(hs/2) rows are written.  `d_dst_words` / `d_dst_f32` point at the START of
+ * the destination level (either may be NULL).  roughness = level/(levels-1)
+ * (tools/ibl.cpp:251).  Asynchronous.
+ */
+int datum_ibl_prefilter_level_device(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, int level, int levels, int samples, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32);
+
+/* ---- SH9 irradiance projection: data/project.comp:23-106 -------------------- */
+
+/*
+ * Partial sums of the projection over rows [row_begin,row_end) of a level-0
+ * cube: 27 unnormalised coefficients in [k][rgb] order (k as in
+ * data/project.comp:64-92) followed by the sum of solid-angle weights.
+ * `d_partial` = 28 doubles on the device; ranks sharing one probe all-reduce
+ * them before datum_ibl_sh9_finish.  Asynchronous.
+ */
+int datum_ibl_sh9_partial_device(datum_ibl_ctx *ctx, void const *d_level0, int format, int width, int height, int row_begin, int row_end, double *d_partial);
+
+/* data/project.comp:99-105: sh[k] = partial[k] * 4*pi / partial[27]; host arithmetic on 28 numbers */
+void datum_ibl_sh9_finish(double const *partial, float *sh);
+
+/*
+ * Whole projection of a host-resident level-0 cube; `sh` = float[9][3], the
+ * layout of `Irradiance` (src/renderer/envmap.h:112-115).  Synchronous.
+ */
+int datum_ibl_project_sh9(datum_ibl_ctx *ctx, void const *level0, int format, int width, int height, float *sh);
+
+/*
+ * Diffuse irradiance cube from SH9: E(n) of data/lighting.inc:351-366, 371
+ * (cosine-lobe band factors, max(.,0)) at the texel directions of
+ * tools/ibl.cpp:269.  Writes rgbe words and/or fp32 rgb triples (either may be
+ * NULL) for a (width x height x 6) cube on the host.  Synchronous.
+ */
+int datum_ibl_sh9_irradiance_cube(datum_ibl_ctx *ctx, float const *sh, int width, int height, uint32_t *words, float *f32);
+
+/* ---- 2D LUTs of tools/ibl.h ---------------------------------------------------- */
+
+/* Replaces image_pack_envbrdf(width, height, bits) (tools/ibl.h:13, tools/ibl.cpp:292-308); host buffer. */
+int datum_ibl_pack_envbrdf(datum_ibl_ctx *ctx, int width, int height, int samples, void *bits);
+
+/* Replaces image_pack_watercolor(...) (tools/ibl.h:15, tools/ibl.cpp:312-329); colours are float[3]; host buffer. */
+int datum_ibl_pack_watercolor(datum_ibl_ctx *ctx, float const *deepcolor, float const *shallowcolor, float depthscale, float const *fresnelcolor, float fresnelbias, float fresnelpower, int width, int height, void *bits);
+
+/* ---- measurement helpers -------------------------------------------------------- */
+
+/*
+ * FP32 FMA throughput of the device in TFLOP/s (2 flop per FMA), measured with
+ * a register-resident FFMA chain kernel timed with CUDA events; the denominator
+ * of the prefilter kernel's roofline fraction.
+ */
+int datum_ibl_measure_fp32_peak(datum_ibl_ctx *ctx, double *tflops);
+
+/* milliseconds the device spent in the prefilter kernels of the last chain call (CUDA events) */
+int datum_ibl_last_prefilter_ms(datum_ibl_ctx *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

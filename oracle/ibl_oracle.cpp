@@ -433,6 +433,61 @@ extern "C"
     convolve(roughness, V3{ dir[0], dir[1], dir[2] }, envmap, samples, rgb);
   }
 
+  // per-sample reflected directions and weights of tools/ibl.cpp:170-184 for one
+  // direction (debug aid for the parity tests): dirs[3*i..], ndotl[i] (<= 0 when rejected)
+  void oracle_trace_samples(float roughness, int samples, float const *dir, float *dirs, float *ndotl)
+  {
+    V3 N = { dir[0], dir[1], dir[2] };
+    for(int i = 0; i < samples; ++i)
+    {
+      V3 H = importancesample_ggx(float(i)/float(samples), radicalinverse_VdC(i), roughness * roughness, N);
+      V3 L = sub3(scale3(2 * dot3(N, H), H), N);
+      dirs[3*i + 0] = L.x; dirs[3*i + 1] = L.y; dirs[3*i + 2] = L.z;
+      ndotl[i] = clampf(dot3(N, L), 0.0f, 1.0f);
+    }
+  }
+
+  // Per output texel of a (wd x hd x 6) level: how many accepted samples point
+  // within `eps` (relative) of a cube-face boundary, i.e. have their two largest
+  // |components| closer than eps.  For those samples ibl.cpp:51-85 is decided by
+  // the last bit of fp32 rounding (exact ties are undefined behaviour there, and
+  // a quotient that rounds to 1.0 wraps to the opposite edge through fmod2,
+  // ibl.cpp:37-38), so the reference's own strict and -ffast-math builds disagree
+  // on them.  The parity tests hold texels with a non-zero count to a looser bound.
+  void oracle_edge_ambiguous_counts(int wd, int hd, float roughness, int samples, float eps, int32_t *counts, int threads)
+  {
+    Xform rot[6];
+    face_rotations(rot);
+
+    parallel_rows(0, 6 * hd, threads, [&](int row)
+    {
+      int face = row / hd;
+      int y = row % hd;
+
+      for(int x = 0; x < wd; ++x)
+      {
+        V3 N = texel_direction(rot[face], x, y, wd, hd);
+
+        int count = 0;
+        for(int i = 0; i < samples; ++i)
+        {
+          V3 H = importancesample_ggx(float(i)/float(samples), radicalinverse_VdC(i), roughness * roughness, N);
+          V3 L = sub3(scale3(2 * dot3(N, H), H), N);
+
+          if (clampf(dot3(N, L), 0.0f, 1.0f) > 0)
+          {
+            float m[3] = { std::abs(L.x), std::abs(L.y), std::abs(L.z) };
+            std::sort(m, m + 3);
+            if (m[1] >= m[2] * (1 - eps))
+              ++count;
+          }
+        }
+
+        counts[(size_t)row * wd + x] = count;
+      }
+    });
+  }
+
   // One level of tools/ibl.cpp:247-278: `src` is a (ws x hs x 6) rgbe level, the
   // output level is (ws/2 x hs/2 x 6).  Rows are numbered face-major over
   // 6*(hs/2); [row_begin,row_end) selects a slab.  `words` / `f32` (rgb triples,
@@ -671,6 +726,193 @@ extern "C"
         *dst++ = rgbe_encode(out[0], out[1], out[2]);
       }
     }
+  }
+
+  // ---- equirect HDR image -> cube level 0: tools/hdr.cpp:26-74, 173-359 ----------
+
+  namespace
+  {
+    struct Image
+    {
+      int width, height;
+      C4 const *bits; // HDRImage::bits, tools/hdr.h:24
+
+      C4 texel(int i, int j) const { return bits[(size_t)j * width + i]; }
+
+      // hdr.cpp:33-40 — bilinear with wrap in both directions
+      C4 sample(float tx, float ty) const
+      {
+        float i, j;
+        float u = std::modf(fmod2(tx * width - 0.5f, (float)width), &i);
+        float v = std::modf(fmod2(ty * height - 0.5f, (float)height), &j);
+
+        int i0 = (int)i, j0 = (int)j;
+        int i1 = (i0 + 1) % width, j1 = (j0 + 1) % height;
+
+        return lerp4(lerp4(texel(i0, j0), texel(i1, j0), u), lerp4(texel(i0, j1), texel(i1, j1), u), v);
+      }
+
+      // hdr.cpp:44-60 — box filter of bilinear taps over `area`; the fp32 loop
+      // counters are part of the behaviour (they decide the tap count)
+      C4 sample_area(float tx, float ty, float ax, float ay) const
+      {
+        C4 sum = { 0, 0, 0, 0 };
+        float totalweight = 0;
+
+        for(float y = ty - 0.5f*ay + 0.5f/height, yend = ty + 0.5f*ay; y < yend; y += 1.0f/height)
+        {
+          for(float x = tx - 0.5f*ax + 0.5f/width, xend = tx + 0.5f*ax; x < xend; x += 1.0f/width)
+          {
+            C4 c = sample(x, y);
+            sum.r += c.r; sum.g += c.g; sum.b += c.b; sum.a += c.a;
+
+            totalweight += 1.0f;
+          }
+        }
+
+        return { sum.r / totalweight, sum.g / totalweight, sum.b / totalweight, sum.a / totalweight };
+      }
+
+      // hdr.cpp:71-74 — equirect lookup (note the reference's `pi/2 +` offset on u)
+      C4 sample_dir(V3 const &d, float ax, float ay) const
+      {
+        return sample_area(kPi/2 + std::atan2(d.x, -d.z) / (2*kPi), std::acos(d.y) / kPi, ax, ay);
+      }
+    };
+
+    inline uint32_t blend3(uint32_t a, uint32_t b, uint32_t c)
+    {
+      C4 ca = rgbe_decode(a), cb = rgbe_decode(b), cc = rgbe_decode(c);
+      return rgbe_encode(0.3f * ca.r + 0.4f * cb.r + 0.3f * cc.r, 0.3f * ca.g + 0.4f * cb.g + 0.3f * cc.g, 0.3f * ca.b + 0.4f * cb.b + 0.3f * cc.b);
+    }
+  }
+
+  // tools/assetpacker.cpp:548-572 — 2x2 box mips of an rgbe image
+  void oracle_image_buildmips_rgbe(int width, int height, int layers, int levels, uint32_t *bits)
+  {
+    uint32_t *src = bits;
+    uint32_t *dst = src + (size_t)width * height * layers;
+
+    for(int level = 1; level < levels; ++level)
+    {
+      for(int layer = 0; layer < layers; ++layer)
+      {
+        for(int y = 0; y < (height >> 1); ++y)
+        {
+          for(int x = 0; x < (width >> 1); ++x)
+          {
+            C4 t[4] = { rgbe_decode(src[(2*y)*width + 2*x]), rgbe_decode(src[(2*y)*width + 2*x + 1]), rgbe_decode(src[(2*y + 1)*width + 2*x]), rgbe_decode(src[(2*y + 1)*width + 2*x + 1]) };
+
+            *dst++ = rgbe_encode((t[0].r + t[1].r + t[2].r + t[3].r) / 4, (t[0].g + t[1].g + t[2].g + t[3].g) / 4, (t[0].b + t[1].b + t[2].b + t[3].b) / 4);
+          }
+        }
+
+        src += (size_t)width * height;
+      }
+
+      width /= 2;
+      height /= 2;
+    }
+  }
+
+  // tools/hdr.cpp:173-318 — 0.3/0.4/0.3 blend across the twelve cube edges.  Each
+  // entry is one of the reference's twelve loops, in order: texel k of the loop
+  // reads a (inner) and b (edge) on the first face and c (edge), d (inner) on the
+  // second, then writes b' = blend(a,b,c) and c' = blend(b,c,d) with the OLD b, c.
+  // Later loops see the texels written by earlier ones (the corners).
+  void oracle_image_blend_edges(int width, int height, int levels, uint32_t *bits)
+  {
+    uint32_t *img = bits;
+
+    for(int level = 0; level < levels && width > 1 && height > 1; ++level)
+    {
+      int w = width, h = height;
+      auto tex = [=](int x, int y, int z) -> uint32_t& { return img[(size_t)z*w*h + (size_t)y*w + x]; };
+
+      auto run = [&](int count, auto coords)
+      {
+        for(int k = 0; k < count; ++k)
+        {
+          int c[4][3];
+          coords(k, c);
+          uint32_t a = tex(c[0][0], c[0][1], c[0][2]), b = tex(c[1][0], c[1][1], c[1][2]);
+          uint32_t cc = tex(c[2][0], c[2][1], c[2][2]), d = tex(c[3][0], c[3][1], c[3][2]);
+          tex(c[1][0], c[1][1], c[1][2]) = blend3(a, b, cc);
+          tex(c[2][0], c[2][1], c[2][2]) = blend3(b, cc, d);
+        }
+      };
+
+      // hdr.cpp:181-223: the four vertical seams around the horizon (right edge of fa -> left edge of fb)
+      int ring[4][2] = { { 4, 0 }, { 0, 5 }, { 5, 1 }, { 1, 4 } };
+      for(auto &seam : ring)
+      {
+        int fa = seam[0], fb = seam[1];
+        run(h, [=](int k, int c[4][3]) {
+          int v[4][3] = { { w - 2, k, fa }, { w - 1, k, fa }, { 0, k, fb }, { 1, k, fb } };
+          memcpy(c, v, sizeof(v));
+        });
+      }
+
+      // hdr.cpp:225-234: bottom row of front (4) -> top row of up (3)
+      run(w, [=](int k, int c[4][3]) { int v[4][3] = { { k, h - 2, 4 }, { k, h - 1, 4 }, { k, 0, 3 }, { k, 1, 3 } }; memcpy(c, v, sizeof(v)); });
+      // hdr.cpp:236-245: bottom row of up (3) -> bottom row of back (5), mirrored
+      run(w, [=](int k, int c[4][3]) { int v[4][3] = { { k, h - 2, 3 }, { k, h - 1, 3 }, { w - 1 - k, h - 1, 5 }, { w - 1 - k, h - 2, 5 } }; memcpy(c, v, sizeof(v)); });
+      // hdr.cpp:247-256: top row of back (5) -> top row of down (2), mirrored
+      run(w, [=](int k, int c[4][3]) { int v[4][3] = { { k, 1, 5 }, { k, 0, 5 }, { w - 1 - k, 0, 2 }, { w - 1 - k, 1, 2 } }; memcpy(c, v, sizeof(v)); });
+      // hdr.cpp:258-267: bottom row of down (2) -> top row of front (4)
+      run(w, [=](int k, int c[4][3]) { int v[4][3] = { { k, h - 2, 2 }, { k, h - 1, 2 }, { k, 0, 4 }, { k, 1, 4 } }; memcpy(c, v, sizeof(v)); });
+
+      int m = std::min(w, h);
+      // hdr.cpp:269-278: bottom row of right (0) -> right column of up (3)
+      run(m, [=](int k, int c[4][3]) { int v[4][3] = { { k, h - 2, 0 }, { k, h - 1, 0 }, { w - 1, k, 3 }, { w - 2, k, 3 } }; memcpy(c, v, sizeof(v)); });
+      // hdr.cpp:280-289: left column of up (3) -> bottom row of left (1), mirrored
+      run(m, [=](int k, int c[4][3]) { int v[4][3] = { { 1, k, 3 }, { 0, k, 3 }, { w - 1 - k, h - 1, 1 }, { w - 1 - k, h - 2, 1 } }; memcpy(c, v, sizeof(v)); });
+      // hdr.cpp:291-300: top row of left (1) -> left column of down (2)
+      run(m, [=](int k, int c[4][3]) { int v[4][3] = { { k, 1, 1 }, { k, 0, 1 }, { 0, k, 2 }, { 1, k, 2 } }; memcpy(c, v, sizeof(v)); });
+      // hdr.cpp:302-311: right column of down (2) -> top row of right (0), mirrored
+      run(m, [=](int k, int c[4][3]) { int v[4][3] = { { w - 2, k, 2 }, { w - 1, k, 2 }, { w - 1 - k, 0, 0 }, { w - 1 - k, 1, 0 } }; memcpy(c, v, sizeof(v)); });
+
+      img += (size_t)width * height * 6;
+
+      width /= 2;
+      height /= 2;
+    }
+  }
+
+  // tools/hdr.cpp:331-359 — `pixels` is imgw*imgh RGBA fp32
+  void oracle_image_pack_cube(int imgw, int imgh, float const *pixels, int width, int height, int levels, uint32_t *bits)
+  {
+    Image image = { imgw, imgh, reinterpret_cast<C4 const *>(pixels) };
+
+    Xform rot[6];
+    face_rotations(rot);
+
+    float ax = 1.0f / std::min(4 * width, imgw);
+    float ay = 1.0f / std::min(2 * height, imgh);
+
+    parallel_rows(0, 6 * height, 0, [&](int row)
+    {
+      int face = row / height;
+      int y = row % height;
+
+      for(int x = 0; x < width; ++x)
+      {
+        C4 c = image.sample_dir(texel_direction(rot[face], x, y, width, height), ax, ay);
+
+        bits[(size_t)row * width + x] = rgbe_encode(c.r, c.g, c.b);
+      }
+    });
+
+    // hdr.cpp:322-327
+    oracle_image_buildmips_rgbe(width, height, 6, levels, bits);
+    oracle_image_blend_edges(width, height, levels, bits);
+  }
+
+  // tools/ibl.cpp:283-288
+  void oracle_image_pack_cube_ibl(int imgw, int imgh, float const *pixels, int width, int height, int levels, int samples, uint32_t *bits, int threads)
+  {
+    oracle_image_pack_cube(imgw, imgh, pixels, width, height, 1, bits);
+    oracle_buildmips_cube_ibl(width, height, levels, samples, bits, nullptr, threads);
   }
 
   int oracle_max_threads() { return (int)std::max(1u, std::thread::hardware_concurrency()); }

@@ -1,0 +1,129 @@
+// TEST INFRASTRUCTURE — host build of the kernel's per-sample math.
+//
+// Compiles datum_b200/csrc/ibl_math.cuh and ibl_tables.cpp with g++ and runs
+// the same per-texel loop the CUDA prefilter kernel runs (table-driven reflected
+// direction, magic-add floor, quad-record addressing, biased-mantissa
+// accumulation), single-threaded and in table order.  tests/test_kernel_math_cpu.py
+// compares it with the oracle so that algorithmic mistakes are caught on the
+// CPU-only CI leg.  It is NOT a fallback: nothing under datum_b200/ builds,
+// links or loads it.
+
+#include "../../datum_b200/csrc/ibl_math.cuh"
+#include "../../datum_b200/csrc/ibl_tables.h"
+
+#include <cmath>
+#include <vector>
+
+using namespace ibl;
+
+extern "C" void emu_prefilter_level(uint32_t const *src, int ws, int hs, int level, int levels, int samples, uint32_t *words, float *f32)
+{
+  LevelSamples table = build_level_samples(level, levels, samples);
+  LevelGeom geom = make_level_geom(ws, hs);
+
+  const float kPi = 3.14159265358979323846f;
+  float angles[6] = { -kPi/2, kPi/2, -kPi/2, kPi/2, 0.0f, kPi };
+  int axes[6] = { 1, 1, 0, 0, 1, 1 };
+  Quatf quats[6];
+  for(int f = 0; f < 6; ++f)
+  {
+    float c = std::cos(angles[f]/2), s = std::sin(angles[f]/2);
+    quats[f] = Quatf{ c, axes[f] == 0 ? s : 0.0f, axes[f] == 1 ? s : 0.0f, 0.0f };
+  }
+
+  int wd = ws >> 1, hd = hs >> 1;
+  float norm = (float)((double)kAccScale / table.total_weight);
+
+  for(int face = 0; face < 6; ++face)
+  {
+    for(int y = 0; y < hd; ++y)
+    {
+      for(int x = 0; x < wd; ++x)
+      {
+        Vec3f N = texel_normal(quats[face], x, y, wd, hd);
+        Vec3f T, B;
+        tangent_frame(N, T, B);
+
+        float acc[4] = { 0, 0, 0, 0 };
+
+        for(int i = 0; i < table.accepted; ++i)
+        {
+          SampleEntry const &e = table.entries[i];
+          float Lx = e.lx * T.x + e.ly * B.x + e.lz * N.x;
+          float Ly = e.lx * T.y + e.ly * B.y + e.lz * N.y;
+          float Lz = e.lx * T.z + e.ly * B.z + e.lz * N.z;
+
+          float du, dv;
+          uint32_t idx = cube_footprint(geom, Lx, Ly, Lz, du, dv);
+
+          float w[4];
+          footprint_weights(du, dv, e.wh, e.lz, w);
+
+          accumulate_tap(src[idx], w[0], acc);
+          accumulate_tap(src[idx + 1], w[1], acc);
+          accumulate_tap(src[idx + ws], w[2], acc);
+          accumulate_tap(src[idx + ws + 1], w[3], acc);
+        }
+
+        float r = (acc[0] - acc[3]) * norm;
+        float g = (acc[1] - acc[3]) * norm;
+        float b = (acc[2] - acc[3]) * norm;
+
+        size_t o = ((size_t)face * hd + y) * wd + x;
+        if (words)
+          words[o] = rgbe_encode(r, g, b);
+        if (f32)
+        {
+          f32[3*o + 0] = r; f32[3*o + 1] = g; f32[3*o + 2] = b;
+        }
+      }
+    }
+  }
+}
+
+extern "C" uint32_t emu_rgbe_encode(float r, float g, float b) { return rgbe_encode(r, g, b); }
+extern "C" void emu_rgbe_decode(uint32_t w, float *rgb) { rgbe_decode(w, rgb[0], rgb[1], rgb[2]); }
+extern "C" void emu_texel_normal(int face, int x, int y, int wd, int hd, float *out)
+{
+  const float kPi = 3.14159265358979323846f;
+  float angles[6] = { -kPi/2, kPi/2, -kPi/2, kPi/2, 0.0f, kPi };
+  int axes[6] = { 1, 1, 0, 0, 1, 1 };
+  float c = std::cos(angles[face]/2), s = std::sin(angles[face]/2);
+  Quatf q = Quatf{ c, axes[face] == 0 ? s : 0.0f, axes[face] == 1 ? s : 0.0f, 0.0f };
+  Vec3f n = texel_normal(q, x, y, wd, hd);
+  out[0] = n.x; out[1] = n.y; out[2] = n.z;
+}
+
+// per-sample trace of one output texel (debug aid for the parity tests):
+// out[i] = {face, i, j, du, dv, weight} for table entry i
+extern "C" int emu_trace_texel(int ws, int hs, int level, int levels, int samples, int face, int x, int y, float *out, float *dirs)
+{
+  LevelSamples table = build_level_samples(level, levels, samples);
+  LevelGeom geom = make_level_geom(ws, hs);
+  const float kPi = 3.14159265358979323846f;
+  float angles[6] = { -kPi/2, kPi/2, -kPi/2, kPi/2, 0.0f, kPi };
+  int axes[6] = { 1, 1, 0, 0, 1, 1 };
+  float c = std::cos(angles[face]/2), s = std::sin(angles[face]/2);
+  Quatf q = Quatf{ c, axes[face] == 0 ? s : 0.0f, axes[face] == 1 ? s : 0.0f, 0.0f };
+  int wd = ws >> 1, hd = hs >> 1;
+  Vec3f N = texel_normal(q, x, y, wd, hd);
+  Vec3f T, B;
+  tangent_frame(N, T, B);
+  for(int i = 0; i < table.accepted; ++i)
+  {
+    SampleEntry const &e = table.entries[i];
+    float Lx = e.lx * T.x + e.ly * B.x + e.lz * N.x;
+    float Ly = e.lx * T.y + e.ly * B.y + e.lz * N.y;
+    float Lz = e.lx * T.z + e.ly * B.z + e.lz * N.z;
+    float du, dv;
+    uint32_t idx = cube_footprint(geom, Lx, Ly, Lz, du, dv);
+    out[6*i + 0] = (float)(idx / geom.face_size);
+    out[6*i + 1] = (float)((idx % geom.face_size) % ws);
+    out[6*i + 2] = (float)((idx % geom.face_size) / ws);
+    out[6*i + 3] = du + 0.5f;
+    out[6*i + 4] = dv + 0.5f;
+    out[6*i + 5] = e.lz;
+    dirs[3*i + 0] = Lx; dirs[3*i + 1] = Ly; dirs[3*i + 2] = Lz;
+  }
+  return table.accepted;
+}
