@@ -43,7 +43,8 @@ namespace
   {
     float4 *d_entries = nullptr;
     int count = 0;
-    float norm = 0; // kAccScale / total weight
+    int samples = 0; // the reference's kSamples this table was built for (accepted + rejected)
+    float norm = 0;  // kAccScale / total weight
   };
 
   template<typename T>
@@ -102,6 +103,13 @@ struct datum_ibl_ctx
   DeviceBuffer<double> sh_partials; // block partials + 28 result doubles
   DeviceBuffer<unsigned char> staging; // generic device staging for host entry points
   DeviceBuffer<float> sink;
+
+  // CUDA-event ring around the dominant kernel of every chain (the level-1
+  // prefilter launch): bench.py's live per-launch duration for the roofline
+  static const int kRing = 512;
+  std::vector<cudaEvent_t> ring_begin, ring_end;
+  int ring_used = 0;            // launches recorded since the last reset (may exceed kRing)
+  double ring_texel_samples = 0; // texel-samples of one recorded launch
 };
 
 namespace
@@ -149,6 +157,7 @@ namespace
 
         DeviceTable &t = built[level];
         t.count = host.accepted;
+        t.samples = samples;
         t.norm = (float)((double)ibl::kAccScale / host.total_weight);
 
         cudaError_t err = cudaMalloc(&t.d_entries, sizeof(float4) * (size_t)(t.count > 0 ? t.count : 1));
@@ -172,7 +181,7 @@ namespace
   }
 
   // one level on the context's stream: records of the source level, then the prefilter slab
-  int run_level(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32)
+  int run_level(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant = false)
   {
     int wd = ws >> 1, hd = hs >> 1;
 
@@ -207,12 +216,35 @@ namespace
     p.geom = ibl::make_level_geom(ws, hs);
     for(int f = 0; f < 6; ++f)
       p.quats[f] = ctx->quats[f];
+    p.masks = ibl::make_decode_masks();
     p.norm = table.norm;
+
+    int slot = -1;
+    if (record_dominant)
+    {
+      if (ctx->ring_begin.empty())
+      {
+        ctx->ring_begin.resize(datum_ibl_ctx::kRing);
+        ctx->ring_end.resize(datum_ibl_ctx::kRing);
+        for(int i = 0; i < datum_ibl_ctx::kRing; ++i)
+        {
+          cudaEventCreate(&ctx->ring_begin[i]);
+          cudaEventCreate(&ctx->ring_end[i]);
+        }
+      }
+      slot = ctx->ring_used % datum_ibl_ctx::kRing;
+      ctx->ring_used += 1;
+      ctx->ring_texel_samples = (double)(row_end - row_begin) * wd * (double)table.samples;
+      cudaEventRecord(ctx->ring_begin[slot], ctx->stream);
+    }
 
     err = ibl::launch_prefilter_level(p, ctx->prefilter_variant, ctx->sm_count, ctx->stream, nullptr);
     if (err != cudaSuccess)
       return fail_cuda("prefilter_level", err);
     ctx->launches += 1;
+
+    if (slot >= 0)
+      cudaEventRecord(ctx->ring_end[slot], ctx->stream);
 
     return 0;
   }
@@ -233,7 +265,7 @@ namespace
     {
       int hd = height >> 1;
 
-      if (run_level(ctx, src, width, height, (*tables)[level], 0, 6 * hd, dst, d_f32))
+      if (run_level(ctx, src, width, height, (*tables)[level], 0, 6 * hd, dst, d_f32, level == 1))
         return 1;
 
       size_t outcount = (size_t)(width >> 1) * hd * 6;
@@ -333,6 +365,11 @@ extern "C"
     ctx->staging.release();
     ctx->sink.release();
 
+    for(auto &e : ctx->ring_begin)
+      cudaEventDestroy(e);
+    for(auto &e : ctx->ring_end)
+      cudaEventDestroy(e);
+
     cudaEventDestroy(ctx->ev_begin);
     cudaEventDestroy(ctx->ev_end);
     cudaStreamDestroy(ctx->stream);
@@ -356,7 +393,7 @@ extern "C"
 
   int datum_ibl_set_prefilter_variant(datum_ibl_ctx *ctx, int variant)
   {
-    if (!ctx || variant < 0 || variant > 7)
+    if (!ctx || variant < 0 || variant > 9)
       return fail("datum_ibl_set_prefilter_variant: bad argument");
 
     ctx->prefilter_variant = variant;
@@ -449,6 +486,38 @@ extern "C"
       err = cudaEventElapsedTime(ms, ctx->ev_begin, ctx->ev_end);
 
     return err == cudaSuccess ? 0 : fail_cuda("cudaEventElapsedTime", err);
+  }
+
+  int datum_ibl_dominant_kernel_stats(datum_ibl_ctx *ctx, int reset, int *launches, double *avg_ms, double *texel_samples_per_launch)
+  {
+    if (!ctx || !launches || !avg_ms || !texel_samples_per_launch)
+      return fail("datum_ibl_dominant_kernel_stats: null argument");
+
+    DeviceGuard guard(ctx->device);
+
+    cudaError_t err = cudaStreamSynchronize(ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("datum_ibl_dominant_kernel_stats", err);
+
+    int n = ctx->ring_used < datum_ibl_ctx::kRing ? ctx->ring_used : datum_ibl_ctx::kRing;
+    double total = 0;
+    for(int i = 0; i < n; ++i)
+    {
+      float ms = 0;
+      err = cudaEventElapsedTime(&ms, ctx->ring_begin[i], ctx->ring_end[i]);
+      if (err != cudaSuccess)
+        return fail_cuda("cudaEventElapsedTime(ring)", err);
+      total += ms;
+    }
+
+    *launches = n;
+    *avg_ms = n ? total / n : 0.0;
+    *texel_samples_per_launch = ctx->ring_texel_samples;
+
+    if (reset)
+      ctx->ring_used = 0;
+
+    return 0;
   }
 
   // ---- SH9 ----------------------------------------------------------------------

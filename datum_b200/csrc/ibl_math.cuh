@@ -135,6 +135,7 @@ namespace ibl
     int ws, hs;          // source level size
     float hw, hh;        // 0.5*(ws-1), 0.5*(hs-1): align-corners scale of ibl.cpp:37-38
     float hwm, hhm;      // hw - 0.5, hh - 0.5
+    float inv_hw, inv_hh;
     uint32_t face_size;  // ws*hs records per face
     uint32_t bias;       // kMagicBits*(ws+1) mod 2^32, removed from the raw index
   };
@@ -145,6 +146,7 @@ namespace ibl
     g.ws = ws; g.hs = hs;
     g.hw = 0.5f * (float)(ws - 1); g.hh = 0.5f * (float)(hs - 1);
     g.hwm = g.hw - 0.5f; g.hhm = g.hh - 0.5f;
+    g.inv_hw = 1.0f / g.hw; g.inv_hh = 1.0f / g.hh;
     g.face_size = (uint32_t)ws * (uint32_t)hs;
     g.bias = kMagicBits * (uint32_t)(ws + 1);
     return g;
@@ -192,20 +194,102 @@ namespace ibl
     return f2u(mv) * (uint32_t)g.ws + f2u(mu) + face * g.face_size - g.bias;
   }
 
+  // ---- same-face fast path ----
+  //
+  // Face-local coordinates (a, b, m) of a world vector for cube face f, chosen so
+  // that on face f (m > 0 major) the uv of ibl.cpp:55-83 read u = .5 + .5 a/m,
+  // v = .5 + .5 b/m:
+  //   0 (+x): ( z, y,  x)   1 (-x): (-z, y, -x)   2 (-y): (x, -z, -y)
+  //   3 (+y): ( x, z,  y)   4 (-z): ( x, y, -z)   5 (+z): (-x, y,  z)
+  IBL_HD Vec3f to_face_local(int face, Vec3f v)
+  {
+    switch (face)
+    {
+      case 0: return Vec3f{ v.z, v.y, v.x };
+      case 1: return Vec3f{ -v.z, v.y, -v.x };
+      case 2: return Vec3f{ v.x, -v.z, -v.y };
+      case 3: return Vec3f{ v.x, v.z, v.y };
+      case 4: return Vec3f{ v.x, v.y, -v.z };
+      default: return Vec3f{ -v.x, v.y, v.z };
+    }
+  }
+
+  IBL_HD Vec3f from_face_local(int face, Vec3f l)
+  {
+    switch (face)
+    {
+      case 0: return Vec3f{ l.z, l.y, l.x };
+      case 1: return Vec3f{ -l.z, l.y, -l.x };
+      case 2: return Vec3f{ l.x, -l.z, -l.y };
+      case 3: return Vec3f{ l.x, l.z, l.y };
+      case 4: return Vec3f{ l.x, l.y, -l.z };
+      default: return Vec3f{ -l.x, l.y, l.z };
+    }
+  }
+
+  // A reflected direction makes the angle acos(lz) with the normal (lz = NdotL of
+  // the sample table).  It cannot leave the normal's own cube face while that
+  // angle is smaller than the normal's angular distance to the nearest of the
+  // four planes |a| = m, |b| = m bounding the face: sin(dist) = (m - |a|)/sqrt(2)
+  // for a unit normal.  Samples with lz above the returned threshold therefore
+  // need no face selection.  The margin absorbs the ~1e-7 non-orthonormality of
+  // the fp32 frame.
+  IBL_HD float same_face_threshold(Vec3f n_local)
+  {
+    float margin = n_local.z - fmaxf(fabsf(n_local.x), fabsf(n_local.y));
+    margin = fmaxf(margin, 0.0f);
+    return sqrtf(fmaxf(0.0f, 1.0f - 0.5f * margin * margin)) + 2e-6f;
+  }
+
+  // footprint on the texel's own face; la_s, lb_s are the a and b coordinates
+  // pre-scaled by 0.5*(ws-1) and 0.5*(hs-1); face_base = face*face_size - bias
+  IBL_HD uint32_t face_footprint(LevelGeom const &g, uint32_t face_base, float la_s, float lb_s, float lm, float &du, float &dv)
+  {
+    float r = rcp_fast(lm);
+    float fu = fmaf(la_s, r, g.hwm);
+    float fv = fmaf(lb_s, r, g.hhm);
+    float mu = fu + kMagic;
+    float mv = fv + kMagic;
+    du = fu - (mu - kMagic);
+    dv = fv - (mv - kMagic);
+
+    return f2u(mv) * (uint32_t)g.ws + f2u(mu) + face_base;
+  }
+
   // ---- packed-texel accumulation ----
   //
-  // A record holds the four rgbe words of a bilinear footprint.  Each 9-bit
-  // mantissa is dropped into the top of an fp32 mantissa under the word's own
-  // exponent field: bits = 0x20000000 | E<<23 | m<<14  ==  2^(E-63) * (1 + m/512),
-  // so no int->float conversion is needed; the "1 +" bias is accumulated once per
-  // tap (acc[3]) and removed at the end: sum_c - bias = sum of w * 2^(E-63) * m/512.
-  IBL_HD void accumulate_tap(uint32_t word, float w, float acc[4])
+  // A quad record holds the four rgbe words of a bilinear footprint, each rotated
+  // right by 4 bits (pack_record_word) so that the exponent field E sits at bits
+  // 23..27 and the blue mantissa at bits 14..22 — exactly where an fp32 keeps its
+  // low exponent bits and top mantissa bits.  Each 9-bit mantissa m is turned
+  // into the float
+  //     bits = 0x20000000 | E<<23 | m<<14   ==   2^(E-63) * (1 + m/512)
+  // with one or two logic ops and no int->float conversion; the "1 +" bias is
+  // accumulated once per tap (acc[3]) and removed at the end:
+  //     acc[c] - acc[3] = sum of w * 2^(E-63) * m_c/512.
+  IBL_HD uint32_t pack_record_word(uint32_t rgbe) { return (rgbe >> 4) | (rgbe << 28); }
+
+  struct DecodeMasks
   {
-    uint32_t sh = word >> 4;
-    uint32_t eb = (sh & 0x0F800000u) | 0x20000000u;
-    float fr = u2f(((word << 14) & 0x007FC000u) | eb);
-    float fg = u2f(((word << 5) & 0x007FC000u) | eb);
-    float fb = u2f((sh & 0x007FC000u) | eb);
+    uint32_t expo;     // 0x0F800000: E in place
+    uint32_t expmant;  // 0x0FFFC000: E and the in-place (blue) mantissa
+    uint32_t mant;     // 0x007FC000: a mantissa moved to bits 14..22
+    uint32_t bias;     // 0x20000000: exponent offset +64
+  };
+
+  IBL_HD DecodeMasks make_decode_masks()
+  {
+    DecodeMasks k;
+    k.expo = 0x0F800000u; k.expmant = 0x0FFFC000u; k.mant = 0x007FC000u; k.bias = 0x20000000u;
+    return k;
+  }
+
+  IBL_HD void accumulate_tap(DecodeMasks const &k, uint32_t word, float w, float acc[4])
+  {
+    uint32_t eb = (word & k.expo) | k.bias;
+    float fb = u2f((word & k.expmant) | k.bias);
+    float fg = u2f(((word << 9) & k.mant) | eb);
+    float fr = u2f((((word << 18) | (word >> 14)) & k.mant) | eb);
     acc[0] = fmaf(w, fr, acc[0]);
     acc[1] = fmaf(w, fg, acc[1]);
     acc[2] = fmaf(w, fb, acc[2]);

@@ -29,7 +29,9 @@ namespace ibl
   // rec[f][j][i] = { t(i,j), t(i+1,j), t(i,j+1), t(i+1,j+1) } of the source level,
   // neighbours clamped inside the face (the clamped ones are never addressed:
   // cube_footprint keeps i <= ws-2, j <= hs-2).  One 16-byte load then fetches
-  // the whole footprint of ibl.cpp:40.
+  // the whole footprint of ibl.cpp:40.  Words are stored rotated right by 4 bits
+  // (pack_record_word) so that exponent and blue mantissa already sit at their
+  // fp32 bit positions.
 
   __global__ void __launch_bounds__(256) build_quad_records_kernel(uint32_t const *__restrict__ src, uint4 *__restrict__ rec, int ws, int hs)
   {
@@ -42,10 +44,10 @@ namespace ibl
       size_t down = (j + 1 < hs) ? (size_t)ws : 0;
 
       uint4 r;
-      r.x = __ldg(src + idx);
-      r.y = __ldg(src + idx + right);
-      r.z = __ldg(src + idx + down);
-      r.w = __ldg(src + idx + down + right);
+      r.x = pack_record_word(__ldg(src + idx));
+      r.y = pack_record_word(__ldg(src + idx + right));
+      r.z = pack_record_word(__ldg(src + idx + down));
+      r.w = pack_record_word(__ldg(src + idx + down + right));
       rec[idx] = r;
     }
   }
@@ -76,7 +78,58 @@ namespace ibl
 
   // ---- the prefilter kernel ------------------------------------------------------
 
-  template<int TW, int TPT, int NW>
+  // per-texel state carried through a tile: the tangent frame as three rows
+  // (T, B, N), first in face-local coordinates for the same-face loop, then
+  // rotated back to world coordinates for the general loop
+  struct TexelState
+  {
+    Vec3f T, B, N;
+    uint32_t face_base; // face*face_size - bias
+    int face;
+  };
+
+  __device__ __forceinline__ void sample_general(PrefilterParams const &p, TexelState const &t, float4 e, float acc[4])
+  {
+    float Lx = fmaf(e.z, t.N.x, fmaf(e.y, t.B.x, e.x * t.T.x));
+    float Ly = fmaf(e.z, t.N.y, fmaf(e.y, t.B.y, e.x * t.T.y));
+    float Lz = fmaf(e.z, t.N.z, fmaf(e.y, t.B.z, e.x * t.T.z));
+
+    float du, dv;
+    uint32_t idx = cube_footprint(p.geom, Lx, Ly, Lz, du, dv);
+
+    const uint4 rec = __ldg(p.records + idx);
+
+    float w[4];
+    footprint_weights(du, dv, e.w, e.z, w);
+
+    accumulate_tap(p.masks, rec.x, w[0], acc);
+    accumulate_tap(p.masks, rec.y, w[1], acc);
+    accumulate_tap(p.masks, rec.z, w[2], acc);
+    accumulate_tap(p.masks, rec.w, w[3], acc);
+  }
+
+  // frame rows in face-local (a, b, m) coordinates, a and b pre-scaled
+  __device__ __forceinline__ void sample_same_face(PrefilterParams const &p, TexelState const &t, float4 e, float acc[4])
+  {
+    float la = fmaf(e.z, t.N.x, fmaf(e.y, t.B.x, e.x * t.T.x));
+    float lb = fmaf(e.z, t.N.y, fmaf(e.y, t.B.y, e.x * t.T.y));
+    float lm = fmaf(e.z, t.N.z, fmaf(e.y, t.B.z, e.x * t.T.z));
+
+    float du, dv;
+    uint32_t idx = face_footprint(p.geom, t.face_base, la, lb, lm, du, dv);
+
+    const uint4 rec = __ldg(p.records + idx);
+
+    float w[4];
+    footprint_weights(du, dv, e.w, e.z, w);
+
+    accumulate_tap(p.masks, rec.x, w[0], acc);
+    accumulate_tap(p.masks, rec.y, w[1], acc);
+    accumulate_tap(p.masks, rec.z, w[2], acc);
+    accumulate_tap(p.masks, rec.w, w[3], acc);
+  }
+
+  template<int TW, int TPT, int NW, int UNROLL>
   __global__ void __launch_bounds__(32 * NW) prefilter_level_kernel(PrefilterParams p)
   {
     extern __shared__ float4 smem[];
@@ -94,49 +147,89 @@ namespace ibl
 
     for(int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
     {
-      Vec3f N[TPT], T[TPT], B[TPT];
+      TexelState st[TPT];
       float acc[TPT][4];
+      float threshold = 0.0f;
 
       #pragma unroll
       for(int k = 0; k < TPT; ++k)
       {
         int x, row;
         bool valid = tile_texel<TW, TPT>(p, tile, lane, k, x, row);
-        if (!valid) { x = 0; row = p.row_begin; }
+
+        // lanes past the slab still walk the sample loops (their sums are dropped):
+        // park them on a face-centre texel, whose lobe stays inside its face
+        if (!valid) { x = p.wd >> 1; row = (p.row_begin / p.hd) * p.hd + (p.hd >> 1); }
 
         int face = row / p.hd;
         int y = row - face * p.hd;
 
-        N[k] = texel_normal(p.quats[face], x, y, p.wd, p.hd);
-        tangent_frame(N[k], T[k], B[k]);
+        Vec3f N = texel_normal(p.quats[face], x, y, p.wd, p.hd);
+        Vec3f T, B;
+        tangent_frame(N, T, B);
+
+        // face-local rows, a and b scaled to source texels (align-corners, ibl.cpp:37-38)
+        Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
+
+        threshold = fmaxf(threshold, same_face_threshold(Nl));
+
+        st[k].T = Vec3f{ Tl.x * p.geom.hw, Tl.y * p.geom.hh, Tl.z };
+        st[k].B = Vec3f{ Bl.x * p.geom.hw, Bl.y * p.geom.hh, Bl.z };
+        st[k].N = Vec3f{ Nl.x * p.geom.hw, Nl.y * p.geom.hh, Nl.z };
+        st[k].face = face;
+        st[k].face_base = (uint32_t)face * p.geom.face_size - p.geom.bias;
 
         acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
       }
 
-      #pragma unroll 2
-      for(int s = warp; s < p.table_count; s += NW)
+      // number of leading (smallest-angle) samples that stay on every texel's own face
+      threshold = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(threshold)));
+
+      int n_same = 0;
+      {
+        int lo = 0, hi = p.table_count; // first index with lz <= threshold (table sorted by decreasing lz)
+        while (lo < hi)
+        {
+          int mid = (lo + hi) >> 1;
+          if (s_table[mid].z > threshold)
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        n_same = lo;
+      }
+
+      int s = warp;
+
+      #pragma unroll UNROLL
+      for(; s < n_same; s += NW)
       {
         const float4 e = s_table[s];
 
         #pragma unroll
         for(int k = 0; k < TPT; ++k)
+          sample_same_face(p, st[k], e, acc[k]);
+      }
+
+      if (s < p.table_count)
+      {
+        // back to world coordinates for the samples that may cross a face edge
+        #pragma unroll
+        for(int k = 0; k < TPT; ++k)
         {
-          float Lx = fmaf(e.z, N[k].x, fmaf(e.y, B[k].x, e.x * T[k].x));
-          float Ly = fmaf(e.z, N[k].y, fmaf(e.y, B[k].y, e.x * T[k].y));
-          float Lz = fmaf(e.z, N[k].z, fmaf(e.y, B[k].z, e.x * T[k].z));
+          st[k].T = from_face_local(st[k].face, Vec3f{ st[k].T.x * p.geom.inv_hw, st[k].T.y * p.geom.inv_hh, st[k].T.z });
+          st[k].B = from_face_local(st[k].face, Vec3f{ st[k].B.x * p.geom.inv_hw, st[k].B.y * p.geom.inv_hh, st[k].B.z });
+          st[k].N = from_face_local(st[k].face, Vec3f{ st[k].N.x * p.geom.inv_hw, st[k].N.y * p.geom.inv_hh, st[k].N.z });
+        }
 
-          float du, dv;
-          uint32_t idx = cube_footprint(p.geom, Lx, Ly, Lz, du, dv);
+        #pragma unroll UNROLL
+        for(; s < p.table_count; s += NW)
+        {
+          const float4 e = s_table[s];
 
-          const uint4 rec = __ldg(p.records + idx);
-
-          float w[4];
-          footprint_weights(du, dv, e.w, e.z, w);
-
-          accumulate_tap(rec.x, w[0], acc[k]);
-          accumulate_tap(rec.y, w[1], acc[k]);
-          accumulate_tap(rec.z, w[2], acc[k]);
-          accumulate_tap(rec.w, w[3], acc[k]);
+          #pragma unroll
+          for(int k = 0; k < TPT; ++k)
+            sample_general(p, st[k], e, acc[k]);
         }
       }
 
@@ -194,11 +287,11 @@ namespace ibl
 
   namespace
   {
-    template<int TW, int TPT, int NW>
+    template<int TW, int TPT, int NW, int UNROLL>
     cudaError_t launch_variant(PrefilterParams p, int sm_count, cudaStream_t stream, int *launched_grid)
     {
       constexpr int TH = 32 / TW;
-      auto kernel = prefilter_level_kernel<TW, TPT, NW>;
+      auto kernel = prefilter_level_kernel<TW, TPT, NW, UNROLL>;
 
       int rows = p.row_end - p.row_begin;
       if (p.wd >= TW)
@@ -263,17 +356,19 @@ namespace ibl
     size_t texels = (size_t)rows * p.wd;
 
     if (variant == 0)
-      variant = (texels >= 64u * 148u * 4u) ? 1 : 2;
+      variant = (texels >= 32u * 148u * 8u) ? 6 : 2;
 
     switch (variant)
     {
-      case 1: return launch_variant<8, 2, 8>(p, sm_count, stream, launched_grid);
-      case 2: return launch_variant<8, 1, 16>(p, sm_count, stream, launched_grid);
-      case 3: return launch_variant<16, 2, 8>(p, sm_count, stream, launched_grid);
-      case 4: return launch_variant<32, 2, 8>(p, sm_count, stream, launched_grid);
-      case 5: return launch_variant<8, 2, 4>(p, sm_count, stream, launched_grid);
-      case 6: return launch_variant<8, 1, 8>(p, sm_count, stream, launched_grid);
-      case 7: return launch_variant<16, 1, 8>(p, sm_count, stream, launched_grid);
+      case 1: return launch_variant<8, 2, 8, 2>(p, sm_count, stream, launched_grid);
+      case 2: return launch_variant<8, 1, 16, 2>(p, sm_count, stream, launched_grid);
+      case 3: return launch_variant<16, 2, 8, 2>(p, sm_count, stream, launched_grid);
+      case 4: return launch_variant<8, 1, 8, 4>(p, sm_count, stream, launched_grid);
+      case 5: return launch_variant<8, 2, 4, 2>(p, sm_count, stream, launched_grid);
+      case 6: return launch_variant<8, 1, 8, 2>(p, sm_count, stream, launched_grid);
+      case 7: return launch_variant<16, 1, 8, 2>(p, sm_count, stream, launched_grid);
+      case 8: return launch_variant<8, 1, 4, 4>(p, sm_count, stream, launched_grid);
+      case 9: return launch_variant<8, 2, 8, 1>(p, sm_count, stream, launched_grid);
       default: return cudaErrorInvalidValue;
     }
   }

@@ -19,11 +19,12 @@ namespace ibl
     int row_begin, row_end;  // slab of the 6*hd face-major rows to compute
     LevelGeom geom;          // source level addressing constants
     Quatf quats[6];          // face rotations, tools/ibl.cpp:253-261
+    DecodeMasks masks;       // bit masks of accumulate_tap, passed as parameters so they live in registers
     float norm;              // kAccScale / total weight
     int tiles_x, tiles;      // filled by the launcher
   };
 
-  // variant 0 = pick by slab size; 1..7 = fixed <tile width, texels per lane, warps per tile>
+  // variant 0 = pick by slab size; 1..9 = fixed <tile width, texels per lane, warps per tile>
   cudaError_t launch_prefilter_level(PrefilterParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid);
 
   cudaError_t launch_build_quad_records(uint32_t const *src, uint4 *records, int ws, int hs, int sm_count, cudaStream_t stream);

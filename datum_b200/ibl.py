@@ -149,6 +149,12 @@ class IblContext:
         self._check(self._lib.datum_ibl_last_prefilter_ms(self._handle, ctypes.byref(ms)))
         return float(ms.value)
 
+    def dominant_kernel_stats(self, reset=True):
+        """(launches, mean ms, texel-samples per launch) of the level-1 prefilter launches since the last reset."""
+        n, ms, ts = ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
+        self._check(self._lib.datum_ibl_dominant_kernel_stats(self._handle, 1 if reset else 0, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(ts)))
+        return int(n.value), float(ms.value), float(ts.value)
+
     def measure_fp32_peak(self):
         """FP32 FMA throughput of the device in TFLOP/s (register-resident FFMA chains)."""
         tflops = ctypes.c_double()

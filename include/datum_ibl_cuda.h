@@ -132,6 +132,14 @@ int datum_ibl_pack_watercolor(datum_ibl_ctx *ctx, float const *deepcolor, float 
  */
 int datum_ibl_measure_fp32_peak(datum_ibl_ctx *ctx, double *tflops);
 
+/*
+ * CUDA-event timings of the dominant kernel (the level-1 prefilter launch of
+ * every chain since the last reset, at most 512): number of launches averaged,
+ * their mean duration, and the texel-samples one such launch processes.
+ * Synchronises the context's stream.
+ */
+int datum_ibl_dominant_kernel_stats(datum_ibl_ctx *ctx, int reset, int *launches, double *avg_ms, double *texel_samples_per_launch);
+
 /* milliseconds the device spent in the prefilter kernels of the last chain call (CUDA events) */
 int datum_ibl_last_prefilter_ms(datum_ibl_ctx *ctx, float *ms);
 

@@ -418,6 +418,15 @@ extern "C"
     out[0] = d.x; out[1] = d.y; out[2] = d.z;
   }
 
+  // src/math/transform.h:173-178 with the face rotations of tools/ibl.cpp:253-261
+  void oracle_face_rotate(int face, float const *v, float *out)
+  {
+    Xform rot[6];
+    face_rotations(rot);
+    V3 r = xapply(rot[face], V3{ v[0], v[1], v[2] });
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+  }
+
   // tools/ibl.cpp:43-88 on one direction (rgba out)
   void oracle_cube_sample(uint32_t const *level, int ws, int hs, float const *dir, float *rgba)
   {

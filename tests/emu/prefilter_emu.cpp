@@ -12,9 +12,12 @@
 #include "../../datum_b200/csrc/ibl_tables.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 using namespace ibl;
+
+static double g_fast_fraction = 0;
 
 extern "C" void emu_prefilter_level(uint32_t const *src, int ws, int hs, int level, int levels, int samples, uint32_t *words, float *f32)
 {
@@ -33,6 +36,19 @@ extern "C" void emu_prefilter_level(uint32_t const *src, int ws, int hs, int lev
 
   int wd = ws >> 1, hd = hs >> 1;
   float norm = (float)((double)kAccScale / table.total_weight);
+  DecodeMasks masks = make_decode_masks();
+
+  // quad records exactly as build_quad_records_kernel lays them out
+  struct Rec { uint32_t x, y, z, w; };
+  std::vector<Rec> records((size_t)6 * ws * hs);
+  for(size_t idx = 0; idx < records.size(); ++idx)
+  {
+    int i = (int)(idx % ws), j = (int)((idx / ws) % hs);
+    size_t right = (i + 1 < ws) ? 1 : 0, down = (j + 1 < hs) ? (size_t)ws : 0;
+    records[idx] = Rec{ pack_record_word(src[idx]), pack_record_word(src[idx + right]), pack_record_word(src[idx + down]), pack_record_word(src[idx + down + right]) };
+  }
+
+  long fast = 0, total = 0;
 
   for(int face = 0; face < 6; ++face)
   {
@@ -44,25 +60,56 @@ extern "C" void emu_prefilter_level(uint32_t const *src, int ws, int hs, int lev
         Vec3f T, B;
         tangent_frame(N, T, B);
 
+        Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
+        float threshold = getenv("EMU_NOFAST") ? 2.0f : same_face_threshold(Nl);
+
+        Vec3f Ts = { Tl.x * geom.hw, Tl.y * geom.hh, Tl.z };
+        Vec3f Bs = { Bl.x * geom.hw, Bl.y * geom.hh, Bl.z };
+        Vec3f Ns = { Nl.x * geom.hw, Nl.y * geom.hh, Nl.z };
+        uint32_t face_base = (uint32_t)face * geom.face_size - geom.bias;
+
+        // back to world exactly as the kernel does between its two loops
+        Vec3f Tw = from_face_local(face, Vec3f{ Ts.x * geom.inv_hw, Ts.y * geom.inv_hh, Ts.z });
+        Vec3f Bw = from_face_local(face, Vec3f{ Bs.x * geom.inv_hw, Bs.y * geom.inv_hh, Bs.z });
+        Vec3f Nw = from_face_local(face, Vec3f{ Ns.x * geom.inv_hw, Ns.y * geom.inv_hh, Ns.z });
+
         float acc[4] = { 0, 0, 0, 0 };
 
         for(int i = 0; i < table.accepted; ++i)
         {
           SampleEntry const &e = table.entries[i];
-          float Lx = e.lx * T.x + e.ly * B.x + e.lz * N.x;
-          float Ly = e.lx * T.y + e.ly * B.y + e.lz * N.y;
-          float Lz = e.lx * T.z + e.ly * B.z + e.lz * N.z;
 
           float du, dv;
-          uint32_t idx = cube_footprint(geom, Lx, Ly, Lz, du, dv);
+          uint32_t idx;
+
+          if (e.lz > threshold)
+          {
+            float la = fmaf(e.lz, Ns.x, fmaf(e.ly, Bs.x, e.lx * Ts.x));
+            float lb = fmaf(e.lz, Ns.y, fmaf(e.ly, Bs.y, e.lx * Ts.y));
+            float lm = fmaf(e.lz, Ns.z, fmaf(e.ly, Bs.z, e.lx * Ts.z));
+            idx = face_footprint(geom, face_base, la, lb, lm, du, dv);
+            ++fast;
+          }
+          else
+          {
+            float Lx = fmaf(e.lz, Nw.x, fmaf(e.ly, Bw.x, e.lx * Tw.x));
+            float Ly = fmaf(e.lz, Nw.y, fmaf(e.ly, Bw.y, e.lx * Tw.y));
+            float Lz = fmaf(e.lz, Nw.z, fmaf(e.ly, Bw.z, e.lx * Tw.z));
+            idx = cube_footprint(geom, Lx, Ly, Lz, du, dv);
+          }
+          ++total;
+
+          if (idx >= records.size())
+            __builtin_trap();
 
           float w[4];
           footprint_weights(du, dv, e.wh, e.lz, w);
 
-          accumulate_tap(src[idx], w[0], acc);
-          accumulate_tap(src[idx + 1], w[1], acc);
-          accumulate_tap(src[idx + ws], w[2], acc);
-          accumulate_tap(src[idx + ws + 1], w[3], acc);
+          Rec const &rec = records[idx];
+          accumulate_tap(masks, rec.x, w[0], acc);
+          accumulate_tap(masks, rec.y, w[1], acc);
+          accumulate_tap(masks, rec.z, w[2], acc);
+          accumulate_tap(masks, rec.w, w[3], acc);
         }
 
         float r = (acc[0] - acc[3]) * norm;
@@ -79,7 +126,11 @@ extern "C" void emu_prefilter_level(uint32_t const *src, int ws, int hs, int lev
       }
     }
   }
+
+  g_fast_fraction = total ? (double)fast / (double)total : 0.0;
 }
+
+extern "C" double emu_last_fast_fraction() { return g_fast_fraction; }
 
 extern "C" uint32_t emu_rgbe_encode(float r, float g, float b) { return rgbe_encode(r, g, b); }
 extern "C" void emu_rgbe_decode(uint32_t w, float *rgb) { rgbe_decode(w, rgb[0], rgb[1], rgb[2]); }
@@ -125,5 +176,18 @@ extern "C" int emu_trace_texel(int ws, int hs, int level, int levels, int sample
     out[6*i + 5] = e.lz;
     dirs[3*i + 0] = Lx; dirs[3*i + 1] = Ly; dirs[3*i + 2] = Lz;
   }
+  return table.accepted;
+}
+
+// the level's sample table as the kernel sees it: entries[4*i..] = (lx, ly, lz, wh), *total = sum of weights
+extern "C" int emu_table(int level, int levels, int samples, float *entries, double *total)
+{
+  LevelSamples table = build_level_samples(level, levels, samples);
+  for(int i = 0; i < table.accepted; ++i)
+  {
+    entries[4*i + 0] = table.entries[i].lx; entries[4*i + 1] = table.entries[i].ly;
+    entries[4*i + 2] = table.entries[i].lz; entries[4*i + 3] = table.entries[i].wh;
+  }
+  *total = table.total_weight;
   return table.accepted;
 }

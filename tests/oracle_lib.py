@@ -45,6 +45,10 @@ def oracle():
         lib.oracle_sh9_irradiance.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
         lib.oracle_pack_envbrdf.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_int]
         lib.oracle_pack_watercolor.argtypes = [c_void_p, c_void_p, c_float, c_void_p, c_float, c_float, c_int, c_int, c_void_p]
+        lib.oracle_face_rotate.argtypes = [c_int, c_void_p, c_void_p]
+        lib.oracle_image_pack_cube.argtypes = [c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
+        lib.oracle_image_pack_cube_ibl.argtypes = [c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int]
+        lib.oracle_image_blend_edges.argtypes = [c_int, c_int, c_int, c_void_p]
         lib.oracle_max_threads.restype = c_int
         _oracle = lib
     return _oracle
@@ -163,6 +167,24 @@ def pack_watercolor(deep, shallow, depthscale, fresnel, fresnelbias, fresnelpowe
     words = np.zeros(width * height, np.uint32)
     oracle().oracle_pack_watercolor(deep.ctypes.data, shallow.ctypes.data, depthscale, fresnel.ctypes.data, fresnelbias, fresnelpower, width, height, words.ctypes.data)
     return words
+
+
+def image_pack_cube(image, width, height, levels=1):
+    """tools/hdr.cpp:331-359 on an (H, W, 4) float32 equirect image."""
+    image = np.ascontiguousarray(image, dtype=np.float32)
+    total = sum(6 * (width >> i) * (height >> i) for i in range(levels))
+    bits = np.zeros(total, np.uint32)
+    oracle().oracle_image_pack_cube(image.shape[1], image.shape[0], image.ctypes.data, width, height, levels, bits.ctypes.data)
+    return bits
+
+
+def image_pack_cube_ibl(image, width, height, levels, samples=1024, threads=0):
+    """tools/ibl.cpp:283-288"""
+    image = np.ascontiguousarray(image, dtype=np.float32)
+    total = sum(6 * (width >> i) * (height >> i) for i in range(levels))
+    bits = np.zeros(total, np.uint32)
+    oracle().oracle_image_pack_cube_ibl(image.shape[1], image.shape[0], image.ctypes.data, width, height, levels, samples, bits.ctypes.data, threads)
+    return bits
 
 
 # ---- parity metrics (SURVEY.md §0 fact 4) ----------------------------------------

@@ -1,0 +1,181 @@
+"""GPU parity of the GGX prefilter chain (tools/ibl.cpp:242-279) through the C ABI."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import datum_b200
+import oracle_lib
+import parity
+from datum_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ibl_golden.npz"))
+DEV = "cuda:0"
+
+
+def run_chain_device(ctx, bits, w, h, levels, samples):
+    """Chain on the device; returns (words, f32 of levels >= 1)."""
+    offs = datum_b200.level_offsets(w, h, levels)
+    d_bits = torch.from_numpy(bits.view(np.int32).copy()).to(DEV)
+    d_f32 = torch.zeros(max(1, (offs[-1] - offs[1]) * 3), dtype=torch.float32, device=DEV)
+    ctx.buildmips_cube_ibl_device(w, h, levels, d_bits, samples, d_f32)
+    ctx.synchronize()
+    return d_bits.cpu().numpy().view(np.uint32), d_f32.cpu().numpy().reshape(-1, 3)
+
+
+@pytest.mark.parametrize("w,h,levels,samples,noise", [
+    (32, 32, 6, 1024, True),       # all levels down to 1x1 faces
+    (64, 64, 7, 1024, False),
+    (128, 128, 8, 1024, True),
+    (64, 64, 4, 4096, True),       # BASELINE config 3's sample count
+    (16, 16, 5, 16, True),         # tiny sample count
+    (24, 12, 3, 1024, True),       # non-square, not a power of two
+    (2, 2, 2, 1024, True),         # smallest legal chain: 2x2 -> 1x1
+])
+def test_every_level_matches_the_oracle_on_the_same_source(ctx, w, h, levels, samples, noise):
+    bits = synth.synthetic_chain(w, h, levels, probe=11, noise=noise, sun=False)
+    got, got_f32 = run_chain_device(ctx, bits, w, h, levels, samples)
+    offs = datum_b200.level_offsets(w, h, levels)
+    assert np.array_equal(got[: offs[1]], bits[: offs[1]])          # level 0 untouched
+    for level in range(1, levels):
+        ws, hs = w >> (level - 1), h >> (level - 1)
+        parity.check_level(got[offs[level]:offs[level + 1]], got_f32[offs[level] - offs[1]:offs[level + 1] - offs[1]],
+                           got[offs[level - 1]:offs[level]], ws, hs, level, levels, samples)
+
+
+def test_hdr_sun_input_stays_within_tolerance(ctx):
+    """A 2e4 sun disc next to 0.1-level sky: the ill-conditioned case."""
+    w, levels = 128, 8
+    bits = synth.synthetic_chain(w, w, levels, probe=2, noise=True, sun=True)
+    got, got_f32 = run_chain_device(ctx, bits, w, w, levels, 1024)
+    offs = datum_b200.level_offsets(w, w, levels)
+    for level in range(1, levels):
+        ws = w >> (level - 1)
+        parity.check_level(got[offs[level]:offs[level + 1]], got_f32[offs[level] - offs[1]:offs[level + 1] - offs[1]],
+                           got[offs[level - 1]:offs[level]], ws, ws, level, levels, 1024)
+
+
+@pytest.mark.parametrize("name,w,h,levels", [("chain16_noise", 16, 16, 5), ("chain16_smooth", 16, 16, 5), ("chain32_noise", 32, 32, 6), ("chain24x12", 24, 12, 3)])
+def test_own_chain_against_reference_golden(ctx, name, w, h, levels):
+    """Whole chain from the reference's level 0, compared with the words the unmodified
+    reference produced (each level here is built from OUR previous level, so one-code
+    differences propagate: the bound is on decoded values)."""
+    want = GOLDEN[name]
+    bits = np.zeros_like(want)
+    bits[: 6 * w * h] = GOLDEN[name + "_level0"]
+    ctx.image_buildmips_cube_ibl(w, h, levels, bits, 1024)            # host entry point, pageable numpy buffer
+    offs = datum_b200.level_offsets(w, h, levels)
+    assert np.array_equal(bits[: offs[1]], want[: offs[1]])
+    got = oracle_lib.rgbe_decode_array(bits[offs[1]:])[:, :3].astype(np.float64)
+    ref = oracle_lib.rgbe_decode_array(want[offs[1]:])[:, :3].astype(np.float64)
+    rel = np.abs(got - ref).max(axis=1) / np.maximum(ref.max(axis=1), 1e-30)
+    assert np.quantile(rel, 0.99) <= 4e-3      # one mantissa code of a 9-bit mantissa
+    assert rel.max() <= 1e-1                   # cube-edge samples, see parity.py
+    assert (bits[offs[1]:] == want[offs[1]:]).mean() >= 0.97
+
+
+def test_host_and_device_entry_points_agree(ctx):
+    w, levels = 64, 7
+    bits = synth.synthetic_chain(w, w, levels, probe=12)
+    dev_words, _ = run_chain_device(ctx, bits, w, w, levels, 1024)
+    host = bits.copy()
+    ctx.image_buildmips_cube_ibl(w, w, levels, host, 1024)
+    assert np.array_equal(host, dev_words)
+    pinned = torch.from_numpy(bits.view(np.int32).copy()).pin_memory()
+    ctx.image_buildmips_cube_ibl(w, w, levels, pinned, 1024)
+    assert np.array_equal(pinned.numpy().view(np.uint32), dev_words)
+    datum_b200.image_buildmips_cube_ibl(w, w, levels, host, 1024)     # reference-named free function
+    assert np.array_equal(host, dev_words)
+
+
+def test_row_slabs_reproduce_the_full_level(ctx):
+    """Multi-GPU sharding primitive: a level computed as row slabs is bit-identical to one launch."""
+    ws, levels, level = 64, 7, 2
+    src = synth.synthetic_chain(ws, ws, 1, probe=13)
+    d_src = torch.from_numpy(src.view(np.int32)).to(DEV)
+    wd = ws // 2
+    full = torch.zeros(6 * wd * wd, dtype=torch.int32, device=DEV)
+    ctx.prefilter_level_device(d_src, ws, ws, level, levels, 1024, 0, 6 * wd, full)
+    slabs = torch.zeros_like(full)
+    cuts = [0, 7, 8, 50, 97, 6 * wd]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ctx.prefilter_level_device(d_src, ws, ws, level, levels, 1024, a, b, slabs)
+    ctx.synchronize()
+    assert torch.equal(full, slabs)
+    # an empty slab is legal and writes nothing
+    ctx.prefilter_level_device(d_src, ws, ws, level, levels, 1024, 5, 5, slabs)
+    ctx.synchronize()
+    assert torch.equal(full, slabs)
+
+
+def test_kernel_variants_agree(ctx):
+    """Every tile shape / warp split computes the same level (fp32 sums differ only by
+    association order: compare through the packed-word criterion)."""
+    w, levels = 64, 6
+    bits = synth.synthetic_chain(w, w, levels, probe=14, sun=False)
+    base = None
+    try:
+        for variant in range(0, 10):
+            ctx.set_prefilter_variant(variant)
+            words, f32 = run_chain_device(ctx, bits, w, w, levels, 1024)
+            if base is None:
+                base = (words, f32)
+            else:
+                assert oracle_lib.relative_error(f32, base[1]).max() <= 2e-4   # one-code word flips of level L feed level L+1
+                assert (words == base[0]).mean() >= 0.995
+    finally:
+        ctx.set_prefilter_variant(0)
+
+
+def test_constant_environment_stays_constant_at_full_size(ctx):
+    """Size-independent property at BASELINE config 2 (512^2, 8 levels, 1024 spp)."""
+    w, levels = 512, 8
+    offs = datum_b200.level_offsets(w, w, levels)
+    word = oracle_lib.rgbe_encode_array(np.array([[3.0, 1.5, 0.75]], np.float32))[0]
+    bits = np.zeros(offs[-1], np.uint32)
+    bits[: offs[1]] = word
+    got, got_f32 = run_chain_device(ctx, bits, w, w, levels, 1024)
+    value = oracle_lib.rgbe_decode_array(np.array([word], np.uint32))[0, :3]
+    assert np.allclose(got_f32, value[None, :], rtol=2e-5)
+    assert oracle_lib.word_stats(got[offs[1]:], np.full(offs[-1] - offs[1], word, np.uint32))["max_code"] <= 1
+
+
+def test_linearity_in_radiance_at_full_size(ctx):
+    """Scaling level 0 by 4 (an exponent shift: exact in rgbe) scales level 1 by exactly 4."""
+    w, levels = 512, 2
+    bits = synth.synthetic_chain(w, w, levels, probe=15, sun=False)
+    scaled = bits.copy()
+    n0 = 6 * w * w
+    scaled[:n0] = bits[:n0] + np.uint32(2 << 27)
+    a, a_f32 = run_chain_device(ctx, bits, w, w, levels, 1024)
+    b, b_f32 = run_chain_device(ctx, scaled, w, w, levels, 1024)
+    assert np.array_equal(b_f32, a_f32 * np.float32(4.0))
+    assert np.array_equal(b[n0:], a[n0:] + np.uint32(2 << 27))
+
+
+def test_bad_arguments_raise(ctx):
+    bits = np.zeros(6 * (64 + 16 + 4 + 1), np.uint32)
+    with pytest.raises(datum_b200.IblError):
+        ctx.image_buildmips_cube_ibl(8, 8, 6, np.zeros(6 * 100, np.uint32))      # 8 >> 5 == 0: level without texels
+    with pytest.raises(datum_b200.IblError):
+        ctx.image_buildmips_cube_ibl(8, 8, 4, bits, samples=0)
+    with pytest.raises(ValueError):
+        ctx.image_buildmips_cube_ibl(8, 8, 4, np.zeros(10, np.uint32))             # payload too small
+    d = torch.zeros(6 * 64, dtype=torch.int32, device=DEV)
+    out = torch.zeros(6 * 16, dtype=torch.int32, device=DEV)
+    with pytest.raises(datum_b200.IblError):
+        ctx.prefilter_level_device(d, 8, 8, 1, 4, 1024, 0, 6 * 4 + 1, out)         # rows outside the level
+    with pytest.raises(datum_b200.IblError):
+        ctx.prefilter_level_device(d, 8, 8, 4, 4, 1024, 0, 6 * 4, out)             # level >= levels
+    ctx.image_buildmips_cube_ibl(8, 8, 1, bits)                                    # one level: nothing to do, like ibl.cpp:247
+
+
+def test_launch_counter_counts_our_kernels(ctx):
+    before = ctx.launch_count
+    bits = synth.synthetic_chain(16, 16, 5)
+    ctx.image_buildmips_cube_ibl(16, 16, 5, bits)
+    assert ctx.launch_count - before == 2 * 4      # per level: quad-record build + prefilter
