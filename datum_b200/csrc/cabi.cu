@@ -12,9 +12,11 @@
 #include "prefilter.h"
 #include "sh9.h"
 #include "luts.h"
+#include "resample.h"
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -641,6 +643,102 @@ extern "C"
       err = cudaStreamSynchronize(ctx->stream);
 
     return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_sh9_irradiance_cube", err);
+  }
+
+  // ---- equirect image -> cube (+ chain) -------------------------------------------------
+
+  static int pack_cube_to_device(datum_ibl_ctx *ctx, int imgwidth, int imgheight, float const *pixels, int width, int height, uint32_t *d_level0)
+  {
+    size_t image_bytes = (size_t)imgwidth * imgheight * sizeof(float4);
+
+    cudaError_t err = ctx->staging.reserve(image_bytes);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(staging)", err);
+
+    err = cudaMemcpyAsync(ctx->staging.ptr, pixels, image_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMemcpyAsync(image)", err);
+
+    ibl::ResampleParams p = {};
+    p.image = reinterpret_cast<float4 const *>(ctx->staging.ptr);
+    p.imgw = imgwidth;
+    p.imgh = imgheight;
+    p.width = width;
+    p.height = height;
+    // tools/hdr.cpp:345
+    p.area_x = 1.0f / (float)std::min(4 * width, imgwidth);
+    p.area_y = 1.0f / (float)std::min(2 * height, imgheight);
+    for(int f = 0; f < 6; ++f)
+      p.quats[f] = ctx->quats[f];
+    p.dst = d_level0;
+
+    err = ibl::launch_equirect_resample(p, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("equirect_resample", err);
+    ctx->launches += 1;
+
+    // tools/hdr.cpp:358 -> 322-327 with levels == 1: image_buildmips_rgbe does nothing, then the edge blend
+    err = ibl::launch_blend_edges(d_level0, width, height, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("blend_edges", err);
+    if (width > 1 && height > 1)
+      ctx->launches += 1;
+
+    return 0;
+  }
+
+  int datum_ibl_pack_cube(datum_ibl_ctx *ctx, int imgwidth, int imgheight, float const *pixels, int width, int height, void *bits)
+  {
+    if (!ctx || !pixels || !bits)
+      return fail("datum_ibl_pack_cube: null argument");
+    if (imgwidth < 1 || imgheight < 1 || width < 1 || height < 1)
+      return fail("datum_ibl_pack_cube: bad image or cube size");
+
+    DeviceGuard guard(ctx->device);
+
+    size_t level0 = (size_t)width * height * 6;
+
+    cudaError_t err = ctx->chain.reserve(level0);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(chain)", err);
+
+    if (pack_cube_to_device(ctx, imgwidth, imgheight, pixels, width, height, ctx->chain.ptr))
+      return 1;
+
+    err = cudaMemcpyAsync(bits, ctx->chain.ptr, level0 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess)
+      err = cudaStreamSynchronize(ctx->stream);
+
+    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_pack_cube", err);
+  }
+
+  int datum_ibl_pack_cube_ibl(datum_ibl_ctx *ctx, int imgwidth, int imgheight, float const *pixels, int width, int height, int levels, int samples, void *bits)
+  {
+    if (!ctx || !pixels || !bits)
+      return fail("datum_ibl_pack_cube_ibl: null argument");
+    if (imgwidth < 1 || imgheight < 1 || !valid_chain(width, height, levels) || samples < 1)
+      return fail("datum_ibl_pack_cube_ibl: bad image size or width/height/levels/samples");
+
+    DeviceGuard guard(ctx->device);
+
+    size_t words = datum_ibl_chain_bytes(width, height, levels) / sizeof(uint32_t);
+
+    cudaError_t err = ctx->chain.reserve(words);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(chain)", err);
+
+    // tools/ibl.cpp:285, 287
+    if (pack_cube_to_device(ctx, imgwidth, imgheight, pixels, width, height, ctx->chain.ptr))
+      return 1;
+
+    if (run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr))
+      return 1;
+
+    err = cudaMemcpyAsync(bits, ctx->chain.ptr, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess)
+      err = cudaStreamSynchronize(ctx->stream);
+
+    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_pack_cube_ibl", err);
   }
 
   // ---- LUTs -----------------------------------------------------------------------

@@ -1,0 +1,19 @@
+// datum_b200 host shim — the reference's tools/ibl.h:9-15, unchanged signatures.
+#pragma once
+
+#include "hdr.h"
+
+void image_buildmips_cube_ibl(int width, int height, int levels, void *bits);
+
+void image_pack_cube_ibl(HDRImage const &image, int width, int height, int levels, void *bits);
+
+void image_pack_envbrdf(int width, int height, void *bits);
+
+void image_pack_watercolor(lml::Color3 const &deepcolor, lml::Color3 const &shallowcolor, float depthscale, lml::Color3 const &fresnelcolor, float fresnelbias, float fresnelpower, int width, int height, void *bits);
+
+// Extensions with no counterpart in the reference's tools: the SH9
+// projection of data/project.comp as an offline step, `sh` = float[9][3] like
+// Irradiance::L (src/renderer/envmap.h:112-115); and the sample count of the bake
+// (tools/ibl.cpp:162 hard-codes 1024, which stays the default).
+void image_project_sh9_cube(int width, int height, void const *level0_rgbe, float *sh);
+void image_set_ibl_samples(int samples);

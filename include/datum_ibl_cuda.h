@@ -87,6 +87,25 @@ int datum_ibl_buildmips_cube_ibl_device(datum_ibl_ctx *ctx, int width, int heigh
  */
 int datum_ibl_prefilter_level_device(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, int level, int levels, int samples, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32);
 
+/* ---- equirectangular HDR image -> cube: tools/hdr.cpp:331-359, tools/ibl.cpp:283-288 ---- */
+
+/*
+ * Replaces image_pack_cube(image, width, height, 1, bits) (tools/hdr.h:39,
+ * tools/hdr.cpp:331) as the IBL path uses it (levels == 1): per cube texel the
+ * box-filtered bilinear equirect lookup of HDRImage::sample (hdr.cpp:44-74),
+ * rgbe(), then image_blend_edges (hdr.cpp:173-318).  `pixels` = HDRImage::bits,
+ * imgwidth*imgheight RGBA fp32 on the host; `bits` receives 6*width*height words.
+ * Synchronous.
+ */
+int datum_ibl_pack_cube(datum_ibl_ctx *ctx, int imgwidth, int imgheight, float const *pixels, int width, int height, void *bits);
+
+/*
+ * Replaces image_pack_cube_ibl(image, width, height, levels, bits) (tools/ibl.h:11,
+ * tools/ibl.cpp:283-288): the resample above, then the prefilter chain; the whole
+ * payload (level 0 included) is written to the host buffer `bits`.  Synchronous.
+ */
+int datum_ibl_pack_cube_ibl(datum_ibl_ctx *ctx, int imgwidth, int imgheight, float const *pixels, int width, int height, int levels, int samples, void *bits);
+
 /* ---- SH9 irradiance projection: data/project.comp:23-106 -------------------- */
 
 /*

@@ -214,3 +214,10 @@ def word_stats(got, want):
         "exp_mismatch": int((~same_exp).sum()),
         "max_value_rel": float(rel.max()) if len(rel) else 0.0,
     }
+
+
+def words_within_one_code(stats, min_identical=0.0):
+    """Packed-word criterion: same-exponent words at most one mantissa code apart; words whose
+    exponents differ (a value straddling a power of two) at most one code apart IN VALUE
+    (one code of a 9-bit mantissa is at most 1/256 of the value)."""
+    return stats["max_code"] <= 1 and stats["max_value_rel"] <= 4e-3 and stats["identical"] >= min_identical
