@@ -1,0 +1,160 @@
+"""Multi-GPU sharding of the IBL bake: one process per GPU over torch.distributed.
+
+The reference has no parallelism at all (the bake is a single-threaded triple
+loop, tools/ibl.cpp:263-272).  Three ways the path shards:
+
+  probes   a batch of independent environment maps: probe p -> rank p % world,
+           every rank runs the full chain (+ SH9) locally.  NO collective.
+  rows     ONE probe split across ranks: inside a level every output row is
+           independent, but level L reads ALL of level L-1 (tools/ibl.cpp:249,
+           274), so after each split level the ranks all-gather their row slabs
+           (NCCL over NVLink).  Tail levels are cheaper to compute redundantly
+           than to exchange.
+  sh9      the projection of one probe split by rows: 27 partial sums + the
+           weight sum, one all-reduce of 28 doubles, then project.comp:99-105.
+
+The collectives are issued on the bake context's own stream (CudaEngine.stream),
+so they are ordered with the kernels without host synchronisation.
+
+`engine` is the object that runs one level slab / one SH9 slab.  The product
+engine is CudaEngine (libdatum_ibl_cuda; raises without a GPU).  The CPU tests
+pass their own oracle-backed engine over the gloo backend to exercise this
+file's partitioning and exchange logic — that engine lives in tests/, not here.
+"""
+
+import contextlib
+
+import numpy as np
+
+from . import ibl
+
+
+def split_rows(rows, world):
+    """Contiguous, near-equal row ranges: [(begin, end)] * world (some may be empty)."""
+    base, extra = divmod(rows, world)
+    ranges, begin = [], 0
+    for r in range(world):
+        end = begin + base + (1 if r < extra else 0)
+        ranges.append((begin, end))
+        begin = end
+    return ranges
+
+
+def shard_probes(count, rank, world):
+    """Probe ids owned by `rank`: p % world == rank."""
+    return list(range(rank, count, world))
+
+
+def plan_single_probe(width, height, levels, world, min_split_texels=6 * 32 * 32):
+    """Per level >= 1: how the 6*(h>>L) destination rows are shared.
+
+    A level is split when its row count divides evenly by the world size (equal
+    slabs keep the exchange a plain all-gather) and it has more than
+    `min_split_texels` texels; otherwise every rank computes it whole."""
+    plan = []
+    for level in range(1, levels):
+        ws, hs = width >> (level - 1), height >> (level - 1)
+        wd, hd = ws >> 1, hs >> 1
+        rows = 6 * hd
+        split = world > 1 and rows % world == 0 and rows * wd > min_split_texels
+        plan.append({
+            "level": level, "ws": ws, "hs": hs, "wd": wd, "hd": hd, "rows": rows, "split": split,
+            "ranges": split_rows(rows, world) if split else [(0, rows)] * world,
+        })
+    return plan
+
+
+class CudaEngine:
+    """Runs slabs on one GPU through libdatum_ibl_cuda."""
+
+    def __init__(self, ctx):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.device = torch.device("cuda", ctx.device)
+
+    def stream(self):
+        return self.torch.cuda.stream(self.ctx.torch_stream())
+
+    def words_tensor(self, bits):
+        """uint32 payload (numpy) -> int32 device tensor"""
+        return self.torch.from_numpy(np.ascontiguousarray(bits).view(np.int32)).to(self.device)
+
+    def to_numpy_words(self, t):
+        self.ctx.synchronize()
+        return t.cpu().numpy().view(np.uint32)
+
+    def prefilter_level(self, src, ws, hs, level, levels, samples, row_begin, row_end, dst):
+        self.ctx.prefilter_level_device(src, ws, hs, level, levels, samples, row_begin, row_end, dst)
+
+    def sh9_partial(self, level0, fmt, width, height, row_begin, row_end):
+        out = self.torch.zeros(28, dtype=self.torch.float64, device=self.device)
+        self.ctx.sh9_partial_device(level0, fmt, width, height, row_begin, row_end, out)
+        return out
+
+    def sh9_finish(self, partial):
+        self.ctx.synchronize()
+        return self.ctx.sh9_finish(partial.cpu().numpy())
+
+
+def _world(group):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return dist, 0, 1
+    return dist, dist.get_rank(group), dist.get_world_size(group)
+
+
+def bake_single_probe(engine, chain, width, height, levels, samples=1024, group=None, min_split_texels=6 * 32 * 32):
+    """tools/ibl.cpp:242-279 for ONE probe shared by all ranks of `group`.
+
+    `chain` is the payload tensor on the engine's device (int32 words, level 0
+    filled on every rank); on return every rank holds the complete chain."""
+    dist, rank, world = _world(group)
+    offs = ibl.level_offsets(width, height, levels)
+    plan = plan_single_probe(width, height, levels, world, min_split_texels)
+
+    ctxmgr = engine.stream() if hasattr(engine, "stream") else contextlib.nullcontext()
+    with ctxmgr:
+        for step in plan:
+            level = step["level"]
+            src = chain[offs[level - 1]:offs[level]]
+            dst = chain[offs[level]:offs[level + 1]]
+            begin, end = step["ranges"][rank]
+
+            engine.prefilter_level(src, step["ws"], step["hs"], level, levels, samples, begin, end, dst)
+
+            if step["split"]:
+                # equal slabs: one all-gather straight into the level (the local slab is copied
+                # first so that input and output of the collective do not alias)
+                wd = step["wd"]
+                slab = dst[begin * wd:end * wd].clone()
+                dist.all_gather_into_tensor(dst, slab, group=group)
+
+    return chain
+
+
+def project_sh9_single_probe(engine, level0, fmt, width, height, group=None):
+    """data/project.comp:23-106 for ONE level-0 cube shared by all ranks: rows split,
+    28 partial sums all-reduced (the only collective), normalised on every rank."""
+    dist, rank, world = _world(group)
+    begin, end = split_rows(6 * height, world)[rank]
+
+    ctxmgr = engine.stream() if hasattr(engine, "stream") else contextlib.nullcontext()
+    with ctxmgr:
+        partial = engine.sh9_partial(level0, fmt, width, height, begin, end)
+        if world > 1:
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+
+    return engine.sh9_finish(partial)
+
+
+def bake_probe_batch(ctx, payloads, width, height, levels, samples=1024, group=None, with_sh9=False):
+    """A batch of independent probes (BASELINE config 4): this rank bakes payloads[p] for
+    p % world == rank, in place, through the reference-facing host entry point.  No
+    collective.  Returns {probe id: sh9 or None}."""
+    _, rank, world = _world(group)
+    results = {}
+    for p in shard_probes(len(payloads), rank, world):
+        ctx.image_buildmips_cube_ibl(width, height, levels, payloads[p], samples)
+        results[p] = ctx.project_sh9(payloads[p][: 6 * width * height], ibl.FORMAT_RGBE, width, height) if with_sh9 else None
+    return results
