@@ -395,7 +395,7 @@ extern "C"
 
   int datum_ibl_set_prefilter_variant(datum_ibl_ctx *ctx, int variant)
   {
-    if (!ctx || variant < 0 || variant > 9)
+    if (!ctx || variant < 0 || variant > 27)
       return fail("datum_ibl_set_prefilter_variant: bad argument");
 
     ctx->prefilter_variant = variant;
@@ -814,10 +814,26 @@ extern "C"
 
   // ---- measurement ------------------------------------------------------------------
 
+  static int measure_peak(datum_ibl_ctx *ctx, double *tflops, bool packed);
+
   int datum_ibl_measure_fp32_peak(datum_ibl_ctx *ctx, double *tflops)
   {
     if (!ctx || !tflops)
       return fail("datum_ibl_measure_fp32_peak: null argument");
+
+    return measure_peak(ctx, tflops, false);
+  }
+
+  int datum_ibl_measure_fp32x2_peak(datum_ibl_ctx *ctx, double *tflops)
+  {
+    if (!ctx || !tflops)
+      return fail("datum_ibl_measure_fp32x2_peak: null argument");
+
+    return measure_peak(ctx, tflops, true);
+  }
+
+  static int measure_peak(datum_ibl_ctx *ctx, double *tflops, bool packed)
+  {
 
     DeviceGuard guard(ctx->device);
 
@@ -836,7 +852,7 @@ extern "C"
     for(int rep = 0; rep < 5 && err == cudaSuccess; ++rep)
     {
       cudaEventRecord(e0, ctx->stream);
-      err = ibl::launch_fma_peak(ctx->sink.ptr, blocks, threads, iters, ctx->stream);
+      err = packed ? ibl::launch_fma2_peak(ctx->sink.ptr, blocks, threads, iters, ctx->stream) : ibl::launch_fma_peak(ctx->sink.ptr, blocks, threads, iters, ctx->stream);
       cudaEventRecord(e1, ctx->stream);
       ctx->launches += 1;
 

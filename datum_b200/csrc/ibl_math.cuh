@@ -269,27 +269,33 @@ namespace ibl
   //     acc[c] - acc[3] = sum of w * 2^(E-63) * m_c/512.
   IBL_HD uint32_t pack_record_word(uint32_t rgbe) { return (rgbe >> 4) | (rgbe << 28); }
 
+  // bit fields of a record word; the exponent offset (+64, bit 29) travels as a kernel
+  // PARAMETER so that each extraction is a single three-input LOP3 of the form
+  // (register & immediate) | register — with every constant immediate the compiler
+  // would need two logic ops, with every constant in a register three register reads.
+  constexpr uint32_t kMaskExpo = 0x0F800000u;     // E in place
+  constexpr uint32_t kMaskExpMant = 0x0FFFC000u;  // E and the in-place (blue) mantissa
+  constexpr uint32_t kMaskMant = 0x007FC000u;     // a mantissa moved to bits 14..22
+  constexpr uint32_t kExpBias = 0x20000000u;      // exponent offset +64
+
   struct DecodeMasks
   {
-    uint32_t expo;     // 0x0F800000: E in place
-    uint32_t expmant;  // 0x0FFFC000: E and the in-place (blue) mantissa
-    uint32_t mant;     // 0x007FC000: a mantissa moved to bits 14..22
-    uint32_t bias;     // 0x20000000: exponent offset +64
+    uint32_t bias; // kExpBias
   };
 
   IBL_HD DecodeMasks make_decode_masks()
   {
     DecodeMasks k;
-    k.expo = 0x0F800000u; k.expmant = 0x0FFFC000u; k.mant = 0x007FC000u; k.bias = 0x20000000u;
+    k.bias = kExpBias;
     return k;
   }
 
   IBL_HD void accumulate_tap(DecodeMasks const &k, uint32_t word, float w, float acc[4])
   {
-    uint32_t eb = (word & k.expo) | k.bias;
-    float fb = u2f((word & k.expmant) | k.bias);
-    float fg = u2f(((word << 9) & k.mant) | eb);
-    float fr = u2f((((word << 18) | (word >> 14)) & k.mant) | eb);
+    uint32_t eb = (word & kMaskExpo) | k.bias;
+    float fb = u2f((word & kMaskExpMant) | k.bias);
+    float fg = u2f(((word << 9) & kMaskMant) | eb);
+    float fr = u2f((((word << 18) | (word >> 14)) & kMaskMant) | eb);
     acc[0] = fmaf(w, fr, acc[0]);
     acc[1] = fmaf(w, fg, acc[1]);
     acc[2] = fmaf(w, fb, acc[2]);

@@ -180,6 +180,45 @@ namespace ibl
       sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
   }
 
+  // the same chains with the packed two-wide fma.rn.f32x2 (FFMA2) of sm_100: 8 chains of float2
+  __global__ void __launch_bounds__(256) fma2_peak_kernel(float *sink, int iters)
+  {
+    unsigned long long x[8];
+    #pragma unroll
+    for(int k = 0; k < 8; ++k)
+    {
+      float2 v = make_float2((float)(threadIdx.x + k) * 1e-3f, (float)(threadIdx.x + k + 8) * 1e-3f);
+      x[k] = *reinterpret_cast<unsigned long long*>(&v);
+    }
+
+    float2 mv = make_float2(0.999f, 0.999f), av = make_float2(1e-4f, 1e-4f);
+    unsigned long long m = *reinterpret_cast<unsigned long long*>(&mv), a = *reinterpret_cast<unsigned long long*>(&av);
+
+    for(int i = 0; i < iters; ++i)
+    {
+      #pragma unroll
+      for(int k = 0; k < 8; ++k)
+        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[k]) : "l"(m), "l"(a));
+    }
+
+    float s = 0.0f;
+    #pragma unroll
+    for(int k = 0; k < 8; ++k)
+    {
+      float2 v = *reinterpret_cast<float2*>(&x[k]);
+      s += v.x + v.y;
+    }
+
+    if (s == 123.456f)
+      sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  }
+
+  cudaError_t launch_fma2_peak(float *sink, int blocks, int threads, int iters, cudaStream_t stream)
+  {
+    fma2_peak_kernel<<<blocks, threads, 0, stream>>>(sink, iters);
+    return cudaGetLastError();
+  }
+
   cudaError_t launch_envbrdf(int width, int height, int samples, uint32_t *words, float *f32, cudaStream_t stream)
   {
     int total = width * height;

@@ -20,4 +20,7 @@ namespace ibl
 
   // register-resident FFMA chains: `iters` x 16 FMAs per thread, for the FP32 roofline denominator
   cudaError_t launch_fma_peak(float *sink, int blocks, int threads, int iters, cudaStream_t stream);
+
+  // same flop count per thread issued as 8 two-wide fma.rn.f32x2 (FFMA2) chains
+  cudaError_t launch_fma2_peak(float *sink, int blocks, int threads, int iters, cudaStream_t stream);
 }

@@ -88,49 +88,337 @@ namespace ibl
     int face;
   };
 
-  __device__ __forceinline__ void sample_general(PrefilterParams const &p, TexelState const &t, float4 e, float acc[4])
+  // One sample of one texel, split in two halves so the gather of sample s+1 can be
+  // issued before the arithmetic on sample s (software pipelining: the 16-byte record
+  // load is the only long-latency operation of the loop).
+  struct Fetched
+  {
+    uint4 rec;     // the 2x2 footprint
+    float du, dv;  // bilinear fractions - 0.5
+    float nl, wh;  // NdotL and 0.5*NdotL of the sample
+  };
+
+  __device__ __forceinline__ Fetched fetch_general(PrefilterParams const &p, TexelState const &t, float4 e)
   {
     float Lx = fmaf(e.z, t.N.x, fmaf(e.y, t.B.x, e.x * t.T.x));
     float Ly = fmaf(e.z, t.N.y, fmaf(e.y, t.B.y, e.x * t.T.y));
     float Lz = fmaf(e.z, t.N.z, fmaf(e.y, t.B.z, e.x * t.T.z));
 
-    float du, dv;
-    uint32_t idx = cube_footprint(p.geom, Lx, Ly, Lz, du, dv);
-
-    const uint4 rec = __ldg(p.records + idx);
-
-    float w[4];
-    footprint_weights(du, dv, e.w, e.z, w);
-
-    accumulate_tap(p.masks, rec.x, w[0], acc);
-    accumulate_tap(p.masks, rec.y, w[1], acc);
-    accumulate_tap(p.masks, rec.z, w[2], acc);
-    accumulate_tap(p.masks, rec.w, w[3], acc);
+    Fetched f;
+    uint32_t idx = cube_footprint(p.geom, Lx, Ly, Lz, f.du, f.dv);
+    f.rec = __ldg(p.records + idx);
+    f.nl = e.z;
+    f.wh = e.w;
+    return f;
   }
 
   // frame rows in face-local (a, b, m) coordinates, a and b pre-scaled
-  __device__ __forceinline__ void sample_same_face(PrefilterParams const &p, TexelState const &t, float4 e, float acc[4])
+  __device__ __forceinline__ Fetched fetch_same_face(PrefilterParams const &p, TexelState const &t, float4 e)
   {
     float la = fmaf(e.z, t.N.x, fmaf(e.y, t.B.x, e.x * t.T.x));
     float lb = fmaf(e.z, t.N.y, fmaf(e.y, t.B.y, e.x * t.T.y));
     float lm = fmaf(e.z, t.N.z, fmaf(e.y, t.B.z, e.x * t.T.z));
 
-    float du, dv;
-    uint32_t idx = face_footprint(p.geom, t.face_base, la, lb, lm, du, dv);
-
-    const uint4 rec = __ldg(p.records + idx);
-
-    float w[4];
-    footprint_weights(du, dv, e.w, e.z, w);
-
-    accumulate_tap(p.masks, rec.x, w[0], acc);
-    accumulate_tap(p.masks, rec.y, w[1], acc);
-    accumulate_tap(p.masks, rec.z, w[2], acc);
-    accumulate_tap(p.masks, rec.w, w[3], acc);
+    Fetched f;
+    uint32_t idx = face_footprint(p.geom, t.face_base, la, lb, lm, f.du, f.dv);
+    f.rec = __ldg(p.records + idx);
+    f.nl = e.z;
+    f.wh = e.w;
+    return f;
   }
 
-  template<int TW, int TPT, int NW, int UNROLL>
-  __global__ void __launch_bounds__(32 * NW) prefilter_level_kernel(PrefilterParams p)
+  __device__ __forceinline__ void consume(PrefilterParams const &p, Fetched const &f, float acc[4])
+  {
+    float w[4];
+    footprint_weights(f.du, f.dv, f.wh, f.nl, w);
+
+    accumulate_tap(p.masks, f.rec.x, w[0], acc);
+    accumulate_tap(p.masks, f.rec.y, w[1], acc);
+    accumulate_tap(p.masks, f.rec.z, w[2], acc);
+    accumulate_tap(p.masks, f.rec.w, w[3], acc);
+  }
+
+  // ---- packed two-wide fp32 (fma.rn.f32x2 -> SASS FFMA2/FMUL2/FADD2, new on sm_100) ----
+  //
+  // One FFMA2 does two FMAs for one issue slot (same lane throughput as two
+  // FFMAs: measured 73 vs 72 TFLOP/s), and the hardware takes a plain fp32
+  // register as a broadcast operand, so pairing costs no moves.  The loop is
+  // bound by issue slots and the half-rate ALU pipe, not by FMA lanes; packing
+  // the (a, b) face coordinates, the bilinear weights and the (r, g) / (b, bias)
+  // accumulators removes ~18 of ~74 issue slots per sample.  Every element goes
+  // through the same round-to-nearest operations as the scalar form in
+  // ibl_math.cuh, so the results are bit-identical to it.
+  typedef unsigned long long f32x2;
+
+  __device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+  __device__ __forceinline__ void unpack2(f32x2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
+  __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+  __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+  __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+  __device__ __forceinline__ f32x2 bcast2(float v) { return pack2(v, v); }
+
+  // face_footprint of ibl_math.cuh with the (a, b) coordinates carried as a pair
+  __device__ __forceinline__ Fetched fetch_same_face_packed(PrefilterParams const &p, TexelState const &t, float4 e)
+  {
+    f32x2 lab = mul2(bcast2(e.x), pack2(t.T.x, t.T.y));
+    lab = fma2(bcast2(e.y), pack2(t.B.x, t.B.y), lab);
+    lab = fma2(bcast2(e.z), pack2(t.N.x, t.N.y), lab);
+    float lm = fmaf(e.z, t.N.z, fmaf(e.y, t.B.z, e.x * t.T.z));
+
+    float r = rcp_fast(lm);
+    f32x2 f = fma2(lab, bcast2(r), pack2(p.geom.hwm, p.geom.hhm));
+    f32x2 m = add2(f, bcast2(kMagic));
+    f32x2 fi = add2(m, bcast2(-kMagic));
+    f32x2 d = fma2(fi, bcast2(-1.0f), f);
+
+    float mu, mv;
+    unpack2(m, mu, mv);
+
+    Fetched out;
+    unpack2(d, out.du, out.dv);
+    uint32_t idx = f2u(mv) * (uint32_t)p.geom.ws + f2u(mu) + t.face_base;
+    out.rec = __ldg(p.records + idx);
+    out.nl = e.z;
+    out.wh = e.w;
+    return out;
+  }
+
+  __device__ __forceinline__ Fetched fetch_same_face_packed_noload(PrefilterParams const &p, TexelState const &t, float4 e)
+  {
+    f32x2 lab = mul2(bcast2(e.x), pack2(t.T.x, t.T.y));
+    lab = fma2(bcast2(e.y), pack2(t.B.x, t.B.y), lab);
+    lab = fma2(bcast2(e.z), pack2(t.N.x, t.N.y), lab);
+    float lm = fmaf(e.z, t.N.z, fmaf(e.y, t.B.z, e.x * t.T.z));
+    float r = rcp_fast(lm);
+    f32x2 f = fma2(lab, bcast2(r), pack2(p.geom.hwm, p.geom.hhm));
+    f32x2 m = add2(f, bcast2(kMagic));
+    f32x2 fi = add2(m, bcast2(-kMagic));
+    f32x2 d = fma2(fi, bcast2(-1.0f), f);
+    float mu, mv;
+    unpack2(m, mu, mv);
+    Fetched out;
+    unpack2(d, out.du, out.dv);
+    uint32_t idx = f2u(mv) * (uint32_t)p.geom.ws + f2u(mu) + t.face_base;
+    out.rec = make_uint4(idx * 2654435761u, idx * 40503u, idx ^ 0x12345678u, idx + 77u);
+    out.nl = e.z;
+    out.wh = e.w;
+    return out;
+  }
+
+  // footprint_weights + accumulate_tap of ibl_math.cuh on (r, g) and (b, bias) accumulator pairs
+  __device__ __forceinline__ void accumulate_tap_packed(DecodeMasks const &k, uint32_t word, float w, f32x2 &acc_rg, f32x2 &acc_bs)
+  {
+    uint32_t eb = (word & kMaskExpo) | k.bias;
+    uint32_t fb = (word & kMaskExpMant) | k.bias;
+    uint32_t fg = ((word << 9) & kMaskMant) | eb;
+    uint32_t fr = (((word << 18) | (word >> 14)) & kMaskMant) | eb;
+    f32x2 wv = bcast2(w);
+    acc_rg = fma2(pack2(u2f(fr), u2f(fg)), wv, acc_rg);
+    acc_bs = fma2(pack2(u2f(fb), u2f(eb)), wv, acc_bs);
+  }
+
+  __device__ __forceinline__ void consume_packed(PrefilterParams const &p, Fetched const &f, f32x2 &acc_rg, f32x2 &acc_bs)
+  {
+    float u0 = 0.5f - f.du, u1 = 0.5f + f.du;
+    float v0 = fmaf(-f.dv, f.nl, f.wh), v1 = fmaf(f.dv, f.nl, f.wh);
+
+    f32x2 u = pack2(u0, u1);
+    float w00, w10, w01, w11;
+    unpack2(mul2(u, bcast2(v0)), w00, w10);
+    unpack2(mul2(u, bcast2(v1)), w01, w11);
+
+    accumulate_tap_packed(p.masks, f.rec.x, w00, acc_rg, acc_bs);
+    accumulate_tap_packed(p.masks, f.rec.y, w10, acc_rg, acc_bs);
+    accumulate_tap_packed(p.masks, f.rec.z, w01, acc_rg, acc_bs);
+    accumulate_tap_packed(p.masks, f.rec.w, w11, acc_rg, acc_bs);
+  }
+
+  // ---- the kernel with packed arithmetic -------------------------------------------
+  // Same tiling, tables, same-face split and reduction as prefilter_level_kernel below.
+
+  // ABLATE (tuning experiments only, results are wrong when non-zero): 1 = no gather (record
+  // synthesised from the index), 2 = gather but trivial arithmetic on it, 3 = no geometry
+  template<int TW, int TPT, int NW, int UNROLL, int MINB, int ABLATE = 0>
+  __global__ void __launch_bounds__(32 * NW, MINB) prefilter_level_packed_kernel(PrefilterParams p)
+  {
+    extern __shared__ float4 smem[];
+    float4 *s_table = smem;
+    float *s_red = reinterpret_cast<float*>(smem + p.table_count);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    for(int i = tid; i < p.table_count; i += 32 * NW)
+      s_table[i] = __ldg(p.table + i);
+
+    __syncthreads();
+
+    for(int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
+    {
+      TexelState st[TPT];
+      f32x2 acc_rg[TPT], acc_bs[TPT];
+      float threshold = 0.0f;
+
+      #pragma unroll
+      for(int k = 0; k < TPT; ++k)
+      {
+        int x, row;
+        bool valid = tile_texel<TW, TPT>(p, tile, lane, k, x, row);
+
+        if (!valid) { x = p.wd >> 1; row = (p.row_begin / p.hd) * p.hd + (p.hd >> 1); }
+
+        int face = row / p.hd;
+        int y = row - face * p.hd;
+
+        Vec3f N = texel_normal(p.quats[face], x, y, p.wd, p.hd);
+        Vec3f T, B;
+        tangent_frame(N, T, B);
+
+        Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
+
+        threshold = fmaxf(threshold, same_face_threshold(Nl));
+
+        st[k].T = Vec3f{ Tl.x * p.geom.hw, Tl.y * p.geom.hh, Tl.z };
+        st[k].B = Vec3f{ Bl.x * p.geom.hw, Bl.y * p.geom.hh, Bl.z };
+        st[k].N = Vec3f{ Nl.x * p.geom.hw, Nl.y * p.geom.hh, Nl.z };
+        st[k].face = face;
+        st[k].face_base = (uint32_t)face * p.geom.face_size - p.geom.bias;
+
+        acc_rg[k] = 0ull;
+        acc_bs[k] = 0ull;
+      }
+
+      threshold = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(threshold)));
+
+      int n_same = 0;
+      {
+        int lo = 0, hi = p.table_count;
+        while (lo < hi)
+        {
+          int mid = (lo + hi) >> 1;
+          if (s_table[mid].z > threshold)
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        n_same = lo;
+      }
+
+      int s = warp;
+
+      #pragma unroll UNROLL
+      for(; s < n_same; s += NW)
+      {
+        const float4 e = s_table[s];
+
+        #pragma unroll
+        for(int k = 0; k < TPT; ++k)
+        {
+          if (ABLATE == 0)
+          {
+            Fetched f = fetch_same_face_packed(p, st[k], e);
+            consume_packed(p, f, acc_rg[k], acc_bs[k]);
+          }
+          else if (ABLATE == 1)
+          {
+            Fetched f = fetch_same_face_packed_noload(p, st[k], e);
+            consume_packed(p, f, acc_rg[k], acc_bs[k]);
+          }
+          else if (ABLATE == 2)
+          {
+            Fetched f = fetch_same_face_packed(p, st[k], e);
+            acc_rg[k] = fma2(pack2(u2f(f.rec.x), u2f(f.rec.y)), bcast2(f.du), acc_rg[k]);
+            acc_bs[k] = fma2(pack2(u2f(f.rec.z), u2f(f.rec.w)), bcast2(f.dv), acc_bs[k]);
+          }
+          else
+          {
+            Fetched f;
+            f.rec = __ldg(p.records + (uint32_t)(s * 64 + lane + k * 32));
+            f.du = e.x; f.dv = e.y; f.nl = e.z; f.wh = e.w;
+            consume_packed(p, f, acc_rg[k], acc_bs[k]);
+          }
+        }
+      }
+
+      if (s < p.table_count)
+      {
+        #pragma unroll
+        for(int k = 0; k < TPT; ++k)
+        {
+          st[k].T = from_face_local(st[k].face, Vec3f{ st[k].T.x * p.geom.inv_hw, st[k].T.y * p.geom.inv_hh, st[k].T.z });
+          st[k].B = from_face_local(st[k].face, Vec3f{ st[k].B.x * p.geom.inv_hw, st[k].B.y * p.geom.inv_hh, st[k].B.z });
+          st[k].N = from_face_local(st[k].face, Vec3f{ st[k].N.x * p.geom.inv_hw, st[k].N.y * p.geom.inv_hh, st[k].N.z });
+        }
+
+        #pragma unroll UNROLL
+        for(; s < p.table_count; s += NW)
+        {
+          const float4 e = s_table[s];
+
+          #pragma unroll
+          for(int k = 0; k < TPT; ++k)
+          {
+            Fetched f = fetch_general(p, st[k], e);
+            consume_packed(p, f, acc_rg[k], acc_bs[k]);
+          }
+        }
+      }
+
+      #pragma unroll
+      for(int k = 0; k < TPT; ++k)
+      {
+        float a[4];
+        unpack2(acc_rg[k], a[0], a[1]);
+        unpack2(acc_bs[k], a[2], a[3]);
+
+        #pragma unroll
+        for(int c = 0; c < 4; ++c)
+          s_red[((warp * TPT + k) * 4 + c) * 32 + lane] = a[c];
+      }
+
+      __syncthreads();
+
+      if (tid < 32 * TPT)
+      {
+        const int k = tid >> 5;
+
+        float sum[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+        #pragma unroll
+        for(int w = 0; w < NW; ++w)
+        {
+          #pragma unroll
+          for(int c = 0; c < 4; ++c)
+            sum[c] += s_red[((w * TPT + k) * 4 + c) * 32 + lane];
+        }
+
+        int x, row;
+        if (tile_texel<TW, TPT>(p, tile, lane, k, x, row))
+        {
+          float r = (sum[0] - sum[3]) * p.norm;
+          float g = (sum[1] - sum[3]) * p.norm;
+          float b = (sum[2] - sum[3]) * p.norm;
+
+          size_t o = (size_t)row * p.wd + x;
+
+          if (p.dst_words)
+            p.dst_words[o] = rgbe_encode(r, g, b);
+
+          if (p.dst_f32)
+          {
+            p.dst_f32[3*o + 0] = r;
+            p.dst_f32[3*o + 1] = g;
+            p.dst_f32[3*o + 2] = b;
+          }
+        }
+      }
+
+      __syncthreads();
+    }
+  }
+
+  template<int TW, int TPT, int NW, int UNROLL, bool PIPE, int MINB>
+  __global__ void __launch_bounds__(32 * NW, MINB) prefilter_level_kernel(PrefilterParams p)
   {
     extern __shared__ float4 smem[];
     float4 *s_table = smem;
@@ -201,14 +489,52 @@ namespace ibl
 
       int s = warp;
 
-      #pragma unroll UNROLL
-      for(; s < n_same; s += NW)
+      if (PIPE)
       {
-        const float4 e = s_table[s];
+        // ---- same-face samples, gather one sample ahead ----
+        if (s < n_same)
+        {
+          Fetched cur[TPT];
+          {
+            const float4 e = s_table[s];
+            #pragma unroll
+            for(int k = 0; k < TPT; ++k)
+              cur[k] = fetch_same_face(p, st[k], e);
+          }
 
-        #pragma unroll
-        for(int k = 0; k < TPT; ++k)
-          sample_same_face(p, st[k], e, acc[k]);
+          #pragma unroll UNROLL
+          for(s += NW; s < n_same; s += NW)
+          {
+            const float4 e = s_table[s];
+
+            #pragma unroll
+            for(int k = 0; k < TPT; ++k)
+            {
+              Fetched nxt = fetch_same_face(p, st[k], e);
+              consume(p, cur[k], acc[k]);
+              cur[k] = nxt;
+            }
+          }
+
+          #pragma unroll
+          for(int k = 0; k < TPT; ++k)
+            consume(p, cur[k], acc[k]);
+        }
+      }
+      else
+      {
+        #pragma unroll UNROLL
+        for(; s < n_same; s += NW)
+        {
+          const float4 e = s_table[s];
+
+          #pragma unroll
+          for(int k = 0; k < TPT; ++k)
+          {
+            Fetched f = fetch_same_face(p, st[k], e);
+            consume(p, f, acc[k]);
+          }
+        }
       }
 
       if (s < p.table_count)
@@ -222,14 +548,48 @@ namespace ibl
           st[k].N = from_face_local(st[k].face, Vec3f{ st[k].N.x * p.geom.inv_hw, st[k].N.y * p.geom.inv_hh, st[k].N.z });
         }
 
-        #pragma unroll UNROLL
-        for(; s < p.table_count; s += NW)
+        if (PIPE)
         {
-          const float4 e = s_table[s];
+          Fetched cur[TPT];
+          {
+            const float4 e = s_table[s];
+            #pragma unroll
+            for(int k = 0; k < TPT; ++k)
+              cur[k] = fetch_general(p, st[k], e);
+          }
+
+          #pragma unroll UNROLL
+          for(s += NW; s < p.table_count; s += NW)
+          {
+            const float4 e = s_table[s];
+
+            #pragma unroll
+            for(int k = 0; k < TPT; ++k)
+            {
+              Fetched nxt = fetch_general(p, st[k], e);
+              consume(p, cur[k], acc[k]);
+              cur[k] = nxt;
+            }
+          }
 
           #pragma unroll
           for(int k = 0; k < TPT; ++k)
-            sample_general(p, st[k], e, acc[k]);
+            consume(p, cur[k], acc[k]);
+        }
+        else
+        {
+          #pragma unroll UNROLL
+          for(; s < p.table_count; s += NW)
+          {
+            const float4 e = s_table[s];
+
+            #pragma unroll
+            for(int k = 0; k < TPT; ++k)
+            {
+              Fetched f = fetch_general(p, st[k], e);
+              consume(p, f, acc[k]);
+            }
+          }
         }
       }
 
@@ -287,11 +647,57 @@ namespace ibl
 
   namespace
   {
-    template<int TW, int TPT, int NW, int UNROLL>
+    template<int TW, int TPT, int NW, int UNROLL, bool PIPE, int MINB>
     cudaError_t launch_variant(PrefilterParams p, int sm_count, cudaStream_t stream, int *launched_grid)
     {
       constexpr int TH = 32 / TW;
-      auto kernel = prefilter_level_kernel<TW, TPT, NW, UNROLL>;
+      auto kernel = prefilter_level_kernel<TW, TPT, NW, UNROLL, PIPE, MINB>;
+
+      int rows = p.row_end - p.row_begin;
+      if (p.wd >= TW)
+      {
+        p.tiles_x = (p.wd + TW - 1) / TW;
+        p.tiles = p.tiles_x * ((rows + TH * TPT - 1) / (TH * TPT));
+      }
+      else
+      {
+        p.tiles_x = 0;
+        p.tiles = (rows * p.wd + 32 * TPT - 1) / (32 * TPT);
+      }
+
+      size_t smem = (size_t)p.table_count * sizeof(float4) + (size_t)NW * TPT * 4 * 32 * sizeof(float);
+
+      cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err != cudaSuccess)
+        return err;
+
+      int resident = 0;
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 32 * NW, smem);
+      if (err != cudaSuccess)
+        return err;
+      if (resident < 1)
+        return cudaErrorLaunchOutOfResources;
+
+      int grid = p.tiles < sm_count * resident ? p.tiles : sm_count * resident;
+      if (grid < 1)
+        grid = 1;
+
+      kernel<<<grid, 32 * NW, smem, stream>>>(p);
+
+      if (launched_grid)
+        *launched_grid = grid;
+
+      return cudaGetLastError();
+    }
+  }
+
+  namespace
+  {
+    template<int TW, int TPT, int NW, int UNROLL, int MINB, int ABLATE = 0>
+    cudaError_t launch_packed(PrefilterParams p, int sm_count, cudaStream_t stream, int *launched_grid)
+    {
+      constexpr int TH = 32 / TW;
+      auto kernel = prefilter_level_packed_kernel<TW, TPT, NW, UNROLL, MINB, ABLATE>;
 
       int rows = p.row_end - p.row_begin;
       if (p.wd >= TW)
@@ -351,24 +757,53 @@ namespace ibl
     if (rows <= 0 || p.wd <= 0)
       return cudaSuccess;
 
-    // Small slabs: fewer texels per tile and more warps per tile so the few
-    // tiles there are still spread over the machine.
+    // Automatic choice by slab size.  All use the packed kernel with 8x4-texel tiles, one
+    // texel per lane; what changes is how many warps share a tile's samples: big slabs have
+    // enough tiles to fill the machine with 4-warp CTAs (cheapest reduction, most CTAs per SM),
+    // small slabs split the samples 8, 16 or 32 ways so that the few tiles still spread out.
     size_t texels = (size_t)rows * p.wd;
 
     if (variant == 0)
-      variant = (texels >= 32u * 148u * 8u) ? 6 : 2;
+    {
+      if (texels >= 32u * 148u * 8u)
+        variant = 19;
+      else if (texels >= 32u * 148u)
+        variant = 17;
+      else if (texels >= 32u * 24u)
+        variant = 14;
+      else
+        variant = 27;
+    }
 
     switch (variant)
     {
-      case 1: return launch_variant<8, 2, 8, 2>(p, sm_count, stream, launched_grid);
-      case 2: return launch_variant<8, 1, 16, 2>(p, sm_count, stream, launched_grid);
-      case 3: return launch_variant<16, 2, 8, 2>(p, sm_count, stream, launched_grid);
-      case 4: return launch_variant<8, 1, 8, 4>(p, sm_count, stream, launched_grid);
-      case 5: return launch_variant<8, 2, 4, 2>(p, sm_count, stream, launched_grid);
-      case 6: return launch_variant<8, 1, 8, 2>(p, sm_count, stream, launched_grid);
-      case 7: return launch_variant<16, 1, 8, 2>(p, sm_count, stream, launched_grid);
-      case 8: return launch_variant<8, 1, 4, 4>(p, sm_count, stream, launched_grid);
-      case 9: return launch_variant<8, 2, 8, 1>(p, sm_count, stream, launched_grid);
+      case 1: return launch_variant<8, 2, 8, 2, false, 1>(p, sm_count, stream, launched_grid);
+      case 2: return launch_variant<8, 1, 16, 2, true, 1>(p, sm_count, stream, launched_grid);
+      case 3: return launch_variant<8, 1, 8, 1, true, 1>(p, sm_count, stream, launched_grid);
+      case 4: return launch_variant<8, 1, 8, 2, true, 1>(p, sm_count, stream, launched_grid);
+      case 5: return launch_variant<8, 1, 8, 2, true, 5>(p, sm_count, stream, launched_grid);
+      case 6: return launch_variant<8, 1, 8, 2, false, 1>(p, sm_count, stream, launched_grid);
+      case 7: return launch_variant<8, 1, 8, 2, true, 4>(p, sm_count, stream, launched_grid);
+      case 8: return launch_variant<8, 2, 8, 1, true, 1>(p, sm_count, stream, launched_grid);
+      case 9: return launch_variant<8, 2, 8, 1, true, 3>(p, sm_count, stream, launched_grid);
+      case 10: return launch_packed<8, 1, 8, 2, 1>(p, sm_count, stream, launched_grid);
+      case 11: return launch_packed<8, 2, 8, 2, 1>(p, sm_count, stream, launched_grid);
+      case 12: return launch_packed<8, 1, 8, 4, 1>(p, sm_count, stream, launched_grid);
+      case 13: return launch_packed<8, 2, 8, 1, 1>(p, sm_count, stream, launched_grid);
+      case 14: return launch_packed<8, 1, 16, 2, 1>(p, sm_count, stream, launched_grid);
+      case 15: return launch_packed<16, 1, 8, 2, 1>(p, sm_count, stream, launched_grid);
+      case 16: return launch_packed<8, 1, 8, 1, 4>(p, sm_count, stream, launched_grid);
+      case 17: return launch_packed<8, 1, 8, 2, 4>(p, sm_count, stream, launched_grid);
+      case 18: return launch_packed<8, 1, 8, 1, 5>(p, sm_count, stream, launched_grid);
+      case 19: return launch_packed<8, 1, 4, 2, 8>(p, sm_count, stream, launched_grid);
+      case 20: return launch_packed<8, 1, 4, 1, 10>(p, sm_count, stream, launched_grid);
+      case 21: return launch_packed<8, 2, 8, 2, 1, 1>(p, sm_count, stream, launched_grid);
+      case 22: return launch_packed<8, 2, 8, 2, 1, 2>(p, sm_count, stream, launched_grid);
+      case 23: return launch_packed<8, 2, 8, 2, 1, 3>(p, sm_count, stream, launched_grid);
+      case 24: return launch_packed<8, 2, 8, 1, 3>(p, sm_count, stream, launched_grid);
+      case 25: return launch_packed<8, 1, 16, 1, 2>(p, sm_count, stream, launched_grid);
+      case 26: return launch_packed<8, 2, 4, 1, 6>(p, sm_count, stream, launched_grid);
+      case 27: return launch_packed<8, 1, 32, 1, 1>(p, sm_count, stream, launched_grid);
       default: return cudaErrorInvalidValue;
     }
   }

@@ -24,7 +24,7 @@ namespace ibl
     int tiles_x, tiles;      // filled by the launcher
   };
 
-  // variant 0 = pick by slab size; 1..9 = fixed <tile width, texels per lane, warps per tile>
+  // variant 0 = pick by slab size; 1..15 = fixed <tile width, texels per lane, warps per tile>
   cudaError_t launch_prefilter_level(PrefilterParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid);
 
   cudaError_t launch_build_quad_records(uint32_t const *src, uint4 *records, int ws, int hs, int sm_count, cudaStream_t stream);

@@ -14,7 +14,10 @@ reference expects it, written in place.  numpy arrays and (pinned) CPU torch
 tensors are accepted.  All arithmetic happens in libdatum_ibl_cuda.
 """
 
+import atexit
 import ctypes
+import sys
+import weakref
 
 import numpy as np
 
@@ -95,6 +98,7 @@ class IblContext:
         self._handle = handle
         self.device = int(device)
         self._torch_stream = None
+        _live.add(self)
 
     # ---- plumbing ----
 
@@ -112,9 +116,13 @@ class IblContext:
 
     def __del__(self):
         try:
-            self.close()
+            if not sys.is_finalizing():
+                self.close()
         except Exception:
             pass
+
+    def __hash__(self):
+        return id(self)
 
     def __enter__(self):
         return self
@@ -159,6 +167,12 @@ class IblContext:
         """FP32 FMA throughput of the device in TFLOP/s (register-resident FFMA chains)."""
         tflops = ctypes.c_double()
         self._check(self._lib.datum_ibl_measure_fp32_peak(self._handle, ctypes.byref(tflops)))
+        return float(tflops.value)
+
+    def measure_fp32x2_peak(self):
+        """Same, issued as packed fma.rn.f32x2 (FFMA2)."""
+        tflops = ctypes.c_double()
+        self._check(self._lib.datum_ibl_measure_fp32x2_peak(self._handle, ctypes.byref(tflops)))
         return float(tflops.value)
 
     # ---- prefilter chain: tools/ibl.cpp:242-279 ----
@@ -268,6 +282,20 @@ class IblContext:
 
 
 _default = {}
+_live = weakref.WeakSet()
+
+
+@atexit.register
+def _drain_all():
+    # At interpreter exit only drain outstanding work.  The contexts (and their streams, which
+    # torch tensors may still reference) are left for process teardown: destroying them here, or
+    # from __del__ while the CUDA runtime unloads, races with torch's own shutdown.
+    for ctx in list(_live):
+        try:
+            if ctx._handle:
+                ctx.synchronize()
+        except Exception:
+            pass
 
 
 def default_context(device=0):

@@ -151,6 +151,9 @@ int datum_ibl_pack_watercolor(datum_ibl_ctx *ctx, float const *deepcolor, float 
  */
 int datum_ibl_measure_fp32_peak(datum_ibl_ctx *ctx, double *tflops);
 
+/* the same measurement issued as packed two-wide fma.rn.f32x2 (SASS FFMA2, new on sm_100) */
+int datum_ibl_measure_fp32x2_peak(datum_ibl_ctx *ctx, double *tflops);
+
 /*
  * CUDA-event timings of the dominant kernel (the level-1 prefilter launch of
  * every chain since the last reset, at most 512): number of launches averaged,

@@ -93,23 +93,37 @@ def test_host_and_device_entry_points_agree(ctx):
 
 
 def test_row_slabs_reproduce_the_full_level(ctx):
-    """Multi-GPU sharding primitive: a level computed as row slabs is bit-identical to one launch."""
+    """Multi-GPU sharding primitive: a level computed as row slabs equals one full launch.  A
+    slab may pick another warp split than the full level (fp32 sums associate differently), so
+    the comparison is the packed-word criterion plus a 2e-5 bound on the fp32 values; with the
+    kernel variant pinned the slabs are bit-identical."""
     ws, levels, level = 64, 7, 2
     src = synth.synthetic_chain(ws, ws, 1, probe=13)
     d_src = torch.from_numpy(src.view(np.int32)).to(DEV)
     wd = ws // 2
-    full = torch.zeros(6 * wd * wd, dtype=torch.int32, device=DEV)
-    ctx.prefilter_level_device(d_src, ws, ws, level, levels, 1024, 0, 6 * wd, full)
-    slabs = torch.zeros_like(full)
     cuts = [0, 7, 8, 50, 97, 6 * wd]
-    for a, b in zip(cuts[:-1], cuts[1:]):
-        ctx.prefilter_level_device(d_src, ws, ws, level, levels, 1024, a, b, slabs)
-    ctx.synchronize()
-    assert torch.equal(full, slabs)
-    # an empty slab is legal and writes nothing
-    ctx.prefilter_level_device(d_src, ws, ws, level, levels, 1024, 5, 5, slabs)
-    ctx.synchronize()
-    assert torch.equal(full, slabs)
+
+    def run(variant):
+        ctx.set_prefilter_variant(variant)
+        full = torch.zeros(6 * wd * wd, dtype=torch.int32, device=DEV)
+        full_f = torch.zeros(6 * wd * wd * 3, dtype=torch.float32, device=DEV)
+        ctx.prefilter_level_device(d_src, ws, ws, level, levels, 1024, 0, 6 * wd, full, full_f)
+        slabs, slabs_f = torch.zeros_like(full), torch.zeros_like(full_f)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            ctx.prefilter_level_device(d_src, ws, ws, level, levels, 1024, a, b, slabs, slabs_f)
+        ctx.prefilter_level_device(d_src, ws, ws, level, levels, 1024, 5, 5, slabs, slabs_f)   # empty slab: legal, writes nothing
+        ctx.synchronize()
+        return full, full_f, slabs, slabs_f
+
+    try:
+        full, full_f, slabs, slabs_f = run(0)
+        assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 2e-5
+        stats = oracle_lib.word_stats(slabs.cpu().numpy().view(np.uint32), full.cpu().numpy().view(np.uint32))
+        assert oracle_lib.words_within_one_code(stats, 0.995), stats
+        full, full_f, slabs, slabs_f = run(17)
+        assert torch.equal(full, slabs) and torch.equal(full_f, slabs_f)
+    finally:
+        ctx.set_prefilter_variant(0)
 
 
 def test_kernel_variants_agree(ctx):
@@ -119,7 +133,7 @@ def test_kernel_variants_agree(ctx):
     bits = synth.synthetic_chain(w, w, levels, probe=14, sun=False)
     base = None
     try:
-        for variant in range(0, 10):
+        for variant in (0, 1, 6, 10, 11, 14, 17, 19, 27):
             ctx.set_prefilter_variant(variant)
             words, f32 = run_chain_device(ctx, bits, w, w, levels, 1024)
             if base is None:
