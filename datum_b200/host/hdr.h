@@ -1,11 +1,7 @@
 // datum_b200 host shim — same declarations as the reference's tools/hdr.h:11-39.
 #pragma once
 
-#ifdef DATUM_IBL_IN_REFERENCE_TREE
-#include "datum/math.h"
-#else
 #include "math.h"
-#endif
 
 #include <string>
 #include <vector>

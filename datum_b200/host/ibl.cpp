@@ -6,9 +6,20 @@
 // std::runtime_error, which assetbuilder's main() already catches and reports
 // (tools/assetbuilder.cpp:968-982).  There is no CPU fallback.
 
+// In the reference tree: copy this file over tools/ibl.cpp and define
+// DATUM_IBL_IN_REFERENCE_TREE; "ibl.h" then resolves to the reference's own header
+// (tools/ibl.h -> tools/hdr.h -> datum/math.h) and tools/hdr.cpp keeps providing
+// load_hdr / image_pack_cube.  Stand-alone (this repository): "ibl.h" is
+// datum_b200/host/ibl.h with the same declarations.
+
 #include "ibl.h"
 
 #include "datum_ibl_cuda.h"
+
+#ifdef DATUM_IBL_IN_REFERENCE_TREE
+void image_project_sh9_cube(int width, int height, void const *level0_rgbe, float *sh);
+void image_set_ibl_samples(int samples);
+#endif
 
 #include <cstdlib>
 #include <mutex>
@@ -91,7 +102,9 @@ void image_set_ibl_samples(int samples)
 }
 
 ///////////////////////// image_pack_cube ///////////////////////////////////
-// declared in hdr.h; lives here so that the shim has a single context
+// declared in hdr.h; lives here so that the shim has a single context.  Inside the
+// reference tree tools/hdr.cpp keeps its own (CPU) definition for other callers.
+#ifndef DATUM_IBL_IN_REFERENCE_TREE
 void image_pack_cube(HDRImage const &image, int width, int height, int levels, void *bits)
 {
   if (levels != 1)
@@ -99,3 +112,4 @@ void image_pack_cube(HDRImage const &image, int width, int height, int levels, v
 
   check(datum_ibl_pack_cube(context(), image.width, image.height, &image.bits[0].r, width, height, bits));
 }
+#endif
