@@ -165,3 +165,22 @@ def test_equirect_pack_matches_oracle(ctx, iw, ih, w, h):
     dec_got, dec_want = oracle_lib.rgbe_decode_array(got)[:, :3], oracle_lib.rgbe_decode_array(want)[:, :3]
     rel = oracle_lib.relative_error(dec_got, dec_want)
     assert np.quantile(rel, 0.995) <= 4e-3, float(np.quantile(rel, 0.995))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/tools/ibl.h"), reason="needs the reference tree")
+def test_forwarder_compiles_against_the_reference_headers(tmp_path):
+    """the shim copied over tools/ibl.cpp compiles against the reference's OWN
+    tools/ibl.h, tools/hdr.h and src/math headers (leap provided by the oracle's stand-in)."""
+    import shutil
+    shutil.copy(os.path.join(ROOT, "datum_b200", "host", "ibl.cpp"), tmp_path / "ibl.cpp")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-std=c++14", "-c", "-DDATUM_IBL_IN_REFERENCE_TREE", "-w",
+           "-I", "/root/reference/tools", "-I", os.path.join(ROOT, "oracle", "shim"), "-I", "/root/reference/src/math",
+           "-I", "/root/reference/include", "-I", os.path.join(ROOT, "include"),
+           "-o", str(tmp_path / "ibl.o"), str(tmp_path / "ibl.cpp")]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0, out.stdout
+    symbols = subprocess.run(["nm", "-C", str(tmp_path / "ibl.o")], stdout=subprocess.PIPE, text=True).stdout
+    for name in ("image_buildmips_cube_ibl(int, int, int, void*)", "image_pack_cube_ibl(HDRImage const&, int, int, int, void*)",
+                 "image_pack_envbrdf(int, int, void*)", "image_pack_watercolor(lml::Color3 const&, lml::Color3 const&, float, lml::Color3 const&, float, float, int, int, void*)"):
+        assert " T " + name in symbols, name
