@@ -62,4 +62,25 @@ namespace ibl
 
     return out;
   }
+
+  BandedSamples build_banded_samples(int level, int levels, int samples, int band)
+  {
+    BandedSamples out;
+    out.level = build_level_samples(level, levels, samples);
+    out.band = band;
+
+    auto &e = out.level.entries;
+    for(size_t begin = 0; begin < e.size(); begin += (size_t)band)
+    {
+      size_t end = std::min(e.size(), begin + (size_t)band);
+
+      out.band_min_lz.push_back(e[end - 1].lz);
+
+      std::stable_sort(e.begin() + begin, e.begin() + end, [](SampleEntry const &a, SampleEntry const &b) {
+        return std::atan2((double)a.ly, (double)a.lx) < std::atan2((double)b.ly, (double)b.lx);
+      });
+    }
+
+    return out;
+  }
 }

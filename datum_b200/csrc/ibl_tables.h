@@ -35,6 +35,20 @@ namespace ibl
   // level in [1, levels), samples >= 1
   LevelSamples build_level_samples(int level, int levels, int samples);
 
+  // The same entries cut into bands of `band` consecutive entries of the lz order (the last band
+  // may be short) and, inside each band, ordered by the angle atan2(ly, lx): a warp that walks a
+  // band walks along a ring of the lobe, so consecutive samples fetch neighbouring footprints.
+  // band_min_lz[k] = smallest lz of band k (decreasing in k): the kernel's same-face test works
+  // on whole bands.
+  struct BandedSamples
+  {
+    LevelSamples level;
+    int band = 0;
+    std::vector<float> band_min_lz;
+  };
+
+  BandedSamples build_banded_samples(int level, int levels, int samples, int band);
+
   // ibl.cpp:95-104
   float radicalinverse_VdC(uint32_t bits);
 }
