@@ -316,7 +316,7 @@ def run_ours(args):
         },
         "gpu_launches": total_launches,
         "roofline": {
-            "bound": "fp32", "kernel": "prefilter_level_kernel (level 1: 512^2 -> 256^2 faces)",
+            "bound": "fp32", "kernel": "prefilter_dn_kernel (level 1: 512^2 -> 256^2 faces)",
             "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
             "peak_source": "FFMA-chain micro-benchmark run in this process (datum_ibl_measure_fp32_peak); MEASURED_PEAKS.json carries no FP32 figure",
             "flop_per_texel_sample": FLOP_PER_TEXEL_SAMPLE, "texel_samples_per_launch": dom_ts,

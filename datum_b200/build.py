@@ -20,7 +20,7 @@ LIBDIR = os.path.join(ROOT, "datum_b200", "lib")
 CUDA_LIB = os.path.join(LIBDIR, "libdatum_ibl_cuda.so")
 HOST_LIB = os.path.join(LIBDIR, "libdatum_ibl_host.so")
 
-CUDA_SOURCES = ["cabi.cu", "prefilter.cu", "prefilter_f16.cu", "sh9.cu", "luts.cu", "resample.cu", "ibl_tables.cpp"]
+CUDA_SOURCES = ["cabi.cu", "prefilter.cu", "prefilter_dn.cu", "sh9.cu", "luts.cu", "resample.cu", "ibl_tables.cpp"]
 CUDA_HEADERS = ["ibl_math.cuh", "ibl_tables.h", "prefilter.h", "sh9.h", "luts.h", "resample.h"]
 
 NVCC_FLAGS = [

@@ -47,10 +47,8 @@ namespace
     int count = 0;
     int samples = 0; // the reference's kSamples this table was built for (accepted + rejected)
     float norm = 0;  // kAccScale / total weight
-    float norm_half = 0; // (512/511) / total weight: half-record kernel
-    float4 *d_banded_dn = nullptr; // d_banded scaled by 2^64 (denormal-mantissa kernel)
     double total_weight = 0;
-    float4 *d_banded = nullptr;  // the entries in banded ring order (ibl_tables.h), half-record kernel
+    float4 *d_banded = nullptr;  // the entries in banded ring order (ibl_tables.h), scaled by kDnTableScale
     float *d_band_min = nullptr; // smallest lz per band
     int bands = 0;
   };
@@ -106,8 +104,7 @@ struct datum_ibl_ctx
 
   DeviceBuffer<uint32_t> chain;   // staged payload for the host entry point
   DeviceBuffer<uint4> records;    // quad records of the current source level
-  DeviceBuffer<uint2> records_b;  // half-record kernel: blue halves of the footprints
-  DeviceBuffer<int> queue_heads;  // half-record kernel: per-SM tile queue heads
+  DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
   DeviceBuffer<float> sh_weights; // solid angle table
   int sh_weights_w = 0, sh_weights_h = 0;
   DeviceBuffer<double> sh_partials; // block partials + 28 result doubles
@@ -169,7 +166,6 @@ namespace
         t.count = host.accepted;
         t.samples = samples;
         t.norm = (float)((double)ibl::kAccScale / host.total_weight);
-        t.norm_half = (float)((512.0 / 511.0) / host.total_weight);
         t.total_weight = host.total_weight;
 
         cudaError_t err = cudaMalloc(&t.d_entries, sizeof(float4) * (size_t)(t.count > 0 ? t.count : 1));
@@ -182,6 +178,11 @@ namespace
         ibl::BandedSamples banded = ibl::build_banded_samples(level, levels, samples, ibl::kSampleBand);
         t.bands = (int)banded.band_min_lz.size();
 
+        for(auto &e : banded.level.entries)
+        {
+          e.lx *= ibl::kDnTableScale; e.ly *= ibl::kDnTableScale; e.lz *= ibl::kDnTableScale; e.wh *= ibl::kDnTableScale;
+        }
+
         if (err == cudaSuccess)
           err = cudaMalloc(&t.d_banded, sizeof(float4) * (size_t)(t.count > 0 ? t.count : 1));
         if (err == cudaSuccess)
@@ -190,16 +191,6 @@ namespace
           err = cudaMemcpyAsync(t.d_banded, banded.level.entries.data(), sizeof(float4) * (size_t)t.count, cudaMemcpyHostToDevice, ctx->stream);
         if (err == cudaSuccess)
           err = cudaMemcpyAsync(t.d_band_min, banded.band_min_lz.data(), sizeof(float) * (size_t)t.bands, cudaMemcpyHostToDevice, ctx->stream);
-
-        std::vector<ibl::SampleEntry> scaled = banded.level.entries;
-        for(auto &e : scaled)
-        {
-          e.lx *= ibl::kDnTableScale; e.ly *= ibl::kDnTableScale; e.lz *= ibl::kDnTableScale; e.wh *= ibl::kDnTableScale;
-        }
-        if (err == cudaSuccess)
-          err = cudaMalloc(&t.d_banded_dn, sizeof(float4) * (size_t)(t.count > 0 ? t.count : 1));
-        if (err == cudaSuccess)
-          err = cudaMemcpyAsync(t.d_banded_dn, scaled.data(), sizeof(float4) * (size_t)t.count, cudaMemcpyHostToDevice, ctx->stream);
 
         if (err == cudaSuccess)
           err = cudaStreamSynchronize(ctx->stream); // `host` and `banded` die at the end of this iteration
@@ -233,33 +224,25 @@ namespace
     return slot;
   }
 
-  // half-record kernel (prefilter_f16.cu): footprint records of twelve halves, FHFMA accumulation
-  int run_level_half(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant)
+  // levels at least 8 texels wide: denormal-mantissa kernel (prefilter_dn.cu)
+  int run_level_dn(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant)
   {
     int wd = ws >> 1, hd = hs >> 1;
-    bool dn = ctx->prefilter_variant >= 50;
-    size_t count = dn ? (size_t)6 * ws * hs : ibl::half_record_count(ws, hs);
 
-    cudaError_t err = ctx->records.reserve(count);
-    if (err == cudaSuccess && !dn)
-      err = ctx->records_b.reserve(count);
+    cudaError_t err = ctx->records.reserve((size_t)6 * ws * hs);
     if (err == cudaSuccess)
       err = ctx->queue_heads.reserve((size_t)ctx->sm_count + 1);
     if (err != cudaSuccess)
-      return fail_cuda("cudaMalloc(half records)", err);
+      return fail_cuda("cudaMalloc(quad records)", err);
 
-    if (dn)
-      err = ibl::launch_build_dn_records(d_src, ctx->records.ptr, ws, hs, ctx->queue_heads.ptr, ctx->sm_count + 1, ctx->sm_count, ctx->stream);
-    else
-      err = ibl::launch_build_half_records(d_src, ctx->records.ptr, ctx->records_b.ptr, ws, hs, ctx->queue_heads.ptr, ctx->sm_count + 1, ctx->sm_count, ctx->stream);
+    err = ibl::launch_build_dn_records(d_src, ctx->records.ptr, ws, hs, ctx->queue_heads.ptr, ctx->sm_count + 1, ctx->sm_count, ctx->stream);
     if (err != cudaSuccess)
-      return fail_cuda("build_half_records", err);
+      return fail_cuda("build_dn_records", err);
     ctx->launches += 1;
 
-    ibl::PrefilterHalfParams p = {};
-    p.recA = ctx->records.ptr;
-    p.recB = ctx->records_b.ptr;
-    p.table = dn ? table.d_banded_dn : table.d_banded;
+    ibl::PrefilterDnParams p = {};
+    p.records = ctx->records.ptr;
+    p.table = table.d_banded;
     p.band_min_lz = table.d_band_min;
     p.table_count = table.count;
     p.bands = table.bands;
@@ -269,27 +252,18 @@ namespace
     p.hd = hd;
     p.row_begin = row_begin;
     p.row_end = row_end;
-    p.geom = dn ? ibl::make_dn_geom(ws, hs) : ibl::make_half_geom(ws, hs);
+    p.geom = ibl::make_level_geom(ws, hs);
     for(int f = 0; f < 6; ++f)
       p.quats[f] = ctx->quats[f];
-    if (dn)
-    {
-      // sums hold m * 2^-149 * 2^(field position) * 2^64 * 2^E * weight; radiance = (m/511) * 2^(E-15)
-      double base = std::ldexp(1.0, 149 - 64 - 15) / 511.0 / table.total_weight;
-      p.norm[0] = (float)base;                      // r: integer bits
-      p.norm[1] = (float)std::ldexp(base, -14);     // g: field at bits 14..22
-      p.norm[2] = (float)std::ldexp(base, -5);      // b: field at bits 5..13
-    }
-    else
-      p.norm[0] = p.norm[1] = p.norm[2] = table.norm_half;
+    ibl::dn_channel_norms(table.total_weight, p.norm);
     p.exp_mul = 0x00800000u;
     p.counters = ctx->queue_heads.ptr;
 
     int slot = record_dominant ? begin_dominant(ctx, (double)(row_end - row_begin) * wd * (double)table.samples) : -1;
 
-    err = ibl::launch_prefilter_half(p, ctx->prefilter_variant, ctx->sm_count, ctx->stream, nullptr);
+    err = ibl::launch_prefilter_dn(p, ctx->prefilter_variant >= 50 ? ctx->prefilter_variant : 0, ctx->sm_count, ctx->stream, nullptr);
     if (err != cudaSuccess)
-      return fail_cuda("prefilter_half", err);
+      return fail_cuda("prefilter_dn", err);
     ctx->launches += 1;
 
     if (slot >= 0)
@@ -312,8 +286,10 @@ namespace
     if (row_begin == row_end)
       return 0;
 
-    if (ctx->prefilter_variant >= 30 && wd >= 8)
-      return run_level_half(ctx, d_src, ws, hs, table, row_begin, row_end, d_dst_words, d_dst_f32, record_dominant);
+    // variant 0 and 50..58: the denormal-mantissa kernel wherever a level is wide enough for its
+    // 8x4 tiles; 10..27 pin a kernel of prefilter.cu (kept for narrow levels and for A/B timing)
+    if ((ctx->prefilter_variant == 0 || ctx->prefilter_variant >= 50) && wd >= 8)
+      return run_level_dn(ctx, d_src, ws, hs, table, row_begin, row_end, d_dst_words, d_dst_f32, record_dominant);
 
     cudaError_t err = ctx->records.reserve((size_t)6 * ws * hs);
     if (err != cudaSuccess)
@@ -342,7 +318,7 @@ namespace
 
     int slot = record_dominant ? begin_dominant(ctx, (double)(row_end - row_begin) * wd * (double)table.samples) : -1;
 
-    err = ibl::launch_prefilter_level(p, ctx->prefilter_variant >= 30 ? 0 : ctx->prefilter_variant, ctx->sm_count, ctx->stream, nullptr);
+    err = ibl::launch_prefilter_level(p, ctx->prefilter_variant >= 50 ? 0 : ctx->prefilter_variant, ctx->sm_count, ctx->stream, nullptr);
     if (err != cudaSuccess)
       return fail_cuda("prefilter_level", err);
     ctx->launches += 1;
@@ -466,13 +442,11 @@ extern "C"
           cudaFree(t.d_banded);
         if (t.d_band_min)
           cudaFree(t.d_band_min);
-        if (t.d_banded_dn)
-          cudaFree(t.d_banded_dn);
+
       }
 
     ctx->chain.release();
     ctx->records.release();
-    ctx->records_b.release();
     ctx->queue_heads.release();
     ctx->sh_weights.release();
     ctx->sh_partials.release();
@@ -507,7 +481,7 @@ extern "C"
 
   int datum_ibl_set_prefilter_variant(datum_ibl_ctx *ctx, int variant)
   {
-    if (!ctx || variant < 0 || variant > 60)
+    if (!ctx || variant < 0 || variant > 99)
       return fail("datum_ibl_set_prefilter_variant: bad argument");
 
     ctx->prefilter_variant = variant;

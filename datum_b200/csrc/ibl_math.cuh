@@ -128,6 +128,7 @@ namespace ibl
   // Magic constant for round-to-nearest-integer through the fp32 adder: adding
   // 1.5*2^23 leaves the integer in the low mantissa bits.
   constexpr float kMagic = 12582912.0f;
+  constexpr float kRcpShrink = 0.99999976158142089844f; // 1 - 2^-22
   constexpr uint32_t kMagicBits = 0x4B400000u;
 
   struct LevelGeom
@@ -175,7 +176,11 @@ namespace ibl
     float un = px ? Lz : Lx;
     float vn = py ? Lz : Ly;
 
-    float r = rcp_fast(major);
+    // rcp.approx may round up by one ulp: on an exact tie |un| == |major| (a direction on a cube
+    // edge) the quotient would then exceed 1 and the footprint would start one texel outside the
+    // face.  Shrinking the reciprocal by two ulps keeps |q| <= 1; it moves a footprint by at most
+    // 2.4e-7 of the face width.
+    float r = rcp_fast(major) * kRcpShrink;
     float ar = fabsf(r);
     float ru = px ? r : (py ? ar : -r);
     float rv = py ? r : ar;
@@ -311,5 +316,45 @@ namespace ibl
     float u1 = 0.5f + du, u0 = 0.5f - du;
     float v1 = fmaf(dv, nl, wh), v0 = fmaf(-dv, nl, wh);
     w[0] = u0 * v0; w[1] = u1 * v0; w[2] = u0 * v1; w[3] = u1 * v1;
+  }
+
+  // ---- "denormal mantissa" records (prefilter_dn.cu) ----
+  //
+  // E5B9G9R9 word (E 27..31, b 18..26, g 9..17, r 0..8) -> r<<23 | g<<14 | b<<5 | E.
+  // A mantissa field is read as the fp32 number its bits spell under a zero exponent field:
+  //     u2f(word >> 23)        = r * 2^-149
+  //     u2f(word & kDnMaskG)   = g * 2^-149 * 2^14
+  //     u2f(word & kDnMaskB)   = b * 2^-149 * 2^5
+  // subnormals, exact, and exact again as FMA operands.  The shared exponent multiplies the
+  // tap's weight instead: bits(w) + (E << 23) == bits(w * 2^E) for any normal w.
+  constexpr uint32_t kDnMaskE = 0x0000001Fu;
+  constexpr uint32_t kDnMaskB = 0x00003FE0u;
+  constexpr uint32_t kDnMaskG = 0x007FC000u;
+
+  // every entry of the sample table is multiplied by 2^64 (directions are scale invariant, weights
+  // carry the factor) so that no weight * mantissa product falls below the normal range
+  constexpr float kDnTableScale = 18446744073709551616.0f;
+
+  IBL_HD uint32_t pack_dn_word(uint32_t w)
+  {
+    return ((w & 0x1FFu) << 23) | (((w >> 9) & 0x1FFu) << 14) | (((w >> 18) & 0x1FFu) << 5) | (w >> 27);
+  }
+
+  // one tap, scalar form of the kernel's accumulate(): acc[c] += w * 2^E * field_c
+  IBL_HD void dn_accumulate_tap(uint32_t word, float w, float acc[3])
+  {
+    float ws = u2f(f2u(w) + ((word & kDnMaskE) << 23));
+    acc[0] = fmaf(u2f(word >> 23), ws, acc[0]);
+    acc[1] = fmaf(u2f(word & kDnMaskG), ws, acc[1]);
+    acc[2] = fmaf(u2f(word & kDnMaskB), ws, acc[2]);
+  }
+
+  // sums -> radiance: radiance = (m/511) * 2^(E-15), sums hold m * 2^-149 * 2^(field position) * 2^64 * 2^E * weight
+  IBL_HD void dn_channel_norms(double total_weight, float norm[3])
+  {
+    double base = ldexp(1.0, 149 - 64 - 15) / 511.0 / total_weight;
+    norm[0] = (float)base;
+    norm[1] = (float)ldexp(base, -14);
+    norm[2] = (float)ldexp(base, -5);
   }
 }

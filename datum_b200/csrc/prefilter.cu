@@ -1,7 +1,10 @@
-// datum_b200 — GGX prefilter of one cube-map mip level (sm_100a).
+// datum_b200 — GGX prefilter of one cube-map mip level, first kernel (sm_100a).
 //
 // Replaces the triple loop of tools/ibl.cpp:263-272 and the per-texel sample
 // loop of tools/ibl.cpp:160-187 (reference paths relative to /root/reference).
+// The library uses it for levels narrower than 8 texels (its tiles may be cut in
+// linear texel order); wider levels run prefilter_dn.cu, which replaced this
+// kernel's six-logic-op tap decode.  Variants 10..27 stay selectable for A/B timing.
 //
 // Work decomposition
 //   tile      = 32*TPT output texels (TW x 32/TW lanes, TPT texels per lane)
@@ -112,32 +115,6 @@ namespace ibl
     return f;
   }
 
-  // frame rows in face-local (a, b, m) coordinates, a and b pre-scaled
-  __device__ __forceinline__ Fetched fetch_same_face(PrefilterParams const &p, TexelState const &t, float4 e)
-  {
-    float la = fmaf(e.z, t.N.x, fmaf(e.y, t.B.x, e.x * t.T.x));
-    float lb = fmaf(e.z, t.N.y, fmaf(e.y, t.B.y, e.x * t.T.y));
-    float lm = fmaf(e.z, t.N.z, fmaf(e.y, t.B.z, e.x * t.T.z));
-
-    Fetched f;
-    uint32_t idx = face_footprint(p.geom, t.face_base, la, lb, lm, f.du, f.dv);
-    f.rec = __ldg(p.records + idx);
-    f.nl = e.z;
-    f.wh = e.w;
-    return f;
-  }
-
-  __device__ __forceinline__ void consume(PrefilterParams const &p, Fetched const &f, float acc[4])
-  {
-    float w[4];
-    footprint_weights(f.du, f.dv, f.wh, f.nl, w);
-
-    accumulate_tap(p.masks, f.rec.x, w[0], acc);
-    accumulate_tap(p.masks, f.rec.y, w[1], acc);
-    accumulate_tap(p.masks, f.rec.z, w[2], acc);
-    accumulate_tap(p.masks, f.rec.w, w[3], acc);
-  }
-
   // ---- packed two-wide fp32 (fma.rn.f32x2 -> SASS FFMA2/FMUL2/FADD2, new on sm_100) ----
   //
   // One FFMA2 does two FMAs for one issue slot (same lane throughput as two
@@ -183,28 +160,6 @@ namespace ibl
     return out;
   }
 
-  __device__ __forceinline__ Fetched fetch_same_face_packed_noload(PrefilterParams const &p, TexelState const &t, float4 e)
-  {
-    f32x2 lab = mul2(bcast2(e.x), pack2(t.T.x, t.T.y));
-    lab = fma2(bcast2(e.y), pack2(t.B.x, t.B.y), lab);
-    lab = fma2(bcast2(e.z), pack2(t.N.x, t.N.y), lab);
-    float lm = fmaf(e.z, t.N.z, fmaf(e.y, t.B.z, e.x * t.T.z));
-    float r = rcp_fast(lm);
-    f32x2 f = fma2(lab, bcast2(r), pack2(p.geom.hwm, p.geom.hhm));
-    f32x2 m = add2(f, bcast2(kMagic));
-    f32x2 fi = add2(m, bcast2(-kMagic));
-    f32x2 d = fma2(fi, bcast2(-1.0f), f);
-    float mu, mv;
-    unpack2(m, mu, mv);
-    Fetched out;
-    unpack2(d, out.du, out.dv);
-    uint32_t idx = f2u(mv) * (uint32_t)p.geom.ws + f2u(mu) + t.face_base;
-    out.rec = make_uint4(idx * 2654435761u, idx * 40503u, idx ^ 0x12345678u, idx + 77u);
-    out.nl = e.z;
-    out.wh = e.w;
-    return out;
-  }
-
   // footprint_weights + accumulate_tap of ibl_math.cuh on (r, g) and (b, bias) accumulator pairs
   __device__ __forceinline__ void accumulate_tap_packed(DecodeMasks const &k, uint32_t word, float w, f32x2 &acc_rg, f32x2 &acc_bs)
   {
@@ -234,11 +189,8 @@ namespace ibl
   }
 
   // ---- the kernel with packed arithmetic -------------------------------------------
-  // Same tiling, tables, same-face split and reduction as prefilter_level_kernel below.
 
-  // ABLATE (tuning experiments only, results are wrong when non-zero): 1 = no gather (record
-  // synthesised from the index), 2 = gather but trivial arithmetic on it, 3 = no geometry
-  template<int TW, int TPT, int NW, int UNROLL, int MINB, int ABLATE = 0>
+  template<int TW, int TPT, int NW, int UNROLL, int MINB>
   __global__ void __launch_bounds__(32 * NW, MINB) prefilter_level_packed_kernel(PrefilterParams p)
   {
     extern __shared__ float4 smem[];
@@ -315,29 +267,8 @@ namespace ibl
         #pragma unroll
         for(int k = 0; k < TPT; ++k)
         {
-          if (ABLATE == 0)
-          {
-            Fetched f = fetch_same_face_packed(p, st[k], e);
-            consume_packed(p, f, acc_rg[k], acc_bs[k]);
-          }
-          else if (ABLATE == 1)
-          {
-            Fetched f = fetch_same_face_packed_noload(p, st[k], e);
-            consume_packed(p, f, acc_rg[k], acc_bs[k]);
-          }
-          else if (ABLATE == 2)
-          {
-            Fetched f = fetch_same_face_packed(p, st[k], e);
-            acc_rg[k] = fma2(pack2(u2f(f.rec.x), u2f(f.rec.y)), bcast2(f.du), acc_rg[k]);
-            acc_bs[k] = fma2(pack2(u2f(f.rec.z), u2f(f.rec.w)), bcast2(f.dv), acc_bs[k]);
-          }
-          else
-          {
-            Fetched f;
-            f.rec = __ldg(p.records + (uint32_t)(s * 64 + lane + k * 32));
-            f.du = e.x; f.dv = e.y; f.nl = e.z; f.wh = e.w;
-            consume_packed(p, f, acc_rg[k], acc_bs[k]);
-          }
+          Fetched f = fetch_same_face_packed(p, st[k], e);
+          consume_packed(p, f, acc_rg[k], acc_bs[k]);
         }
       }
 
@@ -417,287 +348,15 @@ namespace ibl
     }
   }
 
-  template<int TW, int TPT, int NW, int UNROLL, bool PIPE, int MINB>
-  __global__ void __launch_bounds__(32 * NW, MINB) prefilter_level_kernel(PrefilterParams p)
-  {
-    extern __shared__ float4 smem[];
-    float4 *s_table = smem;
-    float *s_red = reinterpret_cast<float*>(smem + p.table_count);
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-
-    for(int i = tid; i < p.table_count; i += 32 * NW)
-      s_table[i] = __ldg(p.table + i);
-
-    __syncthreads();
-
-    for(int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
-    {
-      TexelState st[TPT];
-      float acc[TPT][4];
-      float threshold = 0.0f;
-
-      #pragma unroll
-      for(int k = 0; k < TPT; ++k)
-      {
-        int x, row;
-        bool valid = tile_texel<TW, TPT>(p, tile, lane, k, x, row);
-
-        // lanes past the slab still walk the sample loops (their sums are dropped):
-        // park them on a face-centre texel, whose lobe stays inside its face
-        if (!valid) { x = p.wd >> 1; row = (p.row_begin / p.hd) * p.hd + (p.hd >> 1); }
-
-        int face = row / p.hd;
-        int y = row - face * p.hd;
-
-        Vec3f N = texel_normal(p.quats[face], x, y, p.wd, p.hd);
-        Vec3f T, B;
-        tangent_frame(N, T, B);
-
-        // face-local rows, a and b scaled to source texels (align-corners, ibl.cpp:37-38)
-        Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
-
-        threshold = fmaxf(threshold, same_face_threshold(Nl));
-
-        st[k].T = Vec3f{ Tl.x * p.geom.hw, Tl.y * p.geom.hh, Tl.z };
-        st[k].B = Vec3f{ Bl.x * p.geom.hw, Bl.y * p.geom.hh, Bl.z };
-        st[k].N = Vec3f{ Nl.x * p.geom.hw, Nl.y * p.geom.hh, Nl.z };
-        st[k].face = face;
-        st[k].face_base = (uint32_t)face * p.geom.face_size - p.geom.bias;
-
-        acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
-      }
-
-      // number of leading (smallest-angle) samples that stay on every texel's own face
-      threshold = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(threshold)));
-
-      int n_same = 0;
-      {
-        int lo = 0, hi = p.table_count; // first index with lz <= threshold (table sorted by decreasing lz)
-        while (lo < hi)
-        {
-          int mid = (lo + hi) >> 1;
-          if (s_table[mid].z > threshold)
-            lo = mid + 1;
-          else
-            hi = mid;
-        }
-        n_same = lo;
-      }
-
-      int s = warp;
-
-      if (PIPE)
-      {
-        // ---- same-face samples, gather one sample ahead ----
-        if (s < n_same)
-        {
-          Fetched cur[TPT];
-          {
-            const float4 e = s_table[s];
-            #pragma unroll
-            for(int k = 0; k < TPT; ++k)
-              cur[k] = fetch_same_face(p, st[k], e);
-          }
-
-          #pragma unroll UNROLL
-          for(s += NW; s < n_same; s += NW)
-          {
-            const float4 e = s_table[s];
-
-            #pragma unroll
-            for(int k = 0; k < TPT; ++k)
-            {
-              Fetched nxt = fetch_same_face(p, st[k], e);
-              consume(p, cur[k], acc[k]);
-              cur[k] = nxt;
-            }
-          }
-
-          #pragma unroll
-          for(int k = 0; k < TPT; ++k)
-            consume(p, cur[k], acc[k]);
-        }
-      }
-      else
-      {
-        #pragma unroll UNROLL
-        for(; s < n_same; s += NW)
-        {
-          const float4 e = s_table[s];
-
-          #pragma unroll
-          for(int k = 0; k < TPT; ++k)
-          {
-            Fetched f = fetch_same_face(p, st[k], e);
-            consume(p, f, acc[k]);
-          }
-        }
-      }
-
-      if (s < p.table_count)
-      {
-        // back to world coordinates for the samples that may cross a face edge
-        #pragma unroll
-        for(int k = 0; k < TPT; ++k)
-        {
-          st[k].T = from_face_local(st[k].face, Vec3f{ st[k].T.x * p.geom.inv_hw, st[k].T.y * p.geom.inv_hh, st[k].T.z });
-          st[k].B = from_face_local(st[k].face, Vec3f{ st[k].B.x * p.geom.inv_hw, st[k].B.y * p.geom.inv_hh, st[k].B.z });
-          st[k].N = from_face_local(st[k].face, Vec3f{ st[k].N.x * p.geom.inv_hw, st[k].N.y * p.geom.inv_hh, st[k].N.z });
-        }
-
-        if (PIPE)
-        {
-          Fetched cur[TPT];
-          {
-            const float4 e = s_table[s];
-            #pragma unroll
-            for(int k = 0; k < TPT; ++k)
-              cur[k] = fetch_general(p, st[k], e);
-          }
-
-          #pragma unroll UNROLL
-          for(s += NW; s < p.table_count; s += NW)
-          {
-            const float4 e = s_table[s];
-
-            #pragma unroll
-            for(int k = 0; k < TPT; ++k)
-            {
-              Fetched nxt = fetch_general(p, st[k], e);
-              consume(p, cur[k], acc[k]);
-              cur[k] = nxt;
-            }
-          }
-
-          #pragma unroll
-          for(int k = 0; k < TPT; ++k)
-            consume(p, cur[k], acc[k]);
-        }
-        else
-        {
-          #pragma unroll UNROLL
-          for(; s < p.table_count; s += NW)
-          {
-            const float4 e = s_table[s];
-
-            #pragma unroll
-            for(int k = 0; k < TPT; ++k)
-            {
-              Fetched f = fetch_general(p, st[k], e);
-              consume(p, f, acc[k]);
-            }
-          }
-        }
-      }
-
-      // ---- cross-warp reduction: s_red[((warp*TPT + k)*4 + c)*32 + lane] ----
-      #pragma unroll
-      for(int k = 0; k < TPT; ++k)
-      {
-        #pragma unroll
-        for(int c = 0; c < 4; ++c)
-          s_red[((warp * TPT + k) * 4 + c) * 32 + lane] = acc[k][c];
-      }
-
-      __syncthreads();
-
-      if (tid < 32 * TPT)
-      {
-        const int k = tid >> 5;
-
-        float sum[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-        #pragma unroll
-        for(int w = 0; w < NW; ++w)
-        {
-          #pragma unroll
-          for(int c = 0; c < 4; ++c)
-            sum[c] += s_red[((w * TPT + k) * 4 + c) * 32 + lane];
-        }
-
-        int x, row;
-        if (tile_texel<TW, TPT>(p, tile, lane, k, x, row))
-        {
-          // sum/totalweight of ibl.cpp:186, then rgbe() of ibl.cpp:269
-          float r = (sum[0] - sum[3]) * p.norm;
-          float g = (sum[1] - sum[3]) * p.norm;
-          float b = (sum[2] - sum[3]) * p.norm;
-
-          size_t o = (size_t)row * p.wd + x;
-
-          if (p.dst_words)
-            p.dst_words[o] = rgbe_encode(r, g, b);
-
-          if (p.dst_f32)
-          {
-            p.dst_f32[3*o + 0] = r;
-            p.dst_f32[3*o + 1] = g;
-            p.dst_f32[3*o + 2] = b;
-          }
-        }
-      }
-
-      __syncthreads();
-    }
-  }
-
   // ---- host-side launchers -----------------------------------------------------
 
   namespace
   {
-    template<int TW, int TPT, int NW, int UNROLL, bool PIPE, int MINB>
-    cudaError_t launch_variant(PrefilterParams p, int sm_count, cudaStream_t stream, int *launched_grid)
-    {
-      constexpr int TH = 32 / TW;
-      auto kernel = prefilter_level_kernel<TW, TPT, NW, UNROLL, PIPE, MINB>;
-
-      int rows = p.row_end - p.row_begin;
-      if (p.wd >= TW)
-      {
-        p.tiles_x = (p.wd + TW - 1) / TW;
-        p.tiles = p.tiles_x * ((rows + TH * TPT - 1) / (TH * TPT));
-      }
-      else
-      {
-        p.tiles_x = 0;
-        p.tiles = (rows * p.wd + 32 * TPT - 1) / (32 * TPT);
-      }
-
-      size_t smem = (size_t)p.table_count * sizeof(float4) + (size_t)NW * TPT * 4 * 32 * sizeof(float);
-
-      cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (err != cudaSuccess)
-        return err;
-
-      int resident = 0;
-      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 32 * NW, smem);
-      if (err != cudaSuccess)
-        return err;
-      if (resident < 1)
-        return cudaErrorLaunchOutOfResources;
-
-      int grid = p.tiles < sm_count * resident ? p.tiles : sm_count * resident;
-      if (grid < 1)
-        grid = 1;
-
-      kernel<<<grid, 32 * NW, smem, stream>>>(p);
-
-      if (launched_grid)
-        *launched_grid = grid;
-
-      return cudaGetLastError();
-    }
-  }
-
-  namespace
-  {
-    template<int TW, int TPT, int NW, int UNROLL, int MINB, int ABLATE = 0>
+    template<int TW, int TPT, int NW, int UNROLL, int MINB>
     cudaError_t launch_packed(PrefilterParams p, int sm_count, cudaStream_t stream, int *launched_grid)
     {
       constexpr int TH = 32 / TW;
-      auto kernel = prefilter_level_packed_kernel<TW, TPT, NW, UNROLL, MINB, ABLATE>;
+      auto kernel = prefilter_level_packed_kernel<TW, TPT, NW, UNROLL, MINB>;
 
       int rows = p.row_end - p.row_begin;
       if (p.wd >= TW)
@@ -777,32 +436,10 @@ namespace ibl
 
     switch (variant)
     {
-      case 1: return launch_variant<8, 2, 8, 2, false, 1>(p, sm_count, stream, launched_grid);
-      case 2: return launch_variant<8, 1, 16, 2, true, 1>(p, sm_count, stream, launched_grid);
-      case 3: return launch_variant<8, 1, 8, 1, true, 1>(p, sm_count, stream, launched_grid);
-      case 4: return launch_variant<8, 1, 8, 2, true, 1>(p, sm_count, stream, launched_grid);
-      case 5: return launch_variant<8, 1, 8, 2, true, 5>(p, sm_count, stream, launched_grid);
-      case 6: return launch_variant<8, 1, 8, 2, false, 1>(p, sm_count, stream, launched_grid);
-      case 7: return launch_variant<8, 1, 8, 2, true, 4>(p, sm_count, stream, launched_grid);
-      case 8: return launch_variant<8, 2, 8, 1, true, 1>(p, sm_count, stream, launched_grid);
-      case 9: return launch_variant<8, 2, 8, 1, true, 3>(p, sm_count, stream, launched_grid);
       case 10: return launch_packed<8, 1, 8, 2, 1>(p, sm_count, stream, launched_grid);
-      case 11: return launch_packed<8, 2, 8, 2, 1>(p, sm_count, stream, launched_grid);
-      case 12: return launch_packed<8, 1, 8, 4, 1>(p, sm_count, stream, launched_grid);
-      case 13: return launch_packed<8, 2, 8, 1, 1>(p, sm_count, stream, launched_grid);
       case 14: return launch_packed<8, 1, 16, 2, 1>(p, sm_count, stream, launched_grid);
-      case 15: return launch_packed<16, 1, 8, 2, 1>(p, sm_count, stream, launched_grid);
-      case 16: return launch_packed<8, 1, 8, 1, 4>(p, sm_count, stream, launched_grid);
       case 17: return launch_packed<8, 1, 8, 2, 4>(p, sm_count, stream, launched_grid);
-      case 18: return launch_packed<8, 1, 8, 1, 5>(p, sm_count, stream, launched_grid);
       case 19: return launch_packed<8, 1, 4, 2, 8>(p, sm_count, stream, launched_grid);
-      case 20: return launch_packed<8, 1, 4, 1, 10>(p, sm_count, stream, launched_grid);
-      case 21: return launch_packed<8, 2, 8, 2, 1, 1>(p, sm_count, stream, launched_grid);
-      case 22: return launch_packed<8, 2, 8, 2, 1, 2>(p, sm_count, stream, launched_grid);
-      case 23: return launch_packed<8, 2, 8, 2, 1, 3>(p, sm_count, stream, launched_grid);
-      case 24: return launch_packed<8, 2, 8, 1, 3>(p, sm_count, stream, launched_grid);
-      case 25: return launch_packed<8, 1, 16, 1, 2>(p, sm_count, stream, launched_grid);
-      case 26: return launch_packed<8, 2, 4, 1, 6>(p, sm_count, stream, launched_grid);
       case 27: return launch_packed<8, 1, 32, 1, 1>(p, sm_count, stream, launched_grid);
       default: return cudaErrorInvalidValue;
     }

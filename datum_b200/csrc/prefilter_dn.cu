@@ -1,0 +1,489 @@
+// datum_b200 — GGX prefilter of one cube-map mip level, "denormal mantissa" kernel (sm_100a).
+//
+// Replaces the triple loop of tools/ibl.cpp:263-272 and the per-texel sample loop of
+// tools/ibl.cpp:160-187 (reference paths relative to /root/reference).  This is the kernel the
+// library uses for every level at least 8 texels wide; narrower levels go to prefilter.cu.
+//
+// What one bilinear tap costs decides the speed of this loop (profiles/): the first kernel
+// (prefilter.cu) turned each 9-bit mantissa into a float with shift + mask logic, six ALU-pipe ops
+// per tap on a half-rate pipe.  Here
+//
+//   * a quad record still holds the four E5B9G9R9 words of a footprint (16 bytes, one LDG.128),
+//     re-laid as r<<23 | g<<14 | b<<5 | E (pack_dn_word);
+//   * a mantissa is used as the fp32 number its bits spell under a zero exponent field: a
+//     SUBNORMAL, m * 2^-149 times a per-channel power of two.  FFMA consumes subnormal operands
+//     exactly and at full rate, so "decode" is one AND (g, b) or one shift (r) and the channel
+//     scale moves into the final normalisation;
+//   * the shared exponent goes into the tap's bilinear weight: w * 2^E is one integer
+//     multiply-add on the weight's exponent field (IMAD, FMA pipe), exact;
+//   * no bias accumulator, fp32 weights, exact products: the arithmetic of tools/ibl.cpp:34-41
+//     up to summation order.  Four logic ops + one IMAD per tap instead of six logic ops, and
+//     six packed FMAs per sample instead of eight.
+//
+// Around that loop:
+//   * the sample table is banded (ibl_tables.h): bands of kSampleBand entries of the lobe-angle
+//     order, ring-ordered inside; the warps of a tile each take a quarter arc of every band.  The
+//     same-face test (no cube-face selection needed) is made per band;
+//   * tiles are numbered in 4x4 blocks and, for big levels, handed out from per-SM queues so that
+//     the CTAs resident on one SM work on neighbouring tiles and share the lobe's footprint in L1
+//     (measured: L1 hit rate 38 % -> 68 % on the 512^2 -> 256^2 level).
+
+#include "prefilter.h"
+#include "ibl_math.cuh"
+
+#include <cuda_runtime.h>
+
+namespace ibl
+{
+  typedef unsigned long long f32x2;
+
+  namespace
+  {
+    // packed two-wide fp32 (fma.rn.f32x2 -> SASS FFMA2/FMUL2/FADD2): same lanes as two scalar
+    // ops, one issue slot; every element is rounded exactly like the scalar form
+    __device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+    __device__ __forceinline__ void unpack2(f32x2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
+    __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+    __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+    __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+    __device__ __forceinline__ f32x2 bcast2(float v) { return pack2(v, v); }
+
+    // bits(w) + E * 2^23 == bits(w * 2^E).  The multiplier arrives as a kernel parameter: as a
+    // literal the compiler lowers it to shift + add on the ALU pipe, the pipe this loop is short of.
+    __device__ __forceinline__ float scale_by_exponent(float w, uint32_t e, uint32_t emul)
+    {
+      uint32_t r;
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(e), "r"(emul), "r"(f2u(w)));
+      return u2f(r);
+    }
+  }
+
+  // ---- quad records ----------------------------------------------------------------
+
+  __global__ void __launch_bounds__(256) build_dn_records_kernel(uint32_t const *__restrict__ src, uint4 *__restrict__ rec, int ws, int hs, int *__restrict__ counters, int ncounters)
+  {
+    // the prefilter launch that follows on the stream takes its tiles from these queues
+    if (blockIdx.x == 0)
+      for(int i = threadIdx.x; i < ncounters; i += blockDim.x)
+        counters[i] = 0;
+
+    size_t total = (size_t)6 * ws * hs;
+    for(size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    {
+      int i = (int)(idx % ws);
+      int j = (int)((idx / ws) % hs);
+      size_t right = (i + 1 < ws) ? 1 : 0;      // neighbours clamped inside the face; the clamped
+      size_t down = (j + 1 < hs) ? (size_t)ws : 0; // ones are never addressed (i <= ws-2, j <= hs-2)
+
+      uint4 r;
+      r.x = pack_dn_word(__ldg(src + idx));
+      r.y = pack_dn_word(__ldg(src + idx + right));
+      r.z = pack_dn_word(__ldg(src + idx + down));
+      r.w = pack_dn_word(__ldg(src + idx + down + right));
+      rec[idx] = r;
+    }
+  }
+
+  // ---- one sample of one texel -------------------------------------------------------
+
+  struct TexelFrame
+  {
+    Vec3f T, B, N;      // tangent frame rows: face-local and pre-scaled for the same-face loop, world for the general loop
+    uint32_t face_base; // face*face_size - bias
+    int face;
+  };
+
+  struct Sums
+  {
+    f32x2 rg, bb;       // (r, g) and two partial b sums
+  };
+
+  // weights of the 2x2 footprint (tools/ibl.cpp:40 as four products), exponents folded in, taps accumulated
+  __device__ __forceinline__ void accumulate(uint4 rec, float du, float dv, float nl, float wh, uint32_t emul, Sums &acc)
+  {
+    float u0 = 0.5f - du, u1 = 0.5f + du;
+    float v0 = fmaf(-dv, nl, wh), v1 = fmaf(dv, nl, wh);
+
+    f32x2 u = pack2(u0, u1);
+    float w00, w10, w01, w11;
+    unpack2(mul2(u, bcast2(v0)), w00, w10);
+    unpack2(mul2(u, bcast2(v1)), w01, w11);
+
+    w00 = scale_by_exponent(w00, rec.x & kDnMaskE, emul);
+    w10 = scale_by_exponent(w10, rec.y & kDnMaskE, emul);
+    w01 = scale_by_exponent(w01, rec.z & kDnMaskE, emul);
+    w11 = scale_by_exponent(w11, rec.w & kDnMaskE, emul);
+
+    acc.rg = fma2(pack2(u2f(rec.x >> 23), u2f(rec.x & kDnMaskG)), bcast2(w00), acc.rg);
+    acc.rg = fma2(pack2(u2f(rec.y >> 23), u2f(rec.y & kDnMaskG)), bcast2(w10), acc.rg);
+    acc.rg = fma2(pack2(u2f(rec.z >> 23), u2f(rec.z & kDnMaskG)), bcast2(w01), acc.rg);
+    acc.rg = fma2(pack2(u2f(rec.w >> 23), u2f(rec.w & kDnMaskG)), bcast2(w11), acc.rg);
+    acc.bb = fma2(pack2(u2f(rec.x & kDnMaskB), u2f(rec.y & kDnMaskB)), pack2(w00, w10), acc.bb);
+    acc.bb = fma2(pack2(u2f(rec.z & kDnMaskB), u2f(rec.w & kDnMaskB)), pack2(w01, w11), acc.bb);
+  }
+
+  // sample whose reflected direction provably stays on the texel's own face: frame rows are in
+  // face-local (a, b, m) coordinates with a, b pre-scaled to source texels (face_footprint of ibl_math.cuh,
+  // the (a, b) pair carried packed)
+  __device__ __forceinline__ void sample_same_face(PrefilterDnParams const &p, TexelFrame const &t, float4 e, Sums &acc)
+  {
+    f32x2 lab = mul2(bcast2(e.x), pack2(t.T.x, t.T.y));
+    lab = fma2(bcast2(e.y), pack2(t.B.x, t.B.y), lab);
+    lab = fma2(bcast2(e.z), pack2(t.N.x, t.N.y), lab);
+    float lm = fmaf(e.z, t.N.z, fmaf(e.y, t.B.z, e.x * t.T.z));
+
+    float r = rcp_fast(lm);
+    f32x2 f = fma2(lab, bcast2(r), pack2(p.geom.hwm, p.geom.hhm));
+    f32x2 m = add2(f, bcast2(kMagic));
+    f32x2 fi = add2(m, bcast2(-kMagic));
+    f32x2 d = fma2(fi, bcast2(-1.0f), f);
+
+    float mu, mv, du, dv;
+    unpack2(m, mu, mv);
+    unpack2(d, du, dv);
+
+    uint32_t idx = f2u(mv) * (uint32_t)p.geom.ws + f2u(mu) + t.face_base;
+
+    accumulate(__ldg(p.records + idx), du, dv, e.z, e.w, p.exp_mul, acc);
+  }
+
+  // any direction: cube face selection of tools/ibl.cpp:43-88 (cube_footprint of ibl_math.cuh)
+  __device__ __forceinline__ void sample_general(PrefilterDnParams const &p, TexelFrame const &t, float4 e, Sums &acc)
+  {
+    float Lx = fmaf(e.z, t.N.x, fmaf(e.y, t.B.x, e.x * t.T.x));
+    float Ly = fmaf(e.z, t.N.y, fmaf(e.y, t.B.y, e.x * t.T.y));
+    float Lz = fmaf(e.z, t.N.z, fmaf(e.y, t.B.z, e.x * t.T.z));
+
+    float du, dv;
+    uint32_t idx = cube_footprint(p.geom, Lx, Ly, Lz, du, dv);
+
+    accumulate(__ldg(p.records + idx), du, dv, e.z, e.w, p.exp_mul, acc);
+  }
+
+  // ---- tiles ----------------------------------------------------------------------------
+  //
+  // Tiles of 8x4 texels are numbered in 4x4-blocked order over the slab.  With QUEUES the first
+  // `queued` tiles are cut into one contiguous chunk per SM (queue index = %smid) and the rest form
+  // a common pool that evens out the tail: a group takes tiles from its SM's chunk, then from the pool.
+  __device__ __forceinline__ int next_tile(PrefilterDnParams const &p, uint32_t smid)
+  {
+    if ((int)smid < p.queues)
+    {
+      int k = atomicAdd(p.counters + smid, 1);
+      if (k < p.chunk)
+        return (int)smid * p.chunk + k;
+    }
+
+    int tile = p.queued + atomicAdd(p.counters + p.queues, 1);
+    return tile < p.tiles ? tile : -1;
+  }
+
+  // tile number -> texel of this lane; false when the lane's texel is outside the slab
+  __device__ __forceinline__ bool tile_texel(PrefilterDnParams const &p, int tile, int lane, int &x, int &row)
+  {
+    int block = tile >> 4, in = tile & 15;
+    int bx = block % p.blocks_x, by = block / p.blocks_x;
+    x = (bx * 4 + (in & 3)) * 8 + (lane & 7);
+    row = p.row_begin + (by * 4 + (in >> 2)) * 4 + (lane >> 3);
+    return x < p.wd && row < p.row_end;
+  }
+
+  // ---- the kernel --------------------------------------------------------------------------
+  //
+  // CTA = NW warps sharing one tile at a time; warp w takes entries [w*PER, (w+1)*PER) of every
+  // band, partial sums meet in shared memory.  Big levels use 4 warps per tile (most CTAs per SM,
+  // cheapest reduction), small ones 8, 16 or 32 so that the few tiles still spread over the machine.
+  template<int NW, int UNROLL, int MINB, bool SMEM_TABLE, bool QUEUES>
+  __global__ void __launch_bounds__(32 * NW, MINB) prefilter_dn_kernel(PrefilterDnParams p)
+  {
+    extern __shared__ float4 smem[];
+    float4 *s_table = smem;
+    float *s_red = reinterpret_cast<float*>(smem + (SMEM_TABLE ? p.table_count : 0));
+    int *s_tile = reinterpret_cast<int*>(s_red + NW * 3 * 32);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    if (SMEM_TABLE)
+    {
+      for(int i = tid; i < p.table_count; i += 32 * NW)
+        s_table[i] = __ldg(p.table + i);
+      __syncthreads();
+    }
+
+    float4 const *table = SMEM_TABLE ? s_table : p.table;
+
+    uint32_t smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+
+    constexpr int PER = kSampleBand / NW > 0 ? kSampleBand / NW : 1;   // entries of a band per warp
+    constexpr int SPLIT = kSampleBand / PER;                            // warps that share a band (NW or kSampleBand)
+    static_assert(NW % SPLIT == 0, "warps per tile must be a multiple of the band split");
+
+    // with more warps than band entries, consecutive groups of SPLIT warps take alternate bands
+    const int lane_warp = warp % SPLIT;
+    const int band_first = warp / SPLIT;
+    constexpr int BAND_STEP = NW / SPLIT;
+
+    for(int it = 0; ; ++it)
+    {
+      int tile;
+      if (QUEUES)
+      {
+        if (tid == 0)
+          *s_tile = next_tile(p, smid);
+        __syncthreads();
+        tile = *s_tile;
+      }
+      else
+      {
+        tile = (int)blockIdx.x + it * (int)gridDim.x;
+        if (tile >= p.tiles)
+          tile = -1;
+      }
+
+      if (tile < 0)
+        break;
+
+      int x, row;
+      bool valid = tile_texel(p, tile, lane, x, row);
+
+      // the blocked numbering covers whole 4x4 blocks: a tile past the slab has no work
+      if (__ballot_sync(0xffffffffu, valid) == 0u)
+      {
+        if (QUEUES)
+          __syncthreads();   // s_tile is rewritten in the next round
+        continue;
+      }
+
+      // lanes past the slab still walk the loops (their sums are dropped): park them on a face centre
+      if (!valid) { x = p.wd >> 1; row = (p.row_begin / p.hd) * p.hd + (p.hd >> 1); }
+
+      int face = row / p.hd;
+      int y = row - face * p.hd;
+
+      TexelFrame st;
+      int n_same;
+      {
+        Vec3f N = texel_normal(p.quats[face], x, y, p.wd, p.hd);
+        Vec3f T, B;
+        tangent_frame(N, T, B);
+
+        // face-local rows, a and b scaled to source texels (align-corners, ibl.cpp:37-38)
+        Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
+
+        float threshold = same_face_threshold(Nl);
+        threshold = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(threshold)));
+
+        st.T = Vec3f{ Tl.x * p.geom.hw, Tl.y * p.geom.hh, Tl.z };
+        st.B = Vec3f{ Bl.x * p.geom.hw, Bl.y * p.geom.hh, Bl.z };
+        st.N = Vec3f{ Nl.x * p.geom.hw, Nl.y * p.geom.hh, Nl.z };
+        st.face = face;
+        st.face_base = (uint32_t)face * p.geom.face_size - p.geom.bias;
+
+        // number of leading bands (smallest angles) whose samples all stay on every texel's own face
+        int lo = 0, hi = p.bands;
+        while (lo < hi)
+        {
+          int mid = (lo + hi) >> 1;
+          if (__ldg(p.band_min_lz + mid) > threshold)
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        n_same = lo;
+      }
+
+      Sums acc;
+      acc.rg = 0ull;
+      acc.bb = 0ull;
+
+      const int full_bands = p.table_count / kSampleBand;
+      const int same_full = n_same < full_bands ? n_same : full_bands;
+
+      int band = band_first;
+
+      for(; band < same_full; band += BAND_STEP)
+      {
+        float4 const *tb = table + band * kSampleBand + lane_warp * PER;
+
+        #pragma unroll UNROLL
+        for(int k = 0; k < PER; ++k)
+          sample_same_face(p, st, SMEM_TABLE ? tb[k] : __ldg(tb + k), acc);
+      }
+
+      // the short last band, when it also stays on the face
+      if (band == full_bands && n_same > full_bands)
+      {
+        for(int s = band * kSampleBand + lane_warp * PER, k = 0; k < PER && s < p.table_count; ++k, ++s)
+          sample_same_face(p, st, SMEM_TABLE ? table[s] : __ldg(table + s), acc);
+        band += BAND_STEP;
+      }
+
+      if (band < p.bands)
+      {
+        // back to world coordinates for the samples that may cross a face edge
+        st.T = from_face_local(st.face, Vec3f{ st.T.x * p.geom.inv_hw, st.T.y * p.geom.inv_hh, st.T.z });
+        st.B = from_face_local(st.face, Vec3f{ st.B.x * p.geom.inv_hw, st.B.y * p.geom.inv_hh, st.B.z });
+        st.N = from_face_local(st.face, Vec3f{ st.N.x * p.geom.inv_hw, st.N.y * p.geom.inv_hh, st.N.z });
+
+        for(; band < full_bands; band += BAND_STEP)
+        {
+          float4 const *tb = table + band * kSampleBand + lane_warp * PER;
+
+          #pragma unroll UNROLL
+          for(int k = 0; k < PER; ++k)
+            sample_general(p, st, SMEM_TABLE ? tb[k] : __ldg(tb + k), acc);
+        }
+
+        if (band == full_bands && band < p.bands)
+        {
+          for(int s = band * kSampleBand + lane_warp * PER, k = 0; k < PER && s < p.table_count; ++k, ++s)
+            sample_general(p, st, SMEM_TABLE ? table[s] : __ldg(table + s), acc);
+        }
+      }
+
+      // ---- reduction over the CTA's warps: s_red[(warp*3 + c)*32 + lane] ----
+      float a[4];
+      unpack2(acc.rg, a[0], a[1]);
+      unpack2(acc.bb, a[2], a[3]);
+      a[2] += a[3];
+
+      #pragma unroll
+      for(int c = 0; c < 3; ++c)
+        s_red[(warp * 3 + c) * 32 + lane] = a[c];
+
+      __syncthreads();
+
+      if (warp == 0)
+      {
+        float sum[3] = { 0.0f, 0.0f, 0.0f };
+        #pragma unroll
+        for(int w = 0; w < NW; ++w)
+        {
+          #pragma unroll
+          for(int c = 0; c < 3; ++c)
+            sum[c] += s_red[(w * 3 + c) * 32 + lane];
+        }
+
+        if (valid)
+        {
+          // sum/totalweight of ibl.cpp:186, then rgbe() of ibl.cpp:269
+          float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
+          size_t o = (size_t)row * p.wd + x;
+
+          if (p.dst_words)
+            p.dst_words[o] = rgbe_encode(r, g, b);
+
+          if (p.dst_f32)
+          {
+            p.dst_f32[3*o + 0] = r;
+            p.dst_f32[3*o + 1] = g;
+            p.dst_f32[3*o + 2] = b;
+          }
+        }
+      }
+
+      __syncthreads();   // s_red and s_tile are reused by the next tile
+    }
+  }
+
+  // ---- host-side launchers ---------------------------------------------------------------
+
+  cudaError_t launch_build_dn_records(uint32_t const *src, uint4 *rec, int ws, int hs, int *counters, int ncounters, int sm_count, cudaStream_t stream)
+  {
+    size_t total = (size_t)6 * ws * hs;
+    size_t blocks = (total + 255) / 256;
+    size_t cap = (size_t)sm_count * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    if (grid < 1)
+      grid = 1;
+
+    build_dn_records_kernel<<<grid, 256, 0, stream>>>(src, rec, ws, hs, counters, ncounters);
+
+    return cudaGetLastError();
+  }
+
+  namespace
+  {
+    template<int NW, int UNROLL, int MINB, bool SMEM_TABLE, bool QUEUES>
+    cudaError_t launch_dn(PrefilterDnParams p, int sm_count, cudaStream_t stream, int *launched_grid)
+    {
+      auto kernel = prefilter_dn_kernel<NW, UNROLL, MINB, SMEM_TABLE, QUEUES>;
+
+      int rows = p.row_end - p.row_begin;
+      int tiles_x = (p.wd + 7) / 8, tiles_y = (rows + 3) / 4;
+      p.blocks_x = (tiles_x + 3) / 4;
+      p.tiles = p.blocks_x * ((tiles_y + 3) / 4) * 16;
+
+      size_t smem = (SMEM_TABLE ? (size_t)p.table_count * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
+
+      cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err != cudaSuccess)
+        return err;
+
+      int resident = 0;
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 32 * NW, smem);
+      if (err != cudaSuccess)
+        return err;
+      if (resident < 1)
+        return cudaErrorLaunchOutOfResources;
+
+      int grid = p.tiles < sm_count * resident ? p.tiles : sm_count * resident;
+      if (grid < 1)
+        grid = 1;
+
+      // queues: 7/8 of the tiles in per-SM chunks, the rest in the common pool
+      p.queues = sm_count;
+      p.chunk = (p.tiles - p.tiles / 8) / sm_count;
+      p.queued = p.chunk * sm_count;
+
+      kernel<<<grid, 32 * NW, smem, stream>>>(p);
+
+      if (launched_grid)
+        *launched_grid = grid;
+
+      return cudaGetLastError();
+    }
+  }
+
+  cudaError_t launch_prefilter_dn(PrefilterDnParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid)
+  {
+    int rows = p.row_end - p.row_begin;
+    if (rows <= 0 || p.wd <= 0)
+      return cudaSuccess;
+
+    // Automatic choice by slab size (measured on C2, tools/level_times.py).  A table beyond ~1100
+    // entries (4096-sample bakes) would cost too much shared memory per CTA: read it through L1.
+    if (variant == 0)
+    {
+      size_t texels = (size_t)rows * p.wd;
+      bool big_table = p.table_count > 1100;
+
+      if (texels >= 32u * 148u * 8u)
+        variant = big_table ? 52 : 51;
+      else if (texels >= 32u * 148u * 2u)
+        variant = big_table ? 54 : 53;
+      else if (texels >= 32u * 48u)
+        variant = big_table ? 56 : 55;
+      else
+        variant = big_table ? 58 : 57;
+    }
+
+    switch (variant)
+    {
+      //                        NW UNR MINB SMEM  QUEUES
+      case 50: return launch_dn<4, 4, 8, true, false>(p, sm_count, stream, launched_grid);
+      case 51: return launch_dn<4, 4, 8, true, true>(p, sm_count, stream, launched_grid);
+      case 52: return launch_dn<4, 4, 8, false, true>(p, sm_count, stream, launched_grid);
+      case 53: return launch_dn<8, 2, 4, true, false>(p, sm_count, stream, launched_grid);
+      case 54: return launch_dn<8, 2, 4, false, false>(p, sm_count, stream, launched_grid);
+      case 55: return launch_dn<16, 1, 2, true, false>(p, sm_count, stream, launched_grid);
+      case 56: return launch_dn<16, 1, 2, false, false>(p, sm_count, stream, launched_grid);
+      case 57: return launch_dn<32, 1, 1, true, false>(p, sm_count, stream, launched_grid);
+      case 58: return launch_dn<32, 1, 1, false, false>(p, sm_count, stream, launched_grid);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+}

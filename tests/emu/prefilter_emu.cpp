@@ -1,9 +1,10 @@
 // TEST INFRASTRUCTURE — host build of the kernel's per-sample math.
 //
 // Compiles datum_b200/csrc/ibl_math.cuh and ibl_tables.cpp with g++ and runs
-// the same per-texel loop the CUDA prefilter kernel runs (table-driven reflected
-// direction, magic-add floor, quad-record addressing, biased-mantissa
-// accumulation), single-threaded and in table order.  tests/test_kernel_math_cpu.py
+// the same per-texel loops the CUDA prefilter kernels run (table-driven reflected
+// direction, magic-add floor, quad-record addressing; biased-mantissa accumulation
+// for prefilter.cu, subnormal-mantissa accumulation over the banded table for
+// prefilter_dn.cu), single-threaded and in table order.  tests/test_kernel_math_cpu.py
 // compares it with the oracle so that algorithmic mistakes are caught on the
 // CPU-only CI leg.  It is NOT a fallback: nothing under datum_b200/ builds,
 // links or loads it.
@@ -128,6 +129,148 @@ extern "C" void emu_prefilter_level(uint32_t const *src, int ws, int hs, int lev
   }
 
   g_fast_fraction = total ? (double)fast / (double)total : 0.0;
+}
+
+// The same level through the math of prefilter_dn.cu: banded ring-ordered table scaled by 2^64,
+// per-band same-face decision, quad records re-laid by pack_dn_word, subnormal-mantissa taps with
+// the exponent folded into the weight, per-channel normalisation.
+extern "C" void emu_prefilter_level_dn(uint32_t const *src, int ws, int hs, int level, int levels, int samples, int band, uint32_t *words, float *f32)
+{
+  BandedSamples banded = build_banded_samples(level, levels, samples, band);
+  std::vector<SampleEntry> table = banded.level.entries;
+  for(auto &e : table)
+  {
+    e.lx *= kDnTableScale; e.ly *= kDnTableScale; e.lz *= kDnTableScale; e.wh *= kDnTableScale;
+  }
+  LevelGeom geom = make_level_geom(ws, hs);
+
+  const float kPi = 3.14159265358979323846f;
+  float angles[6] = { -kPi/2, kPi/2, -kPi/2, kPi/2, 0.0f, kPi };
+  int axes[6] = { 1, 1, 0, 0, 1, 1 };
+  Quatf quats[6];
+  for(int f = 0; f < 6; ++f)
+  {
+    float c = std::cos(angles[f]/2), s = std::sin(angles[f]/2);
+    quats[f] = Quatf{ c, axes[f] == 0 ? s : 0.0f, axes[f] == 1 ? s : 0.0f, 0.0f };
+  }
+
+  int wd = ws >> 1, hd = hs >> 1;
+  float norm[3];
+  dn_channel_norms(banded.level.total_weight, norm);
+
+  struct Rec { uint32_t x, y, z, w; };
+  std::vector<Rec> records((size_t)6 * ws * hs);
+  for(size_t idx = 0; idx < records.size(); ++idx)
+  {
+    int i = (int)(idx % ws), j = (int)((idx / ws) % hs);
+    size_t right = (i + 1 < ws) ? 1 : 0, down = (j + 1 < hs) ? (size_t)ws : 0;
+    records[idx] = Rec{ pack_dn_word(src[idx]), pack_dn_word(src[idx + right]), pack_dn_word(src[idx + down]), pack_dn_word(src[idx + down + right]) };
+  }
+
+  long fast = 0, total = 0;
+
+  for(int face = 0; face < 6; ++face)
+  {
+    for(int y = 0; y < hd; ++y)
+    {
+      for(int x = 0; x < wd; ++x)
+      {
+        Vec3f N = texel_normal(quats[face], x, y, wd, hd);
+        Vec3f T, B;
+        tangent_frame(N, T, B);
+
+        Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
+        float threshold = getenv("EMU_NOFAST") ? 2.0f : same_face_threshold(Nl);
+
+        Vec3f Ts = { Tl.x * geom.hw, Tl.y * geom.hh, Tl.z };
+        Vec3f Bs = { Bl.x * geom.hw, Bl.y * geom.hh, Bl.z };
+        Vec3f Ns = { Nl.x * geom.hw, Nl.y * geom.hh, Nl.z };
+        uint32_t face_base = (uint32_t)face * geom.face_size - geom.bias;
+
+        Vec3f Tw = from_face_local(face, Vec3f{ Ts.x * geom.inv_hw, Ts.y * geom.inv_hh, Ts.z });
+        Vec3f Bw = from_face_local(face, Vec3f{ Bs.x * geom.inv_hw, Bs.y * geom.inv_hh, Bs.z });
+        Vec3f Nw = from_face_local(face, Vec3f{ Ns.x * geom.inv_hw, Ns.y * geom.inv_hh, Ns.z });
+
+        float acc[3] = { 0, 0, 0 };
+
+        for(size_t i = 0; i < table.size(); ++i)
+        {
+          SampleEntry const &e = table[i];
+          bool same = banded.band_min_lz[i / (size_t)band] > threshold;
+
+          float du, dv;
+          uint32_t idx;
+
+          if (same)
+          {
+            float la = fmaf(e.lz, Ns.x, fmaf(e.ly, Bs.x, e.lx * Ts.x));
+            float lb = fmaf(e.lz, Ns.y, fmaf(e.ly, Bs.y, e.lx * Ts.y));
+            float lm = fmaf(e.lz, Ns.z, fmaf(e.ly, Bs.z, e.lx * Ts.z));
+            idx = face_footprint(geom, face_base, la, lb, lm, du, dv);
+            ++fast;
+          }
+          else
+          {
+            float Lx = fmaf(e.lz, Nw.x, fmaf(e.ly, Bw.x, e.lx * Tw.x));
+            float Ly = fmaf(e.lz, Nw.y, fmaf(e.ly, Bw.y, e.lx * Tw.y));
+            float Lz = fmaf(e.lz, Nw.z, fmaf(e.ly, Bw.z, e.lx * Tw.z));
+            idx = cube_footprint(geom, Lx, Ly, Lz, du, dv);
+          }
+          ++total;
+
+          if (idx >= records.size())
+            __builtin_trap();
+
+          float w[4];
+          footprint_weights(du, dv, e.wh, e.lz, w);
+
+          Rec const &rec = records[idx];
+          dn_accumulate_tap(rec.x, w[0], acc);
+          dn_accumulate_tap(rec.y, w[1], acc);
+          dn_accumulate_tap(rec.z, w[2], acc);
+          dn_accumulate_tap(rec.w, w[3], acc);
+        }
+
+        float r = acc[0] * norm[0], g = acc[1] * norm[1], b = acc[2] * norm[2];
+
+        size_t o = ((size_t)face * hd + y) * wd + x;
+        if (words)
+          words[o] = rgbe_encode(r, g, b);
+        if (f32)
+        {
+          f32[3*o + 0] = r; f32[3*o + 1] = g; f32[3*o + 2] = b;
+        }
+      }
+    }
+  }
+
+  g_fast_fraction = total ? (double)fast / (double)total : 0.0;
+}
+
+// banded table as the dn kernel sees it (unscaled): entries, per-band minimum lz; returns the entry count
+extern "C" int emu_banded_table(int level, int levels, int samples, int band, float *entries, float *band_min, int *bands)
+{
+  BandedSamples banded = build_banded_samples(level, levels, samples, band);
+  for(size_t i = 0; i < banded.level.entries.size(); ++i)
+  {
+    entries[4*i + 0] = banded.level.entries[i].lx; entries[4*i + 1] = banded.level.entries[i].ly;
+    entries[4*i + 2] = banded.level.entries[i].lz; entries[4*i + 3] = banded.level.entries[i].wh;
+  }
+  for(size_t k = 0; k < banded.band_min_lz.size(); ++k)
+    band_min[k] = banded.band_min_lz[k];
+  *bands = (int)banded.band_min_lz.size();
+  return (int)banded.level.entries.size();
+}
+
+extern "C" uint32_t emu_pack_dn_word(uint32_t w) { return pack_dn_word(w); }
+
+// one tap through dn_accumulate_tap and the channel norms with total weight 1 and weight w: returns w * texel value
+extern "C" void emu_dn_tap(uint32_t rgbe_word, float w, float *rgb)
+{
+  float acc[3] = { 0, 0, 0 }, norm[3];
+  dn_accumulate_tap(pack_dn_word(rgbe_word), w * kDnTableScale, acc);
+  dn_channel_norms(1.0, norm);
+  rgb[0] = acc[0] * norm[0]; rgb[1] = acc[1] * norm[1]; rgb[2] = acc[2] * norm[2];
 }
 
 extern "C" double emu_last_fast_fraction() { return g_fast_fraction; }

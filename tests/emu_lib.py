@@ -22,6 +22,12 @@ def load():
             subprocess.check_call([gxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB] + SRC)
         lib = ctypes.CDLL(LIB)
         lib.emu_prefilter_level.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p] * 2
+        lib.emu_prefilter_level_dn.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2
+        lib.emu_banded_table.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3
+        lib.emu_banded_table.restype = ctypes.c_int
+        lib.emu_pack_dn_word.argtypes = [ctypes.c_uint32]
+        lib.emu_pack_dn_word.restype = ctypes.c_uint32
+        lib.emu_dn_tap.argtypes = [ctypes.c_uint32, ctypes.c_float, ctypes.c_void_p]
         lib.emu_last_fast_fraction.restype = ctypes.c_double
         lib.emu_rgbe_encode.restype = ctypes.c_uint32
         lib.emu_rgbe_encode.argtypes = [ctypes.c_float] * 3

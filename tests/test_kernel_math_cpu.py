@@ -84,6 +84,65 @@ def test_kernel_math_matches_oracle(ws, levels, level, noise):
     assert stats["max_code"] <= 1 and stats["exp_mismatch"] == 0 and stats["identical"] >= 0.99
 
 
+@pytest.mark.parametrize("ws,levels,level,noise", [(16, 5, 1, True), (16, 5, 4, True), (32, 6, 1, False), (32, 6, 2, True), (32, 6, 5, False), (8, 4, 3, True)])
+def test_dn_kernel_math_matches_oracle(ws, levels, level, noise):
+    """prefilter_dn.cu's arithmetic: banded table, subnormal-mantissa taps, exponent in the weight."""
+    emu = emu_lib.load()
+    src = synth.synthetic_chain(ws, ws, 1, probe=6, noise=noise, sun=False)
+    wd = ws // 2
+    n = 6 * wd * wd
+    want_words, want_f32 = oracle_lib.prefilter_level(src, ws, ws, level, levels, 1024)
+    got_words, got_f32 = np.zeros(n, np.uint32), np.zeros((n, 3), np.float32)
+    emu.emu_prefilter_level_dn(src.ctypes.data, ws, ws, level, levels, 1024, 16, got_words.ctypes.data, got_f32.ctypes.data)
+
+    clean = oracle_lib.edge_ambiguous_counts(wd, wd, level, levels, 1024) == 0
+    rel = oracle_lib.relative_error(got_f32, want_f32)
+    assert rel[clean].max() <= 1e-4
+    assert rel.max() <= 5e-2
+    stats = oracle_lib.word_stats(got_words[clean], want_words[clean])
+    assert stats["max_code"] <= 1 and stats["exp_mismatch"] == 0 and stats["identical"] >= 0.99
+
+
+def test_dn_tap_decodes_every_field_exactly():
+    """One tap of weight w through the subnormal-mantissa path == w * rgbe decode, for the
+    extreme exponents, mantissas and weights (products must stay in the normal range)."""
+    emu = emu_lib.load()
+    rng = np.random.default_rng(5)
+    words = [0x00000000, 0xFFFFFFFF, 0x00000001, 0xF8000001, 0x0003FE00, 0x07FC0000, 0x08000200, 31 << 27 | 511 << 18 | 511 << 9 | 511]
+    words += [int(w) for w in rng.integers(0, 2**32, 200, dtype=np.uint64)]
+    for word in words:
+        for w in (1.0, 0.5, 3.0e-5, 0.73, 1e-9):
+            got = np.zeros(3, np.float32)
+            want = np.zeros(3, np.float32)
+            emu.emu_dn_tap(word, w, got.ctypes.data)
+            emu.emu_rgbe_decode(word, want.ctypes.data)
+            assert np.allclose(got, want * np.float32(w), rtol=3e-7, atol=0.0), (hex(word), w, got, want)
+    m = emu.emu_pack_dn_word(5 << 27 | 3 << 18 | 2 << 9 | 1)
+    assert m == (1 << 23 | 2 << 14 | 3 << 5 | 5)
+
+
+@pytest.mark.parametrize("level,levels,samples,band", [(1, 8, 1024, 16), (5, 8, 1024, 16), (1, 12, 4096, 16), (2, 5, 16, 16), (3, 4, 7, 16)])
+def test_banded_table_is_the_sorted_table_cut_in_rings(level, levels, samples, band):
+    emu = emu_lib.load()
+    flat = np.zeros((samples, 4), np.float32)
+    total = np.zeros(1, np.float64)
+    n = emu.emu_table(level, levels, samples, flat.ctypes.data, total.ctypes.data)
+    flat = flat[:n]
+    entries = np.zeros((samples, 4), np.float32)
+    band_min = np.zeros(samples, np.float32)
+    bands = np.zeros(1, np.int32)
+    m = emu.emu_banded_table(level, levels, samples, band, entries.ctypes.data, band_min.ctypes.data, bands.ctypes.data)
+    entries, band_min = entries[:m], band_min[: bands[0]]
+    assert m == n and bands[0] == (n + band - 1) // band
+    for k in range(bands[0]):
+        a = flat[k * band:(k + 1) * band]
+        b = entries[k * band:(k + 1) * band]
+        assert sorted(map(tuple, a)) == sorted(map(tuple, b))                   # same entries per band
+        assert band_min[k] == a[:, 2].min()
+        assert np.all(np.diff(np.arctan2(b[:, 1].astype(np.float64), b[:, 0].astype(np.float64))) >= 0)   # ring order
+    assert np.all(np.diff(band_min) <= 0)
+
+
 def test_fast_path_is_taken_and_agrees_with_general_path(monkeypatch):
     emu = emu_lib.load()
     ws, levels, level = 64, 8, 1

@@ -119,10 +119,11 @@ def test_row_slabs_reproduce_the_full_level(ctx):
         assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 2e-5
         stats = oracle_lib.word_stats(slabs.cpu().numpy().view(np.uint32), full.cpu().numpy().view(np.uint32))
         assert oracle_lib.words_within_one_code(stats, 0.995), stats
-        # pinned variant: same warp split; only the same-face sample count of the re-cut tiles differs
-        full, full_f, slabs, slabs_f = run(17)
-        assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 5e-6
-        assert (full == slabs).float().mean().item() >= 0.999
+        # pinned variants (one of each kernel): same warp split; only the same-face sample count of the re-cut tiles differs
+        for variant in (17, 53):
+            full, full_f, slabs, slabs_f = run(variant)
+            assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 5e-6
+            assert (full == slabs).float().mean().item() >= 0.999
     finally:
         ctx.set_prefilter_variant(0)
 
@@ -134,7 +135,7 @@ def test_kernel_variants_agree(ctx):
     bits = synth.synthetic_chain(w, w, levels, probe=14, sun=False)
     base = None
     try:
-        for variant in (0, 1, 6, 10, 11, 14, 17, 19, 27):
+        for variant in (0, 10, 14, 17, 19, 27, 50, 51, 52, 53, 54, 55, 56, 57, 58):
             ctx.set_prefilter_variant(variant)
             words, f32 = run_chain_device(ctx, bits, w, w, levels, 1024)
             if base is None:
@@ -144,6 +145,28 @@ def test_kernel_variants_agree(ctx):
                 assert (words == base[0]).mean() >= 0.995
     finally:
         ctx.set_prefilter_variant(0)
+
+
+def test_directions_on_cube_edges_stay_inside_the_face(ctx):
+    """Regression: a reflected direction with two equal major components (|x| == |y| exactly)
+    and a reciprocal rounded up put the footprint one texel outside its face.  With 2048^2 faces
+    and 4096 samples some texel hits such a tie; the launch must complete and every word must be
+    a finite colour."""
+    ws, levels, samples = 2048, 3, 4096
+    src = synth.synthetic_chain(ws, ws, 1, probe=21, sun=False)
+    d_src = torch.from_numpy(src.view(np.int32)).to(DEV)
+    wd = ws // 2
+    for variant in (0, 19):
+        ctx.set_prefilter_variant(variant)
+        try:
+            out = torch.zeros(6 * wd * wd, dtype=torch.int32, device=DEV)
+            ctx.prefilter_level_device(d_src, ws, ws, 1, levels, samples, 0, 6 * wd, out)
+            ctx.synchronize()
+        finally:
+            ctx.set_prefilter_variant(0)
+        words = out.cpu().numpy().view(np.uint32)
+        rgb = oracle_lib.rgbe_decode_array(words)[:, :3]
+        assert np.isfinite(rgb).all() and rgb.max() <= 65408.0 and rgb.max() > 0.0
 
 
 def test_constant_environment_stays_constant_at_full_size(ctx):
