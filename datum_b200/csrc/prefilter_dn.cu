@@ -225,6 +225,7 @@ namespace ibl
     const int lane_warp = warp % SPLIT;
     const int band_first = warp / SPLIT;
     constexpr int BAND_STEP = NW / SPLIT;
+    constexpr int BAND_UNROLL = PER >= 4 ? 1 : 4 / PER;
 
     for(int it = 0; ; ++it)
     {
@@ -304,6 +305,8 @@ namespace ibl
 
       int band = band_first;
 
+      // a warp that owns one or two entries per band gets its independent work from several bands
+      #pragma unroll BAND_UNROLL
       for(; band < same_full; band += BAND_STEP)
       {
         float4 const *tb = table + band * kSampleBand + lane_warp * PER;
@@ -328,6 +331,7 @@ namespace ibl
         st.B = from_face_local(st.face, Vec3f{ st.B.x * p.geom.inv_hw, st.B.y * p.geom.inv_hh, st.B.z });
         st.N = from_face_local(st.face, Vec3f{ st.N.x * p.geom.inv_hw, st.N.y * p.geom.inv_hh, st.N.z });
 
+        #pragma unroll BAND_UNROLL
         for(; band < full_bands; band += BAND_STEP)
         {
           float4 const *tb = table + band * kSampleBand + lane_warp * PER;
