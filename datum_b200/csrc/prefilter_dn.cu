@@ -487,6 +487,12 @@ namespace ibl
       case 56: return launch_dn<16, 1, 2, false, false>(p, sm_count, stream, launched_grid);
       case 57: return launch_dn<32, 1, 1, true, false>(p, sm_count, stream, launched_grid);
       case 58: return launch_dn<32, 1, 1, false, false>(p, sm_count, stream, launched_grid);
+      case 60: return launch_dn<4, 2, 9, true, true>(p, sm_count, stream, launched_grid);
+      case 61: return launch_dn<4, 2, 10, true, true>(p, sm_count, stream, launched_grid);
+      case 62: return launch_dn<4, 4, 9, true, true>(p, sm_count, stream, launched_grid);
+      case 63: return launch_dn<4, 2, 8, true, true>(p, sm_count, stream, launched_grid);
+      case 64: return launch_dn<8, 2, 5, true, true>(p, sm_count, stream, launched_grid);
+      case 65: return launch_dn<4, 4, 10, true, true>(p, sm_count, stream, launched_grid);
       default: return cudaErrorInvalidValue;
     }
   }
