@@ -34,6 +34,8 @@ SIGNATURES = {
     "datum_ibl_pack_watercolor": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
     "datum_ibl_pack_cube_ibl": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "datum_ibl_pack_cube": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "datum_ibl_ingest_cube_argb32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "datum_ibl_ingest_cube_argb32_ibl": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "datum_ibl_measure_fp32_peak": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "datum_ibl_measure_fp32x2_peak": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "datum_ibl_dominant_kernel_stats": (c_int, [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),

@@ -110,6 +110,7 @@ struct datum_ibl_ctx
   DeviceBuffer<double> sh_partials; // block partials + 28 result doubles
   DeviceBuffer<unsigned char> staging; // generic device staging for host entry points
   DeviceBuffer<float> sink;
+  DeviceBuffer<float> srgb_lut;   // pow(c/255, 2.2) for the 256 channel values (six-image ingest)
 
   // CUDA-event ring around the dominant kernel of every chain (the level-1
   // prefilter launch): bench.py's live per-launch duration for the roofline
@@ -452,6 +453,7 @@ extern "C"
     ctx->sh_partials.release();
     ctx->staging.release();
     ctx->sink.release();
+    ctx->srgb_lut.release();
 
     for(auto &e : ctx->ring_begin)
       cudaEventDestroy(e);
@@ -825,6 +827,103 @@ extern "C"
       err = cudaStreamSynchronize(ctx->stream);
 
     return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_pack_cube_ibl", err);
+  }
+
+  // ---- six ARGB32 face images -> level 0 (+ chain) -------------------------------------
+
+  namespace
+  {
+    // argb (host) -> ctx->chain level 0 on the context stream
+    int ingest_to_device(datum_ibl_ctx *ctx, int width, int height, uint32_t const *argb, uint32_t *d_level0)
+    {
+      size_t level0 = (size_t)width * height * 6;
+
+      // color.h:103-106, 115-118: the 256 values pow(c/255.0f, 2.2f) a channel can take, computed
+      // once on the host with the C library the reference itself would call
+      if (!ctx->srgb_lut.ptr)
+      {
+        float lut[256];
+        for(int c = 0; c < 256; ++c)
+          lut[c] = std::pow((uint8_t)c / 255.0f, 2.2f);
+
+        cudaError_t err = ctx->srgb_lut.reserve(256);
+        if (err == cudaSuccess)
+          err = cudaMemcpyAsync(ctx->srgb_lut.ptr, lut, sizeof(lut), cudaMemcpyHostToDevice, ctx->stream);
+        if (err == cudaSuccess)
+          err = cudaStreamSynchronize(ctx->stream);   // `lut` is a stack array
+        if (err != cudaSuccess)
+          return fail_cuda("upload(srgb table)", err);
+      }
+
+      cudaError_t err = ctx->staging.reserve(level0 * sizeof(uint32_t));
+      if (err != cudaSuccess)
+        return fail_cuda("cudaMalloc(staging)", err);
+
+      err = cudaMemcpyAsync(ctx->staging.ptr, argb, level0 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+      if (err != cudaSuccess)
+        return fail_cuda("cudaMemcpyAsync(argb)", err);
+
+      err = ibl::launch_ingest_argb32((uint32_t const*)ctx->staging.ptr, ctx->srgb_lut.ptr, width, height, d_level0, ctx->sm_count, ctx->stream);
+      if (err != cudaSuccess)
+        return fail_cuda("ingest_argb32", err);
+      ctx->launches += 1;
+
+      return 0;
+    }
+  }
+
+  int datum_ibl_ingest_cube_argb32(datum_ibl_ctx *ctx, int width, int height, uint32_t const *argb, void *bits)
+  {
+    if (!ctx || !argb || !bits)
+      return fail("datum_ibl_ingest_cube_argb32: null argument");
+    if (width < 1 || height < 1)
+      return fail("datum_ibl_ingest_cube_argb32: bad width/height");
+
+    DeviceGuard guard(ctx->device);
+
+    size_t level0 = (size_t)width * height * 6;
+
+    cudaError_t err = ctx->chain.reserve(level0);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(chain)", err);
+
+    if (ingest_to_device(ctx, width, height, argb, ctx->chain.ptr))
+      return 1;
+
+    err = cudaMemcpyAsync(bits, ctx->chain.ptr, level0 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess)
+      err = cudaStreamSynchronize(ctx->stream);
+
+    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_ingest_cube_argb32", err);
+  }
+
+  int datum_ibl_ingest_cube_argb32_ibl(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, uint32_t const *argb, void *bits)
+  {
+    if (!ctx || !argb || !bits)
+      return fail("datum_ibl_ingest_cube_argb32_ibl: null argument");
+    if (!valid_chain(width, height, levels) || samples < 1)
+      return fail("datum_ibl_ingest_cube_argb32_ibl: bad width/height/levels/samples");
+
+    DeviceGuard guard(ctx->device);
+
+    size_t words = datum_ibl_chain_bytes(width, height, levels) / sizeof(uint32_t);
+
+    cudaError_t err = ctx->chain.reserve(words);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(chain)", err);
+
+    // tools/assetbuilder.cpp:443-462, then :465
+    if (ingest_to_device(ctx, width, height, argb, ctx->chain.ptr))
+      return 1;
+
+    if (run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr))
+      return 1;
+
+    err = cudaMemcpyAsync(bits, ctx->chain.ptr, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess)
+      err = cudaStreamSynchronize(ctx->stream);
+
+    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_ingest_cube_argb32_ibl", err);
   }
 
   // ---- LUTs -----------------------------------------------------------------------

@@ -196,4 +196,47 @@ namespace ibl
     blend_edges_kernel<<<1, 1024, 0, stream>>>(level, width, height);
     return cudaGetLastError();
   }
+
+  // ---- six ARGB32 images -> rgbe level 0 (tools/assetbuilder.cpp:443-462) ----
+
+  __global__ void __launch_bounds__(256) ingest_argb32_kernel(uint32_t const *__restrict__ argb, float const *__restrict__ lut, int width, int height, uint32_t *__restrict__ dst)
+  {
+    __shared__ float s_lut[256];
+    s_lut[threadIdx.x] = __ldg(lut + threadIdx.x);
+    __syncthreads();
+
+    size_t face_size = (size_t)width * height;
+    size_t total = 6 * face_size;
+
+    for(size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    {
+      size_t face = idx / face_size;
+      size_t in_face = idx - face * face_size;
+      int y = (int)(in_face / width);
+      int x = (int)(in_face - (size_t)y * width);
+
+      // QImage::Format_ARGB32 pixel 0xAARRGGBB -> Color4(r, g, b, a) (color.h:115-118), ungamma (color.h:103-106)
+      uint32_t px = __ldg(argb + idx);
+      float r = s_lut[(px >> 16) & 0xFFu];
+      float g = s_lut[(px >> 8) & 0xFFu];
+      float b = s_lut[px & 0xFFu];
+
+      // image.mirrored(): vertical flip (assetbuilder.cpp:458)
+      dst[face * face_size + (size_t)(height - 1 - y) * width + x] = rgbe_encode(r, g, b);
+    }
+  }
+
+  cudaError_t launch_ingest_argb32(uint32_t const *argb, float const *lut, int width, int height, uint32_t *dst, int sm_count, cudaStream_t stream)
+  {
+    size_t total = (size_t)6 * width * height;
+    size_t blocks = (total + 255) / 256;
+    size_t cap = (size_t)sm_count * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    if (grid < 1)
+      grid = 1;
+
+    ingest_argb32_kernel<<<grid, 256, 0, stream>>>(argb, lut, width, height, dst);
+
+    return cudaGetLastError();
+  }
 }

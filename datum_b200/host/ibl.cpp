@@ -18,6 +18,7 @@
 
 #ifdef DATUM_IBL_IN_REFERENCE_TREE
 void image_project_sh9_cube(int width, int height, void const *level0_rgbe, float *sh);
+void image_pack_cube_faces_ibl(unsigned int const *argb, int width, int height, int levels, void *bits);
 void image_set_ibl_samples(int samples);
 #endif
 
@@ -91,6 +92,11 @@ void image_pack_watercolor(lml::Color3 const &deepcolor, lml::Color3 const &shal
 void image_project_sh9_cube(int width, int height, void const *level0_rgbe, float *sh)
 {
   check(datum_ibl_project_sh9(context(), level0_rgbe, DATUM_IBL_FORMAT_RGBE, width, height, sh));
+}
+
+void image_pack_cube_faces_ibl(unsigned int const *argb, int width, int height, int levels, void *bits)
+{
+  check(datum_ibl_ingest_cube_argb32_ibl(context(), width, height, levels, g_samples, argb, bits));
 }
 
 void image_set_ibl_samples(int samples)

@@ -16,4 +16,11 @@ void image_pack_watercolor(lml::Color3 const &deepcolor, lml::Color3 const &shal
 // Irradiance::L (src/renderer/envmap.h:112-115); and the sample count of the bake
 // (tools/ibl.cpp:162 hard-codes 1024, which stays the default).
 void image_project_sh9_cube(int width, int height, void const *level0_rgbe, float *sh);
+
+// The body of write_skybox_asset(fout, id, paths) between image loading and
+// write_imag_asset (tools/assetbuilder.cpp:443-465) as one call: `argb` points at six
+// width*height blocks of QImage::Format_ARGB32 pixels (image.bits() after
+// convertToFormat, :445) in the caller's face order; per pixel rgbe(srgba(pixel)),
+// vertical mirror, then the prefilter chain.  `bits` = the whole payload.
+void image_pack_cube_faces_ibl(unsigned int const *argb, int width, int height, int levels, void *bits);
 void image_set_ibl_samples(int samples);

@@ -281,6 +281,29 @@ class IblContext:
         self._check(fn(self._handle, image.shape[1], image.shape[0], image.ctypes.data, width, height, ptr))
 
 
+    # ---- six ARGB32 face images -> cube chain: tools/assetbuilder.cpp:416-470 ----
+
+    def ingest_cube_argb32(self, faces, bits):
+        """The per-image loop of write_skybox_asset(fout, id, paths) (assetbuilder.cpp:443-462).
+        `faces` is a (6, H, W) uint32 array of QImage::Format_ARGB32 pixels (0xAARRGGBB) in the
+        caller's face order; `bits` receives level 0 (6*W*H rgbe words)."""
+        faces = np.ascontiguousarray(faces, dtype=np.uint32)
+        if faces.ndim != 3 or faces.shape[0] != 6:
+            raise ValueError("faces must be (6, H, W) uint32")
+        height, width = faces.shape[1], faces.shape[2]
+        ptr = _host_pointer(bits, width * height * 6 * 4, "bits")
+        self._check(self._lib.datum_ibl_ingest_cube_argb32(self._handle, width, height, faces.ctypes.data, ptr))
+
+    def skybox_from_argb32(self, faces, levels, bits, samples=1024):
+        """assetbuilder.cpp:443-465: ingest + image_buildmips_cube_ibl, level 0 staying on the device."""
+        faces = np.ascontiguousarray(faces, dtype=np.uint32)
+        if faces.ndim != 3 or faces.shape[0] != 6:
+            raise ValueError("faces must be (6, H, W) uint32")
+        height, width = faces.shape[1], faces.shape[2]
+        ptr = _host_pointer(bits, image_datasize(width, height, 6, levels), "bits")
+        self._check(self._lib.datum_ibl_ingest_cube_argb32_ibl(self._handle, width, height, levels, samples, faces.ctypes.data, ptr))
+
+
 _default = {}
 _live = weakref.WeakSet()
 

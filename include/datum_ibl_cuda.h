@@ -106,6 +106,27 @@ int datum_ibl_pack_cube(datum_ibl_ctx *ctx, int imgwidth, int imgheight, float c
  */
 int datum_ibl_pack_cube_ibl(datum_ibl_ctx *ctx, int imgwidth, int imgheight, float const *pixels, int width, int height, int levels, int samples, void *bits);
 
+/* ---- six face images -> cube: tools/assetbuilder.cpp:416-470 ------------------------ */
+
+/*
+ * Replaces the per-image loop of write_skybox_asset(fout, id, paths)
+ * (tools/assetbuilder.cpp:443-462): for each of the six QImage::Format_ARGB32
+ * images (0xAARRGGBB pixels, `argb` = 6*width*height of them on the host, faces in
+ * the caller's order rt, lf, dn, up, fr, bk) setPixel(rgbe(srgba(pixel)))
+ * (src/math/color.h:125-128, 154-162), QImage::mirrored() and the memcpy into
+ * level 0 of the payload.  `bits` receives 6*width*height words.  Synchronous.
+ */
+int datum_ibl_ingest_cube_argb32(datum_ibl_ctx *ctx, int width, int height, uint32_t const *argb, void *bits);
+
+/*
+ * The whole of write_skybox_asset(fout, id, paths) between image loading and
+ * write_imag_asset (tools/assetbuilder.cpp:443-465): the ingest above followed by
+ * image_buildmips_cube_ibl, level 0 never leaving the device in between.  `bits`
+ * receives the full payload of image_datasize(width, height, 6, levels) bytes.
+ * Synchronous.
+ */
+int datum_ibl_ingest_cube_argb32_ibl(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, uint32_t const *argb, void *bits);
+
 /* ---- SH9 irradiance projection: data/project.comp:23-106 -------------------- */
 
 /*

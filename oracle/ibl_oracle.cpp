@@ -406,6 +406,28 @@ extern "C"
     rgba[3] = (uint8_t)(argb >> 24) / 255.0f;
   }
 
+  // tools/assetbuilder.cpp:443-462: six ARGB32 images -> level 0.  Per pixel
+  // image.setPixel(x, y, rgbe(srgba(image.pixel(x, y)))) (:454), then image.mirrored() (:458, a
+  // vertical flip) and the memcpy behind the previous face (:460-462).
+  void oracle_ingest_cube_argb32(uint32_t const *argb, int width, int height, uint32_t *level0)
+  {
+    size_t face_size = (size_t)width * height;
+
+    for(int face = 0; face < 6; ++face)
+    {
+      for(int y = 0; y < height; ++y)
+      {
+        for(int x = 0; x < width; ++x)
+        {
+          float rgba[4];
+          oracle_srgba_decode(argb[face * face_size + (size_t)y * width + x], rgba);
+
+          level0[face * face_size + (size_t)(height - 1 - y) * width + x] = rgbe_encode(rgba[0], rgba[1], rgba[2]);
+        }
+      }
+    }
+  }
+
   // tools/ibl.cpp:95-104
   float oracle_radicalinverse(uint32_t bits) { return radicalinverse_VdC(bits); }
 

@@ -118,6 +118,18 @@ def main():
     out["water_params"] = np.concatenate([deep, shallow, [1.0], fresnel, [0.328, 5.0]]).astype(np.float32)
     out["water16"] = water
 
+    # ---- per-pixel arithmetic of the six-image ingest (tools/assetbuilder.cpp:454): rgbe(srgba(pixel)),
+    #      composed from the reference's own color.h functions (the loop around it needs Qt) ----
+    gray = np.arange(256, dtype=np.uint32)
+    pixels = np.concatenate([0xFF000000 | gray << 16 | gray << 8 | gray, rng.integers(0, 2**32, 3000, dtype=np.uint64).astype(np.uint32)]).astype(np.uint32)
+    ingest = np.zeros(len(pixels), np.uint32)
+    for i, w in enumerate(pixels):
+        buf = (ctypes.c_float * 4)()
+        ref.ref_srgba_decode(ctypes.c_uint32(int(w)), buf)
+        ingest[i] = ref.ref_rgbe_encode(buf[0], buf[1], buf[2])
+    out["ingest_argb"] = pixels
+    out["ingest_words"] = ingest
+
     path = os.path.join(HERE, "ibl_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

@@ -52,6 +52,18 @@ int main(int argc, char **argv)
       return 0;
     }
 
+    if (mode == "faces" && argc == 7)
+    {
+      // tools/assetbuilder.cpp:416-470 after image loading: six ARGB32 images in, payload out
+      int w = atoi(argv[2]), h = atoi(argv[3]), levels = atoi(argv[4]);
+      std::vector<unsigned int> argb((size_t)w * h * 6);
+      std::ifstream(argv[5], std::ios::binary).read((char*)argb.data(), (std::streamsize)(argb.size() * 4));
+      std::vector<char> payload(datasize(w, h, 6, levels));
+      image_pack_cube_faces_ibl(argb.data(), w, h, levels, payload.data());
+      std::ofstream(argv[6], std::ios::binary).write(payload.data(), (std::streamsize)payload.size());
+      return 0;
+    }
+
     if (mode == "luts" && argc == 3)
     {
       std::vector<char> payload(2 * datasize(256, 256, 1, 1));

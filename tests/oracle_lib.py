@@ -30,6 +30,7 @@ def oracle():
         lib.oracle_rgbe_encode_array.argtypes = [c_void_p, c_size_t, c_int, c_void_p]
         lib.oracle_rgbe_decode_array.argtypes = [c_void_p, c_size_t, c_void_p]
         lib.oracle_srgba_decode.argtypes = [ctypes.c_uint32, c_void_p]
+        lib.oracle_ingest_cube_argb32.argtypes = [c_void_p, c_int, c_int, c_void_p]
         lib.oracle_radicalinverse.restype = c_float
         lib.oracle_radicalinverse.argtypes = [ctypes.c_uint32]
         lib.oracle_texel_direction.argtypes = [c_int] * 5 + [c_void_p]
@@ -92,6 +93,15 @@ def rgbe_decode_array(words):
     words = np.ascontiguousarray(words, dtype=np.uint32)
     out = np.zeros(words.shape + (4,), np.float32)
     oracle().oracle_rgbe_decode_array(words.ctypes.data, words.size, out.ctypes.data)
+    return out
+
+
+def ingest_cube_argb32(faces):
+    """tools/assetbuilder.cpp:443-462 on a (6, H, W) uint32 array of ARGB32 pixels -> level 0 words."""
+    faces = np.ascontiguousarray(faces, dtype=np.uint32)
+    height, width = faces.shape[1], faces.shape[2]
+    out = np.zeros(6 * width * height, np.uint32)
+    oracle().oracle_ingest_cube_argb32(faces.ctypes.data, width, height, out.ctypes.data)
     return out
 
 

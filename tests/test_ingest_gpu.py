@@ -1,0 +1,77 @@
+"""Six-image ingest (tools/assetbuilder.cpp:416-470: QImage ARGB32 pixels -> rgbe(srgba(pixel)),
+vertical mirror, faces in argument order) on the GPU, through the C ABI and the host shim."""
+
+import os
+
+import numpy as np
+import pytest
+
+import datum_b200
+import oracle_lib
+from test_host_shim import run_driver
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ibl_golden.npz"))
+
+
+def random_faces(h, w, seed):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 2**32, (6, h, w), dtype=np.uint64).astype(np.uint32)
+
+
+@pytest.mark.parametrize("h,w", [(1, 1), (7, 13), (64, 64), (512, 512)])
+def test_ingest_is_bit_exact_with_the_oracle(ctx, h, w):
+    faces = random_faces(h, w, 40 + h)
+    got = np.zeros(6 * h * w, np.uint32)
+    ctx.ingest_cube_argb32(faces, got)
+    assert np.array_equal(got, oracle_lib.ingest_cube_argb32(faces))
+
+
+def test_ingest_matches_the_reference_pixel_arithmetic(ctx):
+    """Every gray level and 3000 random pixels against words composed from the compiled reference's
+    own srgba() and rgbe() (tests/golden/make_golden.py)."""
+    pixels, want = GOLDEN["ingest_argb"], GOLDEN["ingest_words"]
+    h, w = 7, len(pixels) // 6 // 7
+    faces = pixels[: 6 * h * w].reshape(6, h, w)
+    got = np.zeros(6 * h * w, np.uint32)
+    ctx.ingest_cube_argb32(faces, got)
+    assert np.array_equal(got.reshape(6, h, w), want[: 6 * h * w].reshape(6, h, w)[:, ::-1, :])
+
+
+def test_skybox_from_faces_equals_ingest_then_bake(ctx):
+    h = w = 32
+    levels = 6
+    faces = random_faces(h, w, 77)
+    faces &= np.uint32(0xFF3F7FBF)                       # some structure: not all channels full range
+    offs = datum_b200.level_offsets(w, h, levels)
+    one = np.zeros(offs[-1], np.uint32)
+    ctx.skybox_from_argb32(faces, levels, one)
+    two = np.zeros(offs[-1], np.uint32)
+    ctx.ingest_cube_argb32(faces, two[: offs[1]])
+    ctx.image_buildmips_cube_ibl(w, h, levels, two)
+    assert np.array_equal(one, two)
+    assert np.array_equal(one[: offs[1]], oracle_lib.ingest_cube_argb32(faces))
+
+
+def test_faces_through_the_host_shim(ctx, tmp_path):
+    """image_pack_cube_faces_ibl, called the way write_skybox_asset(fout, id, paths) would."""
+    h = w = 16
+    levels = 5
+    faces = random_faces(h, w, 91)
+    (tmp_path / "faces.bin").write_bytes(faces.tobytes())
+    out = run_driver("faces", w, h, levels, tmp_path / "faces.bin", tmp_path / "out.bin")
+    assert out.returncode == 0, out.stdout
+    got = np.frombuffer((tmp_path / "out.bin").read_bytes(), np.uint32)
+    want = np.zeros(datum_b200.level_offsets(w, h, levels)[-1], np.uint32)
+    ctx.skybox_from_argb32(faces, levels, want)
+    assert np.array_equal(got, want)
+
+
+def test_ingest_rejects_bad_arguments(ctx):
+    with pytest.raises(ValueError):
+        ctx.ingest_cube_argb32(np.zeros((5, 4, 4), np.uint32), np.zeros(6 * 16, np.uint32))
+    with pytest.raises(ValueError):
+        ctx.ingest_cube_argb32(np.zeros((6, 4, 4), np.uint32), np.zeros(10, np.uint32))
+    with pytest.raises(datum_b200.IblError):
+        ctx.skybox_from_argb32(np.zeros((6, 8, 8), np.uint32), 6, np.zeros(6 * 200, np.uint32))   # 8 >> 5 == 0

@@ -48,6 +48,18 @@ def test_srgba_decode_matches_reference():
     assert np.array_equal(out.view(np.uint32), GOLDEN["srgba_rgba"].view(np.uint32))
 
 
+def test_six_image_ingest_matches_reference_pixel_arithmetic():
+    """oracle_ingest_cube_argb32 == rgbe(srgba(pixel)) of the reference's color.h for every pixel
+    (golden composed from the compiled reference), rows mirrored, faces in argument order
+    (tools/assetbuilder.cpp:443-462)."""
+    pixels, want = GOLDEN["ingest_argb"], GOLDEN["ingest_words"]
+    n = (len(pixels) // 6 // 7) * 7                       # 6 faces of 7 x (n/7)... any rectangle will do
+    h, w = 7, n // 7
+    faces = pixels[: 6 * h * w].reshape(6, h, w)
+    got = oracle_lib.ingest_cube_argb32(faces).reshape(6, h, w)
+    assert np.array_equal(got, want[: 6 * h * w].reshape(6, h, w)[:, ::-1, :])
+
+
 def test_face_rotations_match_reference():
     vecs, want = GOLDEN["rotate_in"], GOLDEN["rotate_out"]
     for f in range(6):
