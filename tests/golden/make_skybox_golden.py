@@ -1,0 +1,52 @@
+"""Regenerates tests/golden/skybox64.npz: BASELINE config 1 (the reference's bundled
+data/skybox_{rt,lf,dn,up,fr,bk}.jpg cube) reduced 8x to 64^2 faces so that it fits a fixture.
+
+Runs in the authoring container only (needs /root/reference and PIL).  Steps, mirroring
+write_skybox_asset(fout, id, paths) (tools/assetbuilder.cpp:416-470):
+  1. decode the six JPEGs (PIL here, QImage in the reference), box-average 8x8 -> 64x64, pack as
+     QImage::Format_ARGB32 pixels (0xFFRRGGBB) in the call-site order rt, lf, dn, up, fr, bk
+     (assetbuilder.cpp:876);
+  2. level 0 = rgbe(srgba(pixel)), mirrored — the oracle's restatement of :443-462 (its per-pixel
+     arithmetic is pinned against the compiled reference in ibl_golden.npz; the loop needs Qt);
+  3. levels 1..6 = the UNMODIFIED reference image_buildmips_cube_ibl (oracle/_ref), 1024 samples.
+
+    python tests/golden/make_skybox_golden.py
+"""
+
+import os
+import sys
+
+import numpy as np
+from PIL import Image
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle_lib  # noqa: E402
+
+ORDER = ("rt", "lf", "dn", "up", "fr", "bk")   # tools/assetbuilder.cpp:876
+W, LEVELS = 64, 7
+
+
+def main():
+    faces = np.zeros((6, W, W), np.uint32)
+    for f, name in enumerate(ORDER):
+        rgb = np.asarray(Image.open("/root/reference/data/skybox_%s.jpg" % name).convert("RGB"), np.float64)
+        k = rgb.shape[0] // W
+        small = rgb.reshape(W, k, W, k, 3).mean(axis=(1, 3)).round().astype(np.uint32)
+        faces[f] = 0xFF000000 | small[..., 0] << 16 | small[..., 1] << 8 | small[..., 2]
+
+    total = sum(6 * (W >> i) ** 2 for i in range(LEVELS))
+    chain = np.zeros(total, np.uint32)
+    chain[: 6 * W * W] = oracle_lib.ingest_cube_argb32(faces)
+    oracle_lib.ref().ref_image_buildmips_cube_ibl(W, W, LEVELS, chain.ctypes.data)
+
+    path = os.path.join(HERE, "skybox64.npz")
+    np.savez_compressed(path, faces_argb=faces, chain=chain)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -75,3 +75,26 @@ def test_ingest_rejects_bad_arguments(ctx):
         ctx.ingest_cube_argb32(np.zeros((6, 4, 4), np.uint32), np.zeros(10, np.uint32))
     with pytest.raises(datum_b200.IblError):
         ctx.skybox_from_argb32(np.zeros((6, 8, 8), np.uint32), 6, np.zeros(6 * 200, np.uint32))   # 8 >> 5 == 0
+
+
+def test_bundled_skybox_bake_matches_the_reference(ctx):
+    """BASELINE config 1 reduced to 64^2 faces (tests/golden/make_skybox_golden.py): the reference's
+    bundled data/skybox_*.jpg cube through ingest + bake, against the chain the UNMODIFIED reference
+    produced.  Each level here is built from OUR previous level, so one-code differences propagate:
+    the bound is on decoded values, as in test_own_chain_against_reference_golden."""
+    fixture = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "skybox64.npz"))
+    faces, want = fixture["faces_argb"], fixture["chain"]
+    w, levels = faces.shape[2], 7
+    offs = datum_b200.level_offsets(w, w, levels)
+    got = np.zeros(offs[-1], np.uint32)
+    ctx.skybox_from_argb32(faces, levels, got)
+    assert np.array_equal(got[: offs[1]], want[: offs[1]])                       # level 0: bit exact
+    dec_got = oracle_lib.rgbe_decode_array(got[offs[1]:])[:, :3].astype(np.float64)
+    dec_ref = oracle_lib.rgbe_decode_array(want[offs[1]:])[:, :3].astype(np.float64)
+    rel = np.abs(dec_got - dec_ref).max(axis=1) / np.maximum(dec_ref.max(axis=1), 1e-30)
+    assert np.quantile(rel, 0.99) <= 4e-3      # one mantissa code of a 9-bit mantissa
+    assert rel.max() <= 1e-1                   # cube-edge samples, see parity.py
+    assert (got[offs[1]:] == want[offs[1]:]).mean() >= 0.97
+    # level 1 alone is built from the same source as the reference's: the per-level contract applies
+    lvl1 = slice(offs[1], offs[2])
+    assert (got[lvl1] == want[lvl1]).mean() >= 0.99
