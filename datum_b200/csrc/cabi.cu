@@ -49,6 +49,7 @@ namespace
     float norm = 0;  // kAccScale / total weight
     double total_weight = 0;
     float4 *d_banded = nullptr;  // the entries in banded ring order (ibl_tables.h), scaled by kDnTableScale
+    float4 *d_pairs = nullptr;   // the banded entries, last band filled up, interleaved two by two (build_paired_entries)
     float *d_band_min = nullptr; // smallest lz per band
     int bands = 0;
   };
@@ -179,6 +180,8 @@ namespace
         ibl::BandedSamples banded = ibl::build_banded_samples(level, levels, samples, ibl::kSampleBand);
         t.bands = (int)banded.band_min_lz.size();
 
+        std::vector<float> paired = ibl::build_paired_entries(banded, ibl::kDnTableScale);
+
         for(auto &e : banded.level.entries)
         {
           e.lx *= ibl::kDnTableScale; e.ly *= ibl::kDnTableScale; e.lz *= ibl::kDnTableScale; e.wh *= ibl::kDnTableScale;
@@ -192,6 +195,10 @@ namespace
           err = cudaMemcpyAsync(t.d_banded, banded.level.entries.data(), sizeof(float4) * (size_t)t.count, cudaMemcpyHostToDevice, ctx->stream);
         if (err == cudaSuccess)
           err = cudaMemcpyAsync(t.d_band_min, banded.band_min_lz.data(), sizeof(float) * (size_t)t.bands, cudaMemcpyHostToDevice, ctx->stream);
+        if (err == cudaSuccess)
+          err = cudaMalloc(&t.d_pairs, sizeof(float) * (paired.size() > 0 ? paired.size() : 4));
+        if (err == cudaSuccess)
+          err = cudaMemcpyAsync(t.d_pairs, paired.data(), sizeof(float) * paired.size(), cudaMemcpyHostToDevice, ctx->stream);
 
         if (err == cudaSuccess)
           err = cudaStreamSynchronize(ctx->stream); // `host` and `banded` die at the end of this iteration
@@ -244,6 +251,7 @@ namespace
     ibl::PrefilterDnParams p = {};
     p.records = ctx->records.ptr;
     p.table = table.d_banded;
+    p.table_pairs = table.d_pairs;
     p.band_min_lz = table.d_band_min;
     p.table_count = table.count;
     p.bands = table.bands;
@@ -443,6 +451,8 @@ extern "C"
           cudaFree(t.d_banded);
         if (t.d_band_min)
           cudaFree(t.d_band_min);
+        if (t.d_pairs)
+          cudaFree(t.d_pairs);
 
       }
 

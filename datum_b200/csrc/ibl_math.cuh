@@ -166,7 +166,8 @@ namespace ibl
   // round-to-nearest of fu-0.5 through the magic add; when fu is an exact
   // integer this may pick i-1 with frac 1, which addresses the same bilinear
   // value.  |q| <= 1 keeps i in [0, ws-2], so the footprint never leaves the face.
-  IBL_HD uint32_t cube_footprint(LevelGeom const &g, float Lx, float Ly, float Lz, float &du, float &dv)
+  // face selection and the two face coordinates in [-1, 1] (qu = 2u - 1, qv = 2v - 1)
+  IBL_HD void cube_select(float Lx, float Ly, float Lz, float &qu, float &qv, uint32_t &face)
   {
     float ax = fabsf(Lx), ay = fabsf(Ly), az = fabsf(Lz);
     bool px = ax >= fmaxf(ay, az);
@@ -187,10 +188,20 @@ namespace ibl
 
     // face index: x -> 0/1, y -> 3/2, z -> 5/4 for positive/negative major
     uint32_t neg = f2u(major) >> 31;
-    uint32_t face = px ? neg : (py ? 3u - neg : 5u - neg);
+    face = px ? neg : (py ? 3u - neg : 5u - neg);
 
-    float fu = fmaf(un * ru, g.hw, g.hwm);
-    float fv = fmaf(vn * rv, g.hh, g.hhm);
+    qu = un * ru;
+    qv = vn * rv;
+  }
+
+  IBL_HD uint32_t cube_footprint(LevelGeom const &g, float Lx, float Ly, float Lz, float &du, float &dv)
+  {
+    float qu, qv;
+    uint32_t face;
+    cube_select(Lx, Ly, Lz, qu, qv, face);
+
+    float fu = fmaf(qu, g.hw, g.hwm);
+    float fv = fmaf(qv, g.hh, g.hhm);
     float mu = fu + kMagic;
     float mv = fv + kMagic;
     du = fu - (mu - kMagic);

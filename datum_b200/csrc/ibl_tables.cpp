@@ -83,4 +83,34 @@ namespace ibl
 
     return out;
   }
+
+  std::vector<float> build_paired_entries(BandedSamples const &banded, float scale)
+  {
+    std::vector<SampleEntry> e = banded.level.entries;
+    for(auto &s : e)
+    {
+      s.lx *= scale; s.ly *= scale; s.lz *= scale; s.wh *= scale;
+    }
+
+    // fill the last band: direction (0, 0, 1) in the tangent frame, i.e. the normal itself (always on
+    // the texel's own face), at 2^-60 of the scale of a real entry
+    size_t band = (size_t)(banded.band > 0 ? banded.band : 1);
+    size_t padded = (e.size() + band - 1) / band * band;
+    float tiny = std::ldexp(scale, -60);
+    padded += padded & 1;   // pairs: an even count whatever the band size
+    while (e.size() < padded)
+      e.push_back(SampleEntry{ 0.0f, 0.0f, tiny, 0.5f * tiny });
+
+    std::vector<float> out(4 * padded);
+    for(size_t i = 0; i < padded; i += 2)
+    {
+      SampleEntry const &a = e[i];
+      SampleEntry const &b = e[i + 1];
+      float *o = out.data() + 4 * i;
+      o[0] = a.lx; o[1] = b.lx; o[2] = a.ly; o[3] = b.ly;
+      o[4] = a.lz; o[5] = b.lz; o[6] = a.wh; o[7] = b.wh;
+    }
+
+    return out;
+  }
 }

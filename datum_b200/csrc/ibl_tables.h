@@ -49,6 +49,15 @@ namespace ibl
 
   BandedSamples build_banded_samples(int level, int levels, int samples, int band);
 
+  // The banded entries for the kernel that works on two samples at a time (prefilter_dn.cu,
+  // prefilter_dp_kernel): every entry multiplied by `scale`, the last band filled up with
+  // samples of no effect (direction = the normal, weight 2^-60 of a real one: it rounds away in
+  // every fp32 sum), and consecutive entries (a, b) interleaved as
+  //     { lx_a, lx_b, ly_a, ly_b }  { lz_a, lz_b, wh_a, wh_b }
+  // so that one 16-byte load yields two register pairs for the packed fp32x2 arithmetic.
+  // Returns 4 floats per entry, band * ceil(count / band) entries.
+  std::vector<float> build_paired_entries(BandedSamples const &banded, float scale);
+
   // ibl.cpp:95-104
   float radicalinverse_VdC(uint32_t bits);
 }

@@ -32,6 +32,7 @@ namespace ibl
   {
     uint4 const *records;     // quad records of the SOURCE level, words re-laid by pack_dn_word (6*ws*hs)
     float4 const *table;      // banded sample table of this level, every entry scaled by kDnTableScale
+    float4 const *table_pairs; // the same entries, last band filled up, two entries interleaved per 32 bytes (ibl_tables.h)
     float const *band_min_lz; // smallest lz of each band (unscaled), decreasing
     int table_count;
     int bands;                // ceil(table_count / kSampleBand)
@@ -48,7 +49,8 @@ namespace ibl
     int queues, chunk, queued;
   };
 
-  // variant 0 = pick by slab size and table size; 50..58 = fixed <warps per tile, table in shared memory, tile queues>
+  // variant 0 = pick by slab size and table size; 50..58 = one sample at a time, fixed <warps per tile,
+  // table in shared memory, tile queues>; 70..75 = two samples at a time (prefilter_dp_kernel)
   cudaError_t launch_prefilter_dn(PrefilterDnParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid);
 
   // also zeroes the `ncounters` tile queue heads for the prefilter launch that follows

@@ -58,6 +58,22 @@ namespace ibl
     }
   }
 
+  // the same on the ALU pipe: LOP3 + LEA.  The pair kernel spreads its taps over both forms so that
+  // neither the FMA pipe (IMAD shares it with the packed FMAs) nor the ALU pipe saturates.
+  __device__ __forceinline__ float scale_by_exponent_alu(float w, uint32_t word)
+  {
+    uint32_t e, r;
+    asm volatile("and.b32 %0, %1, 31;" : "=r"(e) : "r"(word));
+    asm volatile("shl.b32 %0, %1, 23;" : "=r"(r) : "r"(e));
+    return u2f(r + f2u(w));
+  }
+
+  template<bool ALU>
+  __device__ __forceinline__ float scale_tap(float w, uint32_t word, uint32_t emul)
+  {
+    return ALU ? scale_by_exponent_alu(w, word) : scale_by_exponent(w, word & kDnMaskE, emul);
+  }
+
   // ---- quad records ----------------------------------------------------------------
 
   __global__ void __launch_bounds__(256) build_dn_records_kernel(uint32_t const *__restrict__ src, uint4 *__restrict__ rec, int ws, int hs, int *__restrict__ counters, int ncounters)
@@ -393,6 +409,339 @@ namespace ibl
     }
   }
 
+  // ---- two samples at a time --------------------------------------------------------------
+  //
+  // The kernel above packs the (a, b) face coordinates of ONE sample into fp32x2 operations; the
+  // third coordinate, the bilinear weights and half of the magic-add floor stay scalar.  Packing
+  // the SAME quantity of TWO consecutive samples instead makes every per-sample fp32 operation a
+  // half-instruction: direction 9 packed ops per pair (was 6 per sample), weights 9 per pair (was
+  // 6 per sample), and the general (cube-face-selecting) path gets the packed direction and floor
+  // it never had.  Per element the operations and their order are the ones of the kernel above,
+  // so r and g sums are bit-identical to it; the two b partial sums now belong to the two samples
+  // of a pair instead of to the tap columns.  The table arrives pair-interleaved with its last
+  // band filled up (build_paired_entries), so there is no short-band code.
+  //
+  // Footprint address: the magic-add integers carry kMagicBits each, kMagicBits*(ws+1) in the
+  // index.  Instead of subtracting that per sample the record pointer is moved back by it once
+  // (the launcher checks that index + bias cannot wrap in 32 bits, else it uses the kernel above):
+  // one IMAD + one IMAD.WIDE per footprint.
+
+  struct PairEntry
+  {
+    f32x2 lx, ly, lz, wh;   // each: (sample a, sample b)
+  };
+
+  template<bool SMEM_TABLE>
+  __device__ __forceinline__ PairEntry load_pair(float4 const *t)
+  {
+    ulonglong2 const *q = reinterpret_cast<ulonglong2 const*>(t);
+    ulonglong2 lo = SMEM_TABLE ? q[0] : __ldg(q);
+    ulonglong2 hi = SMEM_TABLE ? q[1] : __ldg(q + 1);
+    return PairEntry{ lo.x, lo.y, hi.x, hi.y };
+  }
+
+  struct Frame
+  {
+    Vec3f T, B, N;
+  };
+
+  // record `idx` (unsigned 32-bit, bias included): one IMAD.WIDE.U32 as long as `base` is an opaque
+  // register pair (see opaque()); otherwise the compiler re-associates the 64-bit sum into four adds
+  __device__ __forceinline__ uint4 load_record(uint4 const *base, uint32_t idx)
+  {
+    return __ldg(base + idx);
+  }
+
+  __device__ __forceinline__ uint4 const *opaque(uint4 const *ptr)
+  {
+    asm volatile("" : "+l"(ptr));
+    return ptr;
+  }
+
+  __device__ __forceinline__ f32x2 neg2(f32x2 a)
+  {
+    float lo, hi;
+    unpack2(a, lo, hi);
+    return pack2(-lo, -hi);
+  }
+
+  // reflected directions of both samples in the frame's coordinates, the kernel above's operation order
+  __device__ __forceinline__ void direction_pair(Frame const &t, PairEntry const &e, f32x2 &x, f32x2 &y, f32x2 &z)
+  {
+    x = fma2(e.lz, bcast2(t.N.x), fma2(e.ly, bcast2(t.B.x), mul2(e.lx, bcast2(t.T.x))));
+    y = fma2(e.lz, bcast2(t.N.y), fma2(e.ly, bcast2(t.B.y), mul2(e.lx, bcast2(t.T.y))));
+    z = fma2(e.lz, bcast2(t.N.z), fma2(e.ly, bcast2(t.B.z), mul2(e.lx, bcast2(t.T.z))));
+  }
+
+  // (fu, fv) of both samples -> records, weights, taps.  EXP_ALU of the four taps of a sample take their exponent on the ALU pipe.  `base` holds the bias (and the face on the same-face path).
+  template<int EXP_ALU>
+  __device__ __forceinline__ void gather_pair(PrefilterDnParams const &p, uint4 const *base, uint32_t off_a, uint32_t off_b, f32x2 fu, f32x2 fv, PairEntry const &e, Sums &acc)
+  {
+    f32x2 mu = add2(fu, bcast2(kMagic));
+    f32x2 mv = add2(fv, bcast2(kMagic));
+    f32x2 iu = add2(mu, bcast2(-kMagic));
+    f32x2 iv = add2(mv, bcast2(-kMagic));
+    f32x2 du = fma2(iu, bcast2(-1.0f), fu);
+    f32x2 dv = fma2(iv, bcast2(-1.0f), fv);
+
+    float mua, mub, mva, mvb;
+    unpack2(mu, mua, mub);
+    unpack2(mv, mva, mvb);
+
+    uint4 ra = load_record(base, f2u(mva) * (uint32_t)p.geom.ws + f2u(mua) + off_a);
+    uint4 rb = load_record(base, f2u(mvb) * (uint32_t)p.geom.ws + f2u(mub) + off_b);
+
+    // tools/ibl.cpp:40 as four products, times the sample weight: (0.5 -+ du) * (wh -+ dv * nl)
+    f32x2 u0 = fma2(du, bcast2(-1.0f), bcast2(0.5f));
+    f32x2 u1 = add2(du, bcast2(0.5f));
+    f32x2 v0 = fma2(neg2(dv), e.lz, e.wh);
+    f32x2 v1 = fma2(dv, e.lz, e.wh);
+
+    float w00a, w00b, w10a, w10b, w01a, w01b, w11a, w11b;
+    unpack2(mul2(u0, v0), w00a, w00b);
+    unpack2(mul2(u1, v0), w10a, w10b);
+    unpack2(mul2(u0, v1), w01a, w01b);
+    unpack2(mul2(u1, v1), w11a, w11b);
+
+    const uint32_t emul = p.exp_mul;
+    w00a = scale_tap<(EXP_ALU > 0)>(w00a, ra.x, emul);
+    w10a = scale_tap<(EXP_ALU > 2)>(w10a, ra.y, emul);
+    w01a = scale_tap<(EXP_ALU > 1)>(w01a, ra.z, emul);
+    w11a = scale_tap<(EXP_ALU > 3)>(w11a, ra.w, emul);
+    w00b = scale_tap<(EXP_ALU > 0)>(w00b, rb.x, emul);
+    w10b = scale_tap<(EXP_ALU > 2)>(w10b, rb.y, emul);
+    w01b = scale_tap<(EXP_ALU > 1)>(w01b, rb.z, emul);
+    w11b = scale_tap<(EXP_ALU > 3)>(w11b, rb.w, emul);
+
+    acc.rg = fma2(pack2(u2f(ra.x >> 23), u2f(ra.x & kDnMaskG)), bcast2(w00a), acc.rg);
+    acc.rg = fma2(pack2(u2f(ra.y >> 23), u2f(ra.y & kDnMaskG)), bcast2(w10a), acc.rg);
+    acc.rg = fma2(pack2(u2f(ra.z >> 23), u2f(ra.z & kDnMaskG)), bcast2(w01a), acc.rg);
+    acc.rg = fma2(pack2(u2f(ra.w >> 23), u2f(ra.w & kDnMaskG)), bcast2(w11a), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.x >> 23), u2f(rb.x & kDnMaskG)), bcast2(w00b), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.y >> 23), u2f(rb.y & kDnMaskG)), bcast2(w10b), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.z >> 23), u2f(rb.z & kDnMaskG)), bcast2(w01b), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.w >> 23), u2f(rb.w & kDnMaskG)), bcast2(w11b), acc.rg);
+
+    acc.bb = fma2(pack2(u2f(ra.x & kDnMaskB), u2f(rb.x & kDnMaskB)), pack2(w00a, w00b), acc.bb);
+    acc.bb = fma2(pack2(u2f(ra.y & kDnMaskB), u2f(rb.y & kDnMaskB)), pack2(w10a, w10b), acc.bb);
+    acc.bb = fma2(pack2(u2f(ra.z & kDnMaskB), u2f(rb.z & kDnMaskB)), pack2(w01a, w01b), acc.bb);
+    acc.bb = fma2(pack2(u2f(ra.w & kDnMaskB), u2f(rb.w & kDnMaskB)), pack2(w11a, w11b), acc.bb);
+  }
+
+  // frame rows in face-local (a, b, m) coordinates, a and b pre-scaled to source texels
+  template<int EXP_ALU>
+  __device__ __forceinline__ void pair_same_face(PrefilterDnParams const &p, Frame const &t, uint4 const *base, PairEntry const &e, Sums &acc)
+  {
+    f32x2 la, lb, lm;
+    direction_pair(t, e, la, lb, lm);
+
+    float ma, mb;
+    unpack2(lm, ma, mb);
+    f32x2 r = pack2(rcp_fast(ma), rcp_fast(mb));
+
+    gather_pair<EXP_ALU>(p, base, 0u, 0u, fma2(la, r, bcast2(p.geom.hwm)), fma2(lb, r, bcast2(p.geom.hhm)), e, acc);
+  }
+
+  // frame rows in world coordinates: cube face selection of tools/ibl.cpp:43-88 per sample
+  template<int EXP_ALU>
+  __device__ __forceinline__ void pair_general(PrefilterDnParams const &p, Frame const &t, uint4 const *base, PairEntry const &e, Sums &acc)
+  {
+    f32x2 x, y, z;
+    direction_pair(t, e, x, y, z);
+
+    float xa, xb, ya, yb, za, zb;
+    unpack2(x, xa, xb);
+    unpack2(y, ya, yb);
+    unpack2(z, za, zb);
+
+    float qua, qva, qub, qvb;
+    uint32_t fa, fb;
+    cube_select(xa, ya, za, qua, qva, fa);
+    cube_select(xb, yb, zb, qub, qvb, fb);
+
+    f32x2 fu = fma2(pack2(qua, qub), bcast2(p.geom.hw), bcast2(p.geom.hwm));
+    f32x2 fv = fma2(pack2(qva, qvb), bcast2(p.geom.hh), bcast2(p.geom.hhm));
+
+    // the face offset goes into the 32-bit index (bias + 6 faces cannot wrap, see the launcher)
+    gather_pair<EXP_ALU>(p, base, fa * p.geom.face_size, fb * p.geom.face_size, fu, fv, e, acc);
+  }
+
+  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU>
+  __global__ void __launch_bounds__(32 * NW, MINB) prefilter_dp_kernel(PrefilterDnParams p)
+  {
+    extern __shared__ float4 smem[];
+    const int padded = p.bands * kSampleBand;
+    float4 *s_table = smem;
+    float *s_red = reinterpret_cast<float*>(smem + (SMEM_TABLE ? padded : 0));
+    int *s_tile = reinterpret_cast<int*>(s_red + NW * 3 * 32);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    if (SMEM_TABLE)
+    {
+      for(int i = tid; i < padded; i += 32 * NW)
+        s_table[i] = __ldg(p.table_pairs + i);
+      __syncthreads();
+    }
+
+    float4 const *table = SMEM_TABLE ? s_table : p.table_pairs;
+
+    uint32_t smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+
+    constexpr int PER = kSampleBand / NW;        // entries of a band per warp: an arc of the ring
+    constexpr int PAIRS = PER / 2;
+    static_assert(PER >= 2 && PER % 2 == 0, "a warp takes whole pairs of every band");
+    constexpr int BAND_UNROLL = PAIRS >= 2 ? 1 : 2;
+
+    // records, moved back by the bias of the magic-add integers
+    uint4 const *biased = opaque(p.records - (size_t)p.geom.bias);
+
+    for(int it = 0; ; ++it)
+    {
+      int tile;
+      if (QUEUES)
+      {
+        if (tid == 0)
+          *s_tile = next_tile(p, smid);
+        __syncthreads();
+        tile = *s_tile;
+      }
+      else
+      {
+        tile = (int)blockIdx.x + it * (int)gridDim.x;
+        if (tile >= p.tiles)
+          tile = -1;
+      }
+
+      if (tile < 0)
+        break;
+
+      int x, row;
+      bool valid = tile_texel(p, tile, lane, x, row);
+
+      if (__ballot_sync(0xffffffffu, valid) == 0u)
+      {
+        if (QUEUES)
+          __syncthreads();
+        continue;
+      }
+
+      if (!valid) { x = p.wd >> 1; row = (p.row_begin / p.hd) * p.hd + (p.hd >> 1); }
+
+      int face = row / p.hd;
+      int y = row - face * p.hd;
+
+      Frame st;
+      int n_same;
+      {
+        Vec3f N = texel_normal(p.quats[face], x, y, p.wd, p.hd);
+        Vec3f T, B;
+        tangent_frame(N, T, B);
+
+        Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
+
+        float threshold = same_face_threshold(Nl);
+        threshold = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(threshold)));
+
+        st.T = Vec3f{ Tl.x * p.geom.hw, Tl.y * p.geom.hh, Tl.z };
+        st.B = Vec3f{ Bl.x * p.geom.hw, Bl.y * p.geom.hh, Bl.z };
+        st.N = Vec3f{ Nl.x * p.geom.hw, Nl.y * p.geom.hh, Nl.z };
+
+        int lo = 0, hi = p.bands;
+        while (lo < hi)
+        {
+          int mid = (lo + hi) >> 1;
+          if (__ldg(p.band_min_lz + mid) > threshold)
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        n_same = lo;
+      }
+
+      Sums acc;
+      acc.rg = 0ull;
+      acc.bb = 0ull;
+
+      float4 const *tw = table + warp * PER;   // entry index == float4 index in the pair-interleaved table
+      int band = 0;
+
+      {
+        uint4 const *base = opaque(biased + (size_t)face * p.geom.face_size);
+
+        #pragma unroll BAND_UNROLL
+        for(; band < n_same; ++band)
+        {
+          #pragma unroll
+          for(int k = 0; k < PAIRS; ++k)
+            pair_same_face<EXP_ALU>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+        }
+      }
+
+      if (band < p.bands)
+      {
+        // back to world coordinates for the samples that may cross a face edge
+        st.T = from_face_local(face, Vec3f{ st.T.x * p.geom.inv_hw, st.T.y * p.geom.inv_hh, st.T.z });
+        st.B = from_face_local(face, Vec3f{ st.B.x * p.geom.inv_hw, st.B.y * p.geom.inv_hh, st.B.z });
+        st.N = from_face_local(face, Vec3f{ st.N.x * p.geom.inv_hw, st.N.y * p.geom.inv_hh, st.N.z });
+
+        #pragma unroll BAND_UNROLL
+        for(; band < p.bands; ++band)
+        {
+          #pragma unroll
+          for(int k = 0; k < PAIRS; ++k)
+            pair_general<EXP_ALU>(p, st, biased, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+        }
+      }
+
+      // ---- reduction over the CTA's warps: s_red[(warp*3 + c)*32 + lane] ----
+      float a[4];
+      unpack2(acc.rg, a[0], a[1]);
+      unpack2(acc.bb, a[2], a[3]);
+      a[2] += a[3];
+
+      #pragma unroll
+      for(int c = 0; c < 3; ++c)
+        s_red[(warp * 3 + c) * 32 + lane] = a[c];
+
+      __syncthreads();
+
+      if (warp == 0)
+      {
+        float sum[3] = { 0.0f, 0.0f, 0.0f };
+        #pragma unroll
+        for(int w = 0; w < NW; ++w)
+        {
+          #pragma unroll
+          for(int c = 0; c < 3; ++c)
+            sum[c] += s_red[(w * 3 + c) * 32 + lane];
+        }
+
+        if (valid)
+        {
+          // sum/totalweight of ibl.cpp:186, then rgbe() of ibl.cpp:269
+          float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
+          size_t o = (size_t)row * p.wd + x;
+
+          if (p.dst_words)
+            p.dst_words[o] = rgbe_encode(r, g, b);
+
+          if (p.dst_f32)
+          {
+            p.dst_f32[3*o + 0] = r;
+            p.dst_f32[3*o + 1] = g;
+            p.dst_f32[3*o + 2] = b;
+          }
+        }
+      }
+
+      __syncthreads();
+    }
+  }
+
   // ---- host-side launchers ---------------------------------------------------------------
 
   cudaError_t launch_build_dn_records(uint32_t const *src, uint4 *rec, int ws, int hs, int *counters, int ncounters, int sm_count, cudaStream_t stream)
@@ -452,6 +801,54 @@ namespace ibl
     }
   }
 
+  namespace
+  {
+    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0>
+    cudaError_t launch_dp(PrefilterDnParams p, int sm_count, cudaStream_t stream, int *launched_grid)
+    {
+      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU>;
+
+      int rows = p.row_end - p.row_begin;
+      int tiles_x = (p.wd + 7) / 8, tiles_y = (rows + 3) / 4;
+      p.blocks_x = (tiles_x + 3) / 4;
+      p.tiles = p.blocks_x * ((tiles_y + 3) / 4) * 16;
+
+      size_t smem = (SMEM_TABLE ? (size_t)p.bands * kSampleBand * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
+
+      cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err != cudaSuccess)
+        return err;
+
+      int resident = 0;
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 32 * NW, smem);
+      if (err != cudaSuccess)
+        return err;
+      if (resident < 1)
+        return cudaErrorLaunchOutOfResources;
+
+      int grid = p.tiles < sm_count * resident ? p.tiles : sm_count * resident;
+      if (grid < 1)
+        grid = 1;
+
+      p.queues = sm_count;
+      p.chunk = (p.tiles - p.tiles / 8) / sm_count;
+      p.queued = p.chunk * sm_count;
+
+      kernel<<<grid, 32 * NW, smem, stream>>>(p);
+
+      if (launched_grid)
+        *launched_grid = grid;
+
+      return cudaGetLastError();
+    }
+
+    // the pair kernel folds the magic-add bias into the record pointer: index + bias must not wrap
+    bool pair_kernel_usable(PrefilterDnParams const &p)
+    {
+      return p.table_pairs != nullptr && (unsigned long long)p.geom.bias + 6ull * p.geom.face_size <= 0xFFFFFFFFull;
+    }
+  }
+
   cudaError_t launch_prefilter_dn(PrefilterDnParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid)
   {
     int rows = p.row_end - p.row_begin;
@@ -465,18 +862,39 @@ namespace ibl
       size_t texels = (size_t)rows * p.wd;
       bool big_table = p.table_count > 1100;
 
+      // the two biggest classes work on two samples at a time (prefilter_dp_kernel; measured on C2:
+      // level 1 885 -> 862 us, level 2 277 -> 262, level 3 96 -> 88); launch_prefilter_dn falls back to
+      // the one-sample kernel when the biased record index could wrap
       if (texels >= 32u * 148u * 8u)
-        variant = big_table ? 52 : 51;
+        variant = big_table ? 71 : 70;
       else if (texels >= 32u * 148u * 2u)
-        variant = big_table ? 54 : 53;
+        variant = big_table ? 73 : 72;
       else if (texels >= 32u * 48u)
         variant = big_table ? 56 : 55;
       else
         variant = big_table ? 58 : 57;
     }
 
+    // two samples at a time; when the biased index could wrap, the same shape one sample at a time
+    if (variant >= 70 && variant <= 79 && !pair_kernel_usable(p))
+    {
+      static const int fallback[10] = { 51, 52, 53, 54, 50, 51, 51, 51, 51, 53 };
+      variant = fallback[variant - 70];
+    }
+
     switch (variant)
     {
+      //                        NW MINB SMEM  QUEUES
+      case 70: return launch_dp<4, 8, true, true>(p, sm_count, stream, launched_grid);
+      case 71: return launch_dp<4, 8, false, true>(p, sm_count, stream, launched_grid);
+      case 72: return launch_dp<8, 4, true, false>(p, sm_count, stream, launched_grid);
+      case 73: return launch_dp<8, 4, false, false>(p, sm_count, stream, launched_grid);
+      case 74: return launch_dp<4, 8, true, false>(p, sm_count, stream, launched_grid);
+      case 75: return launch_dp<4, 8, true, true, 1>(p, sm_count, stream, launched_grid);
+      case 76: return launch_dp<4, 8, true, true, 2>(p, sm_count, stream, launched_grid);
+      case 77: return launch_dp<4, 8, true, true, 3>(p, sm_count, stream, launched_grid);
+      case 78: return launch_dp<4, 8, true, true, 4>(p, sm_count, stream, launched_grid);
+      case 79: return launch_dp<8, 4, true, false, 2>(p, sm_count, stream, launched_grid);
       //                        NW UNR MINB SMEM  QUEUES
       case 50: return launch_dn<4, 4, 8, true, false>(p, sm_count, stream, launched_grid);
       case 51: return launch_dn<4, 4, 8, true, true>(p, sm_count, stream, launched_grid);

@@ -134,13 +134,32 @@ extern "C" void emu_prefilter_level(uint32_t const *src, int ws, int hs, int lev
 // The same level through the math of prefilter_dn.cu: banded ring-ordered table scaled by 2^64,
 // per-band same-face decision, quad records re-laid by pack_dn_word, subnormal-mantissa taps with
 // the exponent folded into the weight, per-channel normalisation.
-extern "C" void emu_prefilter_level_dn(uint32_t const *src, int ws, int hs, int level, int levels, int samples, int band, uint32_t *words, float *f32)
+//
+// pairs = true: the arithmetic of prefilter_dp_kernel instead — the pair-interleaved table with its
+// filled-up last band (build_paired_entries), footprint addresses taken relative to a record pointer
+// moved back by the magic-add bias (32-bit wrap-around index, 64-bit pointer), blue summed in one
+// partial per sample of a pair.
+static void emu_dn_impl(uint32_t const *src, int ws, int hs, int level, int levels, int samples, int band, uint32_t *words, float *f32, bool pairs)
 {
   BandedSamples banded = build_banded_samples(level, levels, samples, band);
   std::vector<SampleEntry> table = banded.level.entries;
   for(auto &e : table)
   {
     e.lx *= kDnTableScale; e.ly *= kDnTableScale; e.lz *= kDnTableScale; e.wh *= kDnTableScale;
+  }
+
+  if (pairs)
+  {
+    std::vector<float> paired = build_paired_entries(banded, kDnTableScale);
+    table.assign(paired.size() / 4, SampleEntry{});
+    for(size_t i = 0; i < table.size(); i += 2)
+    {
+      float const *q = paired.data() + 4 * i;
+      table[i] = SampleEntry{ q[0], q[2], q[4], q[6] };
+      table[i + 1] = SampleEntry{ q[1], q[3], q[5], q[7] };
+    }
+    if (table.size() != banded.band_min_lz.size() * (size_t)band)
+      __builtin_trap();
   }
   LevelGeom geom = make_level_geom(ws, hs);
 
@@ -192,6 +211,7 @@ extern "C" void emu_prefilter_level_dn(uint32_t const *src, int ws, int hs, int 
         Vec3f Nw = from_face_local(face, Vec3f{ Ns.x * geom.inv_hw, Ns.y * geom.inv_hh, Ns.z });
 
         float acc[3] = { 0, 0, 0 };
+        float blue[2] = { 0, 0 };
 
         for(size_t i = 0; i < table.size(); ++i)
         {
@@ -218,6 +238,17 @@ extern "C" void emu_prefilter_level_dn(uint32_t const *src, int ws, int hs, int 
           }
           ++total;
 
+          if (pairs)
+          {
+            // the kernel's address: 32-bit index that still carries the bias, pointer moved back by it
+            uint32_t raw = idx + geom.bias;
+            if ((unsigned long long)geom.bias + 6ull * geom.face_size > 0xFFFFFFFFull)
+              __builtin_trap();   // the launcher never picks the pair kernel here
+            long long element = (long long)raw - (long long)geom.bias;
+            if (element < 0 || (size_t)element != (size_t)idx)
+              __builtin_trap();
+          }
+
           if (idx >= records.size())
             __builtin_trap();
 
@@ -225,11 +256,26 @@ extern "C" void emu_prefilter_level_dn(uint32_t const *src, int ws, int hs, int 
           footprint_weights(du, dv, e.wh, e.lz, w);
 
           Rec const &rec = records[idx];
-          dn_accumulate_tap(rec.x, w[0], acc);
-          dn_accumulate_tap(rec.y, w[1], acc);
-          dn_accumulate_tap(rec.z, w[2], acc);
-          dn_accumulate_tap(rec.w, w[3], acc);
+          if (pairs)
+          {
+            float one[3] = { acc[0], acc[1], blue[i & 1] };
+            dn_accumulate_tap(rec.x, w[0], one);
+            dn_accumulate_tap(rec.y, w[1], one);
+            dn_accumulate_tap(rec.z, w[2], one);
+            dn_accumulate_tap(rec.w, w[3], one);
+            acc[0] = one[0]; acc[1] = one[1]; blue[i & 1] = one[2];
+          }
+          else
+          {
+            dn_accumulate_tap(rec.x, w[0], acc);
+            dn_accumulate_tap(rec.y, w[1], acc);
+            dn_accumulate_tap(rec.z, w[2], acc);
+            dn_accumulate_tap(rec.w, w[3], acc);
+          }
         }
+
+        if (pairs)
+          acc[2] = blue[0] + blue[1];
 
         float r = acc[0] * norm[0], g = acc[1] * norm[1], b = acc[2] * norm[2];
 
@@ -245,6 +291,28 @@ extern "C" void emu_prefilter_level_dn(uint32_t const *src, int ws, int hs, int 
   }
 
   g_fast_fraction = total ? (double)fast / (double)total : 0.0;
+}
+
+extern "C" void emu_prefilter_level_dn(uint32_t const *src, int ws, int hs, int level, int levels, int samples, int band, uint32_t *words, float *f32)
+{
+  emu_dn_impl(src, ws, hs, level, levels, samples, band, words, f32, false);
+}
+
+extern "C" void emu_prefilter_level_dp(uint32_t const *src, int ws, int hs, int level, int levels, int samples, int band, uint32_t *words, float *f32)
+{
+  emu_dn_impl(src, ws, hs, level, levels, samples, band, words, f32, true);
+}
+
+// pair-interleaved, filled-up table of the pair kernel; returns the entry count (a multiple of `band`)
+extern "C" int emu_paired_table(int level, int levels, int samples, int band, float scale, float *out, int capacity)
+{
+  BandedSamples banded = build_banded_samples(level, levels, samples, band);
+  std::vector<float> paired = build_paired_entries(banded, scale);
+  if ((int)paired.size() > capacity)
+    return -1;
+  for(size_t i = 0; i < paired.size(); ++i)
+    out[i] = paired[i];
+  return (int)(paired.size() / 4);
 }
 
 // banded table as the dn kernel sees it (unscaled): entries, per-band minimum lz; returns the entry count

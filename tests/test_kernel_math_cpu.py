@@ -103,6 +103,50 @@ def test_dn_kernel_math_matches_oracle(ws, levels, level, noise):
     assert stats["max_code"] <= 1 and stats["exp_mismatch"] == 0 and stats["identical"] >= 0.99
 
 
+@pytest.mark.parametrize("ws,levels,level,samples,noise", [(16, 5, 1, 1024, True), (32, 6, 2, 1024, True), (8, 4, 3, 1024, True), (16, 5, 2, 7, True), (24, 4, 1, 100, False)])
+def test_pair_kernel_math_matches_the_one_sample_kernel_and_the_oracle(ws, levels, level, samples, noise):
+    """prefilter_dp_kernel's arithmetic: the table with its filled-up last band read two entries at a
+    time, the record pointer moved back by the magic-add bias, blue summed per sample of a pair.
+    r and g are bit-identical to the one-sample kernel; blue differs by association only."""
+    emu = emu_lib.load()
+    src = synth.synthetic_chain(ws, ws, 1, probe=8, noise=noise, sun=False)
+    wd = ws // 2
+    n = 6 * wd * wd
+    a_w, a_f = np.zeros(n, np.uint32), np.zeros((n, 3), np.float32)
+    b_w, b_f = np.zeros(n, np.uint32), np.zeros((n, 3), np.float32)
+    emu.emu_prefilter_level_dn(src.ctypes.data, ws, ws, level, levels, samples, 16, a_w.ctypes.data, a_f.ctypes.data)
+    emu.emu_prefilter_level_dp(src.ctypes.data, ws, ws, level, levels, samples, 16, b_w.ctypes.data, b_f.ctypes.data)
+    assert np.array_equal(a_f[:, :2], b_f[:, :2])
+    assert np.allclose(a_f[:, 2], b_f[:, 2], rtol=2e-5, atol=0)   # ~sqrt(samples) * 2^-24
+
+    want_words, want_f32 = oracle_lib.prefilter_level(src, ws, ws, level, levels, samples)
+    clean = oracle_lib.edge_ambiguous_counts(wd, wd, level, levels, samples) == 0
+    assert oracle_lib.relative_error(b_f, want_f32)[clean].max() <= 1e-4
+    stats = oracle_lib.word_stats(b_w[clean], want_words[clean])
+    assert stats["max_code"] <= 1 and stats["exp_mismatch"] == 0
+
+
+@pytest.mark.parametrize("level,levels,samples", [(1, 8, 1024), (7, 8, 1024), (2, 5, 16), (3, 4, 7), (1, 12, 4096)])
+def test_paired_table_is_the_banded_table_filled_up_and_interleaved(level, levels, samples):
+    emu = emu_lib.load()
+    band = 16
+    entries = np.zeros((samples, 4), np.float32)
+    band_min = np.zeros(samples, np.float32)
+    bands = np.zeros(1, np.int32)
+    m = emu.emu_banded_table(level, levels, samples, band, entries.ctypes.data, band_min.ctypes.data, bands.ctypes.data)
+    out = np.zeros(4 * (samples + band), np.float32)
+    scale = np.float32(2.0 ** 64)
+    padded = emu.emu_paired_table(level, levels, samples, band, scale, out.ctypes.data, out.size)
+    assert padded == bands[0] * band and padded % 2 == 0
+    q = out[: 4 * padded].reshape(padded // 2, 2, 2, 2)          # pair, half (xy | zw), component, sample
+    flat = np.zeros((padded, 4), np.float32)
+    flat[0::2] = np.stack([q[:, 0, 0, 0], q[:, 0, 1, 0], q[:, 1, 0, 0], q[:, 1, 1, 0]], axis=1)
+    flat[1::2] = np.stack([q[:, 0, 0, 1], q[:, 0, 1, 1], q[:, 1, 0, 1], q[:, 1, 1, 1]], axis=1)
+    assert np.array_equal(flat[:m], entries[:m] * scale)
+    fill = flat[m:]
+    assert np.all(fill[:, :2] == 0) and np.all(fill[:, 2] == scale * np.float32(2.0 ** -60)) and np.all(fill[:, 3] == 0.5 * fill[:, 2])
+
+
 def test_dn_tap_decodes_every_field_exactly():
     """One tap of weight w through the subnormal-mantissa path == w * rgbe decode, for the
     extreme exponents, mantissas and weights (products must stay in the normal range)."""

@@ -135,7 +135,7 @@ def test_kernel_variants_agree(ctx):
     bits = synth.synthetic_chain(w, w, levels, probe=14, sun=False)
     base = None
     try:
-        for variant in (0, 10, 14, 17, 19, 27, 50, 51, 52, 53, 54, 55, 56, 57, 58):
+        for variant in (0, 10, 14, 17, 19, 27, 50, 51, 52, 53, 54, 55, 56, 57, 58, 70, 71, 72, 73, 74):
             ctx.set_prefilter_variant(variant)
             words, f32 = run_chain_device(ctx, bits, w, w, levels, 1024)
             if base is None:
@@ -145,6 +145,30 @@ def test_kernel_variants_agree(ctx):
                 assert (words == base[0]).mean() >= 0.995
     finally:
         ctx.set_prefilter_variant(0)
+
+
+def test_pair_kernel_hands_over_when_its_biased_index_would_wrap(ctx):
+    """The two-samples-at-a-time kernel folds the magic-add bias into the record pointer; for a
+    few source widths (1370 is the smallest) bias + index would wrap in 32 bits and the launcher
+    must take the one-sample kernel instead: same words as that kernel pinned, and oracle parity."""
+    ws, levels, samples = 1370, 3, 8
+    src = synth.synthetic_chain(ws, ws, 1, probe=23, sun=False)
+    d_src = torch.from_numpy(src.view(np.int32)).to(DEV)
+    wd = ws // 2
+    rows = (0, 16)
+    outs = []
+    for variant in (0, 51, 70):
+        ctx.set_prefilter_variant(variant)
+        try:
+            out = torch.zeros(6 * wd * wd, dtype=torch.int32, device=DEV)
+            f32 = torch.zeros(6 * wd * wd * 3, dtype=torch.float32, device=DEV)
+            ctx.prefilter_level_device(d_src, ws, ws, 1, levels, samples, rows[0], rows[1], out, f32)
+            ctx.synchronize()
+        finally:
+            ctx.set_prefilter_variant(0)
+        outs.append((out.cpu().numpy().view(np.uint32), f32.cpu().numpy().reshape(-1, 3)))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[2][0], outs[1][0])
+    parity.check_level(outs[0][0], outs[0][1], src, ws, ws, 1, levels, samples, rows[0], rows[1])
 
 
 def test_directions_on_cube_edges_stay_inside_the_face(ctx):
