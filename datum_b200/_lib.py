@@ -24,6 +24,7 @@ SIGNATURES = {
     "datum_ibl_set_prefilter_variant": (c_int, [c_void_p, c_int]),
     "datum_ibl_chain_bytes": (c_size_t, [c_int, c_int, c_int]),
     "datum_ibl_buildmips_cube_ibl": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "datum_ibl_bake_probes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p]),
     "datum_ibl_buildmips_cube_ibl_device": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "datum_ibl_prefilter_level_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "datum_ibl_sh9_partial_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

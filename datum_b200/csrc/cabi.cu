@@ -104,6 +104,11 @@ struct datum_ibl_ctx
   std::map<std::pair<int, int>, std::vector<DeviceTable>> tables; // (levels, samples) -> per level
 
   DeviceBuffer<uint32_t> chain;   // staged payload for the host entry point
+  DeviceBuffer<uint32_t> chain2;  // second payload of datum_ibl_bake_probes (double buffering)
+  DeviceBuffer<double> batch_sh;  // 28 doubles per probe of a batch
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;   // created on first use by datum_ibl_bake_probes
+  cudaEvent_t ev_uploaded[2] = { nullptr, nullptr }, ev_computed[2] = { nullptr, nullptr }, ev_downloaded[2] = { nullptr, nullptr };
+  cudaEvent_t ev_level[16] = {};  // level L of the current chain is complete (its download starts behind it)
   DeviceBuffer<uint4> records;    // quad records of the current source level
   DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
   DeviceBuffer<float> sh_weights; // solid angle table
@@ -338,10 +343,42 @@ namespace
     return 0;
   }
 
-  int run_chain(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, uint32_t *d_bits, float *d_f32)
+  // the copy streams and events of the host entry points, created on first use
+  int ensure_pipeline(datum_ibl_ctx *ctx)
+  {
+    if (ctx->copy_in)
+      return 0;
+
+    cudaError_t err = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking);
+    if (err == cudaSuccess)
+      err = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
+    for(int k = 0; k < 2 && err == cudaSuccess; ++k)
+    {
+      err = cudaEventCreateWithFlags(&ctx->ev_uploaded[k], cudaEventDisableTiming);
+      if (err == cudaSuccess)
+        err = cudaEventCreateWithFlags(&ctx->ev_computed[k], cudaEventDisableTiming);
+      if (err == cudaSuccess)
+        err = cudaEventCreateWithFlags(&ctx->ev_downloaded[k], cudaEventDisableTiming);
+    }
+    for(int k = 0; k < 16 && err == cudaSuccess; ++k)
+      err = cudaEventCreateWithFlags(&ctx->ev_level[k], cudaEventDisableTiming);
+
+    if (err != cudaSuccess)
+      return fail_cuda("copy streams", err);
+
+    return 0;
+  }
+
+  // `host_bits` (optional): the caller's payload; every computed level is copied into it on the
+  // download stream as soon as it is complete, under the kernels of the next level.  The caller
+  // synchronises ctx->copy_out.
+  int run_chain(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, uint32_t *d_bits, float *d_f32, uint32_t *host_bits = nullptr)
   {
     std::vector<DeviceTable> *tables = nullptr;
     if (get_tables(ctx, levels, samples, &tables))
+      return 1;
+
+    if (host_bits && ensure_pipeline(ctx))
       return 1;
 
     cudaEventRecord(ctx->ev_begin, ctx->stream);
@@ -358,6 +395,17 @@ namespace
         return 1;
 
       size_t outcount = (size_t)(width >> 1) * hd * 6;
+
+      if (host_bits)
+      {
+        cudaError_t err = cudaEventRecord(ctx->ev_level[level], ctx->stream);
+        if (err == cudaSuccess)
+          err = cudaStreamWaitEvent(ctx->copy_out, ctx->ev_level[level], 0);
+        if (err == cudaSuccess)
+          err = cudaMemcpyAsync(host_bits + (dst - d_bits), dst, outcount * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_out);
+        if (err != cudaSuccess)
+          return fail_cuda("cudaMemcpyAsync(level)", err);
+      }
 
       src += (size_t)width * height * 6;
       dst += outcount;
@@ -457,6 +505,20 @@ extern "C"
       }
 
     ctx->chain.release();
+    ctx->chain2.release();
+    ctx->batch_sh.release();
+    if (ctx->copy_in)
+      cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out)
+      cudaStreamDestroy(ctx->copy_out);
+    for(int k = 0; k < 2; ++k)
+    {
+      if (ctx->ev_uploaded[k]) cudaEventDestroy(ctx->ev_uploaded[k]);
+      if (ctx->ev_computed[k]) cudaEventDestroy(ctx->ev_computed[k]);
+      if (ctx->ev_downloaded[k]) cudaEventDestroy(ctx->ev_downloaded[k]);
+    }
+    for(int k = 0; k < 16; ++k)
+      if (ctx->ev_level[k]) cudaEventDestroy(ctx->ev_level[k]);
     ctx->records.release();
     ctx->queue_heads.release();
     ctx->sh_weights.release();
@@ -539,19 +601,102 @@ extern "C"
     if (err != cudaSuccess)
       return fail_cuda("cudaMemcpyAsync(level 0)", err);
 
-    if (run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr))
+    if (run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr, (uint32_t*)bits))
       return 1;
 
-    if (words > level0)
-    {
-      err = cudaMemcpyAsync((uint32_t*)bits + level0, ctx->chain.ptr + level0, (words - level0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
-      if (err != cudaSuccess)
-        return fail_cuda("cudaMemcpyAsync(levels)", err);
-    }
-
     err = cudaStreamSynchronize(ctx->stream);
+    if (err == cudaSuccess && ctx->copy_out)
+      err = cudaStreamSynchronize(ctx->copy_out);
     if (err != cudaSuccess)
       return fail_cuda("datum_ibl_buildmips_cube_ibl", err);
+
+    return 0;
+  }
+
+  int datum_ibl_bake_probes(datum_ibl_ctx *ctx, int count, int width, int height, int levels, int samples, void *const *bits, float *sh)
+  {
+    if (!ctx || (count > 0 && !bits))
+      return fail("datum_ibl_bake_probes: null argument");
+    if (count < 0 || !valid_chain(width, height, levels) || samples < 1)
+      return fail("datum_ibl_bake_probes: bad count/width/height/levels/samples");
+    for(int i = 0; i < count; ++i)
+      if (!bits[i])
+        return fail("datum_ibl_bake_probes: null payload in the batch");
+    if (count == 0)
+      return 0;
+
+    DeviceGuard guard(ctx->device);
+
+    size_t words = datum_ibl_chain_bytes(width, height, levels) / sizeof(uint32_t);
+    size_t level0 = (size_t)width * height * 6;
+
+    cudaError_t err = ctx->chain.reserve(words);
+    if (err == cudaSuccess && count > 1)
+      err = ctx->chain2.reserve(words);
+    if (err == cudaSuccess && sh)
+      err = ctx->batch_sh.reserve((size_t)count * 28);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(batch)", err);
+
+    if (ensure_pipeline(ctx))
+      return 1;
+
+    // sample tables and the solid-angle table are built on the compute stream before the pipeline starts
+    std::vector<DeviceTable> *tables = nullptr;
+    if (get_tables(ctx, levels, samples, &tables))
+      return 1;
+
+    uint32_t *slots[2] = { ctx->chain.ptr, ctx->chain2.ptr };
+
+    for(int i = 0; i < count; ++i)
+    {
+      int k = i & 1;
+      uint32_t *d_bits = slots[k];
+
+      // upload i waits until download i-2 has drained this payload
+      if (i >= 2)
+        err = cudaStreamWaitEvent(ctx->copy_in, ctx->ev_downloaded[k], 0);
+      if (err == cudaSuccess)
+        err = cudaMemcpyAsync(d_bits, bits[i], level0 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_in);
+      if (err == cudaSuccess)
+        err = cudaEventRecord(ctx->ev_uploaded[k], ctx->copy_in);
+      if (err == cudaSuccess)
+        err = cudaStreamWaitEvent(ctx->stream, ctx->ev_uploaded[k], 0);
+      if (err != cudaSuccess)
+        return fail_cuda("datum_ibl_bake_probes: upload", err);
+
+      if (sh && datum_ibl_sh9_partial_device(ctx, d_bits, DATUM_IBL_FORMAT_RGBE, width, height, 0, 6 * height, ctx->batch_sh.ptr + (size_t)i * 28))
+        return 1;
+
+      if (run_chain(ctx, width, height, levels, samples, d_bits, nullptr, (uint32_t*)bits[i]))
+        return 1;
+
+      err = cudaEventRecord(ctx->ev_computed[k], ctx->stream);
+      if (err == cudaSuccess)
+        err = cudaEventRecord(ctx->ev_downloaded[k], ctx->copy_out);
+      if (err != cudaSuccess)
+        return fail_cuda("datum_ibl_bake_probes: download", err);
+    }
+
+    std::vector<double> partials;
+    if (sh)
+    {
+      partials.resize((size_t)count * 28);
+      err = cudaStreamWaitEvent(ctx->copy_out, ctx->ev_computed[(count - 1) & 1], 0);
+      if (err == cudaSuccess)
+        err = cudaMemcpyAsync(partials.data(), ctx->batch_sh.ptr, partials.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_out);
+      if (err != cudaSuccess)
+        return fail_cuda("datum_ibl_bake_probes: sh9 download", err);
+    }
+
+    err = cudaStreamSynchronize(ctx->copy_out);
+    if (err == cudaSuccess)
+      err = cudaStreamSynchronize(ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("datum_ibl_bake_probes", err);
+
+    for(int i = 0; sh && i < count; ++i)
+      datum_ibl_sh9_finish(partials.data() + (size_t)i * 28, sh + (size_t)i * 27);
 
     return 0;
   }

@@ -20,6 +20,7 @@
 void image_project_sh9_cube(int width, int height, void const *level0_rgbe, float *sh);
 void image_pack_cube_faces_ibl(unsigned int const *argb, int width, int height, int levels, void *bits);
 void image_set_ibl_samples(int samples);
+void image_buildmips_cube_ibl_batch(int count, int width, int height, int levels, void *const *bits, float *sh);
 #endif
 
 #include <cstdlib>
@@ -97,6 +98,11 @@ void image_project_sh9_cube(int width, int height, void const *level0_rgbe, floa
 void image_pack_cube_faces_ibl(unsigned int const *argb, int width, int height, int levels, void *bits)
 {
   check(datum_ibl_ingest_cube_argb32_ibl(context(), width, height, levels, g_samples, argb, bits));
+}
+
+void image_buildmips_cube_ibl_batch(int count, int width, int height, int levels, void *const *bits, float *sh)
+{
+  check(datum_ibl_bake_probes(context(), count, width, height, levels, g_samples, bits, sh));
 }
 
 void image_set_ibl_samples(int samples)

@@ -24,3 +24,8 @@ void image_project_sh9_cube(int width, int height, void const *level0_rgbe, floa
 // vertical mirror, then the prefilter chain.  `bits` = the whole payload.
 void image_pack_cube_faces_ibl(unsigned int const *argb, int width, int height, int levels, void *bits);
 void image_set_ibl_samples(int samples);
+
+// `count` image_buildmips_cube_ibl calls as one: payloads of the same width/height/levels, their
+// uploads, kernels and downloads overlapped (datum_ibl_bake_probes).  `sh` (may be null)
+// receives count x float[9][3], the SH9 projection of every level 0.
+void image_buildmips_cube_ibl_batch(int count, int width, int height, int levels, void *const *bits, float *sh);

@@ -182,6 +182,20 @@ class IblContext:
         ptr = _host_pointer(bits, image_datasize(width, height, 6, levels), "bits")
         self._check(self._lib.datum_ibl_buildmips_cube_ibl(self._handle, width, height, levels, samples, ptr))
 
+    def bake_probes(self, width, height, levels, payloads, samples=1024, sh9=False):
+        """A batch of independent bakes (datum_ibl_bake_probes): every payload is a host array used
+        like the `bits` of image_buildmips_cube_ibl; uploads, kernels and downloads of consecutive
+        probes overlap (fully when the payloads are pinned).  With sh9=True returns the SH9
+        projection of every level 0 as a (count, 9, 3) float32 array."""
+        count = len(payloads)
+        need = image_datasize(width, height, 6, levels)
+        pointers = (ctypes.c_void_p * max(count, 1))()
+        for i, payload in enumerate(payloads):
+            pointers[i] = _host_pointer(payload, need, "payloads[%d]" % i)
+        sh = np.zeros((count, 9, 3), np.float32) if sh9 else None
+        self._check(self._lib.datum_ibl_bake_probes(self._handle, count, width, height, levels, samples, pointers, sh.ctypes.data if sh9 and count else None))
+        return sh
+
     def buildmips_cube_ibl_device(self, width, height, levels, d_bits, samples=1024, d_f32=None):
         """Same chain on a device-resident payload (int32/uint32 CUDA tensor); asynchronous.
         d_f32: optional float32 CUDA tensor receiving the pre-quantisation rgb of levels >= 1."""

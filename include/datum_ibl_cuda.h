@@ -71,6 +71,18 @@ size_t datum_ibl_chain_bytes(int width, int height, int levels);
 int datum_ibl_buildmips_cube_ibl(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, void *bits);
 
 /*
+ * A batch of independent bakes ("batched probes"; the reference bakes one
+ * skybox per write_skybox_asset call, tools/assetbuilder.cpp:416-491).  bits[i] is the i-th
+ * caller payload, all of the same width/height/levels, level 0 pre-filled, used exactly like
+ * the `bits` of datum_ibl_buildmips_cube_ibl.  `sh` (optional, may be NULL) receives the SH9
+ * projection (data/project.comp) of every level 0, count x float[9][3].  Results are those
+ * of `count` single calls; the uploads, the kernels and the downloads of consecutive probes
+ * overlap on three streams over two device payloads.  Pinned host payloads overlap fully;
+ * pageable ones are staged by the driver.  Synchronous.
+ */
+int datum_ibl_bake_probes(datum_ibl_ctx *ctx, int count, int width, int height, int levels, int samples, void *const *bits, float *sh);
+
+/*
  * Same chain on a device-resident payload.  `d_f32` (optional, may be NULL)
  * receives the fp32 rgb triples handed to rgbe() at tools/ibl.cpp:269 for levels
  * >= 1, level-major starting at level 1 (3 floats per texel).  Asynchronous.

@@ -152,12 +152,14 @@ def test_pair_kernel_hands_over_when_its_biased_index_would_wrap(ctx):
     few source widths (1370 is the smallest) bias + index would wrap in 32 bits and the launcher
     must take the one-sample kernel instead: same words as that kernel pinned, and oracle parity."""
     ws, levels, samples = 1370, 3, 8
-    src = synth.synthetic_chain(ws, ws, 1, probe=23, sun=False)
+    # smooth radiance: with 8 samples over 6-stop per-texel noise the 1e-7 coordinate rounding of a
+    # 1370-wide face alone flips 8 % of the words by one code (DESIGN.md "Conditioning")
+    src = synth.synthetic_chain(ws, ws, 1, probe=23, noise=False, sun=False)
     d_src = torch.from_numpy(src.view(np.int32)).to(DEV)
     wd = ws // 2
     rows = (0, 16)
     outs = []
-    for variant in (0, 51, 70):
+    for variant in (0, 51, 70, 53, 72):
         ctx.set_prefilter_variant(variant)
         try:
             out = torch.zeros(6 * wd * wd, dtype=torch.int32, device=DEV)
@@ -167,7 +169,8 @@ def test_pair_kernel_hands_over_when_its_biased_index_would_wrap(ctx):
         finally:
             ctx.set_prefilter_variant(0)
         outs.append((out.cpu().numpy().view(np.uint32), f32.cpu().numpy().reshape(-1, 3)))
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[2][0], outs[1][0])
+    assert np.array_equal(outs[2][1], outs[1][1])     # 70 ran as 51
+    assert np.array_equal(outs[4][1], outs[3][1])     # 72 ran as 53
     parity.check_level(outs[0][0], outs[0][1], src, ws, ws, 1, levels, samples, rows[0], rows[1])
 
 
