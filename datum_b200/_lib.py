@@ -27,6 +27,12 @@ SIGNATURES = {
     "datum_ibl_bake_probes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p]),
     "datum_ibl_buildmips_cube_ibl_device": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "datum_ibl_prefilter_level_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "datum_ibl_prefilter_level_peers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, ctypes.POINTER(c_void_p)]),
+    "datum_ibl_peer_barrier": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.c_uint32]),
+    "datum_ibl_peer_alloc": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
+    "datum_ibl_peer_free": (c_int, [c_void_p, c_void_p]),
+    "datum_ibl_peer_open": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
+    "datum_ibl_peer_close": (c_int, [c_void_p, c_void_p]),
     "datum_ibl_sh9_partial_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "datum_ibl_sh9_finish": (None, [c_void_p, c_void_p]),
     "datum_ibl_project_sh9": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

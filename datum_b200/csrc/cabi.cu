@@ -238,7 +238,7 @@ namespace
   }
 
   // levels at least 8 texels wide: denormal-mantissa kernel (prefilter_dn.cu)
-  int run_level_dn(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant)
+  int run_level_dn(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant, int npeers = 0, uint32_t *const *peer_words = nullptr)
   {
     int wd = ws >> 1, hd = hs >> 1;
 
@@ -262,6 +262,9 @@ namespace
     p.bands = table.bands;
     p.dst_words = d_dst_words;
     p.dst_f32 = d_dst_f32;
+    p.peers = npeers;
+    for(int k = 0; k < npeers; ++k)
+      p.peer_words[k] = peer_words[k];
     p.wd = wd;
     p.hd = hd;
     p.row_begin = row_begin;
@@ -287,7 +290,7 @@ namespace
   }
 
   // one level on the context's stream: records of the source level, then the prefilter slab
-  int run_level(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant = false)
+  int run_level(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant = false, int npeers = 0, uint32_t *const *peer_words = nullptr)
   {
     int wd = ws >> 1, hd = hs >> 1;
 
@@ -303,7 +306,10 @@ namespace
     // variant 0 and 50..58: the denormal-mantissa kernel wherever a level is wide enough for its
     // 8x4 tiles; 10..27 pin a kernel of prefilter.cu (kept for narrow levels and for A/B timing)
     if ((ctx->prefilter_variant == 0 || ctx->prefilter_variant >= 50) && wd >= 8)
-      return run_level_dn(ctx, d_src, ws, hs, table, row_begin, row_end, d_dst_words, d_dst_f32, record_dominant);
+      return run_level_dn(ctx, d_src, ws, hs, table, row_begin, row_end, d_dst_words, d_dst_f32, record_dominant, npeers, peer_words);
+
+    if (npeers > 0)
+      return fail("prefilter: peer stores need a level at least 8 texels wide (narrow levels are computed by every GPU)");
 
     cudaError_t err = ctx->records.reserve((size_t)6 * ws * hs);
     if (err != cudaSuccess)
@@ -715,6 +721,129 @@ extern "C"
       return 1;
 
     return run_level(ctx, d_src, ws, hs, (*tables)[level], row_begin, row_end, d_dst_words, d_dst_f32);
+  }
+
+  int datum_ibl_prefilter_level_peers(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, int level, int levels, int samples, int row_begin, int row_end, uint32_t *d_dst_words, int npeers, uint32_t *const *d_peer_dst_words)
+  {
+    if (!ctx || !d_src || (npeers > 0 && !d_peer_dst_words))
+      return fail("datum_ibl_prefilter_level_peers: null argument");
+    if (levels < 2 || levels > 16 || level < 1 || level >= levels || samples < 1)
+      return fail("datum_ibl_prefilter_level_peers: bad level/levels/samples");
+    if (npeers < 0 || npeers > DATUM_IBL_MAX_PEERS)
+      return fail("datum_ibl_prefilter_level_peers: at most 7 peers");
+    for(int k = 0; k < npeers; ++k)
+      if (!d_peer_dst_words[k])
+        return fail("datum_ibl_prefilter_level_peers: null peer pointer");
+
+    DeviceGuard guard(ctx->device);
+
+    std::vector<DeviceTable> *tables = nullptr;
+    if (get_tables(ctx, levels, samples, &tables))
+      return 1;
+
+    return run_level(ctx, d_src, ws, hs, (*tables)[level], row_begin, row_end, d_dst_words, nullptr, false, npeers, d_peer_dst_words);
+  }
+
+  int datum_ibl_peer_barrier(datum_ibl_ctx *ctx, int rank, int world, uint32_t *const *d_flags, uint32_t epoch)
+  {
+    if (!ctx || !d_flags)
+      return fail("datum_ibl_peer_barrier: null argument");
+    if (world < 1 || world > DATUM_IBL_MAX_PEERS + 1 || rank < 0 || rank >= world || epoch == 0)
+      return fail("datum_ibl_peer_barrier: bad rank/world/epoch");
+
+    ibl::PeerFlags flags = {};
+    for(int r = 0; r < world; ++r)
+    {
+      if (!d_flags[r])
+        return fail("datum_ibl_peer_barrier: null flag array");
+      flags.ptr[r] = d_flags[r];
+    }
+
+    DeviceGuard guard(ctx->device);
+
+    cudaError_t err = ibl::launch_peer_barrier(flags, rank, world, epoch, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("peer_barrier", err);
+    ctx->launches += 1;
+
+    return 0;
+  }
+
+  int datum_ibl_peer_alloc(datum_ibl_ctx *ctx, size_t bytes, void **d_ptr, void *handle)
+  {
+    if (!ctx || !d_ptr || !handle || bytes == 0)
+      return fail("datum_ibl_peer_alloc: null argument");
+
+    static_assert(sizeof(cudaIpcMemHandle_t) == DATUM_IBL_IPC_HANDLE_BYTES, "IPC handle size");
+
+    DeviceGuard guard(ctx->device);
+
+    void *ptr = nullptr;
+    cudaError_t err = cudaMalloc(&ptr, bytes);
+    if (err == cudaSuccess)
+      err = cudaMemsetAsync(ptr, 0, bytes, ctx->stream);
+    if (err == cudaSuccess)
+      err = cudaStreamSynchronize(ctx->stream);
+
+    cudaIpcMemHandle_t h;
+    if (err == cudaSuccess)
+      err = cudaIpcGetMemHandle(&h, ptr);
+
+    if (err != cudaSuccess)
+    {
+      if (ptr)
+        cudaFree(ptr);
+      return fail_cuda("datum_ibl_peer_alloc", err);
+    }
+
+    std::memcpy(handle, &h, sizeof(h));
+    *d_ptr = ptr;
+    return 0;
+  }
+
+  int datum_ibl_peer_free(datum_ibl_ctx *ctx, void *d_ptr)
+  {
+    if (!ctx)
+      return fail("datum_ibl_peer_free: null argument");
+    if (!d_ptr)
+      return 0;
+
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaError_t err = cudaFree(d_ptr);
+    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_peer_free", err);
+  }
+
+  int datum_ibl_peer_open(datum_ibl_ctx *ctx, void const *handle, void **d_ptr)
+  {
+    if (!ctx || !handle || !d_ptr)
+      return fail("datum_ibl_peer_open: null argument");
+
+    DeviceGuard guard(ctx->device);
+
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+
+    void *ptr = nullptr;
+    cudaError_t err = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess)
+      return fail_cuda("datum_ibl_peer_open (the GPUs must be NVLink/PCIe peers in one node)", err);
+
+    *d_ptr = ptr;
+    return 0;
+  }
+
+  int datum_ibl_peer_close(datum_ibl_ctx *ctx, void *d_ptr)
+  {
+    if (!ctx)
+      return fail("datum_ibl_peer_close: null argument");
+    if (!d_ptr)
+      return 0;
+
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaError_t err = cudaIpcCloseMemHandle(d_ptr);
+    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_peer_close", err);
   }
 
   int datum_ibl_last_prefilter_ms(datum_ibl_ctx *ctx, float *ms)

@@ -26,6 +26,7 @@ namespace ibl
 
   // ---- denormal-mantissa kernel (prefilter_dn.cu): every level at least 8 texels wide ----
 
+  constexpr int kMaxPeers = 7;      // one probe split over at most 8 GPUs (one NVSwitch domain)
   constexpr int kSampleBand = 16;   // entries per band of the banded sample table (ibl_tables.h)
 
   struct PrefilterDnParams
@@ -38,6 +39,8 @@ namespace ibl
     int bands;                // ceil(table_count / kSampleBand)
     uint32_t *dst_words;      // destination level base, rgbe words (may be null)
     float *dst_f32;           // destination level base, fp32 rgb triples before quantisation (may be null)
+    uint32_t *peer_words[kMaxPeers]; // the same destination level in the chains of other GPUs (NVLink peer stores)
+    int peers;                // how many of them: the epilogue writes every word to dst_words and to each peer
     int wd, hd;               // destination level size
     int row_begin, row_end;   // slab of the 6*hd face-major rows to compute
     LevelGeom geom;           // source level addressing constants
@@ -52,6 +55,16 @@ namespace ibl
   // variant 0 = pick by slab size and table size; 50..58 = one sample at a time, fixed <warps per tile,
   // table in shared memory, tile queues>; 70..75 = two samples at a time (prefilter_dp_kernel)
   cudaError_t launch_prefilter_dn(PrefilterDnParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid);
+
+  // Barrier between the GPUs that share one probe, on the stream: rank `rank` publishes `epoch` into
+  // slot [rank] of every peer's flag array (flags[r] = rank r's array of `world` words) and waits until
+  // its own array holds `epoch` in every slot.  Traps (loudly failing the context) after ~10 s.
+  struct PeerFlags
+  {
+    uint32_t *ptr[kMaxPeers + 1];   // by rank, own array included (host array of device pointers, passed by value)
+  };
+
+  cudaError_t launch_peer_barrier(PeerFlags const &flags, int rank, int world, uint32_t epoch, cudaStream_t stream);
 
   // also zeroes the `ncounters` tile queue heads for the prefilter launch that follows
   cudaError_t launch_build_dn_records(uint32_t const *src, uint4 *rec, int ws, int hs, int *counters, int ncounters, int sm_count, cudaStream_t stream);

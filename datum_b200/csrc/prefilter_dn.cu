@@ -393,8 +393,17 @@ namespace ibl
           float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
           size_t o = (size_t)row * p.wd + x;
 
-          if (p.dst_words)
-            p.dst_words[o] = rgbe_encode(r, g, b);
+          if (p.dst_words || p.peers > 0)
+          {
+            uint32_t word = rgbe_encode(r, g, b);
+
+            if (p.dst_words)
+              p.dst_words[o] = word;
+
+            // one probe split over several GPUs: the slab goes straight into every peer's chain
+            for(int k = 0; k < p.peers; ++k)
+              p.peer_words[k][o] = word;
+          }
 
           if (p.dst_f32)
           {
@@ -726,8 +735,17 @@ namespace ibl
           float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
           size_t o = (size_t)row * p.wd + x;
 
-          if (p.dst_words)
-            p.dst_words[o] = rgbe_encode(r, g, b);
+          if (p.dst_words || p.peers > 0)
+          {
+            uint32_t word = rgbe_encode(r, g, b);
+
+            if (p.dst_words)
+              p.dst_words[o] = word;
+
+            // one probe split over several GPUs: the slab goes straight into every peer's chain
+            for(int k = 0; k < p.peers; ++k)
+              p.peer_words[k][o] = word;
+          }
 
           if (p.dst_f32)
           {
@@ -740,6 +758,43 @@ namespace ibl
 
       __syncthreads();
     }
+  }
+
+  // ---- barrier between the GPUs sharing a probe ------------------------------------------------
+  //
+  // Runs on the bake's stream right behind a prefilter launch whose epilogue stored the slab into
+  // the peers' chains.  Stream order puts those stores before this kernel; the system-scope fence
+  // and release store publish them, the acquire loads of the waiting side order its next level
+  // behind them.
+  __global__ void peer_barrier_kernel(PeerFlags flags, int rank, int world, uint32_t epoch)
+  {
+    int r = threadIdx.x;
+    if (r >= world)
+      return;
+
+    __threadfence_system();
+
+    uint32_t *theirs = flags.ptr[r] + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(theirs), "r"(epoch) : "memory");
+
+    uint32_t const *mine = flags.ptr[rank] + r;
+    long long start = clock64();
+    for(;;)
+    {
+      uint32_t seen;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+      if ((int)(seen - epoch) >= 0)
+        break;
+      if (clock64() - start > 20000000000ll)   // ~10 s: a peer is gone; fail the context instead of hanging the GPU
+        __trap();
+      __nanosleep(200);
+    }
+  }
+
+  cudaError_t launch_peer_barrier(PeerFlags const &flags, int rank, int world, uint32_t epoch, cudaStream_t stream)
+  {
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(flags, rank, world, epoch);
+    return cudaGetLastError();
   }
 
   // ---- host-side launchers ---------------------------------------------------------------

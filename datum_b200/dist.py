@@ -133,6 +133,93 @@ def bake_single_probe(engine, chain, width, height, levels, samples=1024, group=
     return chain
 
 
+class _DeviceArray:
+    """A range of device memory owned by someone else, for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, address, count, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (address, False), "version": 3, "strides": None}
+
+
+class PeerChain:
+    """One probe's payload on every GPU of the group, each mapped into every process.
+
+    The payload (and a small flag array) is allocated by libdatum_ibl_cuda
+    (datum_ibl_peer_alloc), the 64-byte IPC handles travel once through
+    torch.distributed (all_gather_object: plumbing, not data path), and every rank
+    maps its peers' allocations.  bake() then needs no collective: the prefilter
+    kernel's epilogue stores each slab into all chains over NVLink and a one-CTA
+    barrier kernel on the same stream separates the levels."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, ctx, width, height, levels, group=None):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.group = group
+        self.dist, self.rank, self.world = _world(group)
+        if self.world > 8:
+            raise ValueError("a probe is shared by at most 8 GPUs (one NVSwitch domain)")
+        self.width, self.height, self.levels = width, height, levels
+        self.offs = ibl.level_offsets(width, height, levels)
+        self.words = self.offs[-1]
+        self.epoch = 0
+
+        # flags first (256 B), then the chain
+        self.local, handle = ctx.peer_alloc(self.FLAG_BYTES + 4 * self.words)
+        self.bases = [None] * self.world
+        self.bases[self.rank] = self.local
+        if self.world > 1:
+            handles = [None] * self.world
+            self.dist.all_gather_object(handles, handle, group=group)
+            for r in range(self.world):
+                if r != self.rank:
+                    self.bases[r] = ctx.peer_open(handles[r])
+        self.chain = torch.as_tensor(_DeviceArray(self.local + self.FLAG_BYTES, self.words), device=torch.device("cuda", ctx.device))
+
+    def chain_address(self, rank):
+        return self.bases[rank] + self.FLAG_BYTES
+
+    def barrier(self):
+        self.epoch += 1
+        self.ctx.peer_barrier(self.rank, self.world, self.bases, self.epoch)
+
+    def bake(self, samples=1024, min_split_texels=6 * 32 * 32):
+        """tools/ibl.cpp:242-279 for the probe whose level 0 every rank has put into `self.chain`;
+        on return (asynchronously, on the context's stream) every rank holds the whole chain."""
+        plan = plan_single_probe(self.width, self.height, self.levels, self.world, min_split_texels)
+        others = [r for r in range(self.world) if r != self.rank]
+
+        # nobody may still be reading the previous probe out of this chain, or lag a whole bake behind
+        if self.world > 1:
+            self.barrier()
+
+        for step in plan:
+            level = step["level"]
+            src = self.chain_address(self.rank) + 4 * self.offs[level - 1]
+            dst = self.chain_address(self.rank) + 4 * self.offs[level]
+            begin, end = step["ranges"][self.rank]
+            peers = [self.chain_address(r) + 4 * self.offs[level] for r in others] if step["split"] else []
+
+            self.ctx.prefilter_level_peers(src, step["ws"], step["hs"], level, self.levels, samples, begin, end, dst, peers)
+
+            if step["split"]:
+                self.barrier()
+
+        return self.chain
+
+    def close(self):
+        self.ctx.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)      # no peer may still be storing into a chain that goes away
+        self.chain = None
+        for r in range(self.world):
+            if r != self.rank and self.bases[r] is not None:
+                self.ctx.peer_close(self.bases[r])
+        self.ctx.peer_free(self.local)
+        self.bases = []
+
+
 def project_sh9_single_probe(engine, level0, fmt, width, height, group=None):
     """data/project.comp:23-106 for ONE level-0 cube shared by all ranks: rows split,
     28 partial sums all-reduced (the only collective), normalised on every rank."""

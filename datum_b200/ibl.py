@@ -215,6 +215,40 @@ class IblContext:
 
     # ---- SH9: data/project.comp:23-106 ----
 
+    # ---- one probe shared by the GPUs of a node: peer-mapped payloads, NVLink stores from the kernel epilogue ----
+
+    def peer_alloc(self, nbytes):
+        """Zeroed device memory other processes of the node can map.  Returns (address, 64-byte IPC handle)."""
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        self._check(self._lib.datum_ibl_peer_alloc(self._handle, nbytes, ctypes.byref(ptr), handle))
+        return int(ptr.value), bytes(handle.raw)
+
+    def peer_free(self, address):
+        self._check(self._lib.datum_ibl_peer_free(self._handle, ctypes.c_void_p(address)))
+
+    def peer_open(self, handle):
+        """Map a peer's allocation (its 64-byte IPC handle) into this process; returns the local address."""
+        ptr = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(bytes(handle), 64)
+        self._check(self._lib.datum_ibl_peer_open(self._handle, buf, ctypes.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, address):
+        self._check(self._lib.datum_ibl_peer_close(self._handle, ctypes.c_void_p(address)))
+
+    def prefilter_level_peers(self, src_address, ws, hs, level, levels, samples, row_begin, row_end, dst_address, peer_dst_addresses):
+        """prefilter_level_device on raw device addresses whose words also go to the same level of the
+        peers' payloads (addresses of the START of the destination level in each mapped chain)."""
+        n = len(peer_dst_addresses)
+        peers = (ctypes.c_void_p * max(n, 1))(*peer_dst_addresses)
+        self._check(self._lib.datum_ibl_prefilter_level_peers(self._handle, ctypes.c_void_p(src_address), ws, hs, level, levels, samples, row_begin, row_end, ctypes.c_void_p(dst_address), n, peers))
+
+    def peer_barrier(self, rank, world, flag_addresses, epoch):
+        """Barrier of the GPUs sharing a probe, on the context's stream (flag_addresses by rank)."""
+        flags = (ctypes.c_void_p * world)(*flag_addresses)
+        self._check(self._lib.datum_ibl_peer_barrier(self._handle, rank, world, flags, epoch))
+
     def sh9_partial_device(self, d_level0, fmt, width, height, row_begin, row_end, d_partial):
         """28 partial sums (27 coefficients + weight) into a float64 CUDA tensor; asynchronous."""
         texel_bytes = 4 if fmt == FORMAT_RGBE else 16

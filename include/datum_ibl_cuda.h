@@ -99,6 +99,42 @@ int datum_ibl_buildmips_cube_ibl_device(datum_ibl_ctx *ctx, int width, int heigh
  */
 int datum_ibl_prefilter_level_device(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, int level, int levels, int samples, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32);
 
+/* ---- one probe shared by several GPUs of a node (SURVEY.md 8e "one probe split") ------------ */
+
+/*
+ * The reference has no counterpart (its bake is one thread, tools/ibl.cpp:263-272).  Inside a
+ * level every destination row is independent, but level L reads all of level L-1
+ * (tools/ibl.cpp:249, 274): the GPUs sharing a probe each compute a slab of rows and need the
+ * whole level before the next one.  Here the prefilter kernel's epilogue writes its slab into
+ * every peer's payload over NVLink (peer stores), and a one-CTA barrier kernel on the same stream
+ * separates the levels: compute and exchange are one launch, no collective library call.
+ *
+ * datum_ibl_peer_alloc: device memory other processes can map; `handle` receives the 64 bytes of
+ * its cudaIpcMemHandle_t, to be sent to the peers by any means (torch.distributed in dist.py).
+ * datum_ibl_peer_open / _close: map / unmap a peer's allocation in this process.
+ */
+#define DATUM_IBL_MAX_PEERS 7
+#define DATUM_IBL_IPC_HANDLE_BYTES 64
+int datum_ibl_peer_alloc(datum_ibl_ctx *ctx, size_t bytes, void **d_ptr, void *handle);
+int datum_ibl_peer_free(datum_ibl_ctx *ctx, void *d_ptr);
+int datum_ibl_peer_open(datum_ibl_ctx *ctx, void const *handle, void **d_ptr);
+int datum_ibl_peer_close(datum_ibl_ctx *ctx, void *d_ptr);
+
+/*
+ * datum_ibl_prefilter_level_device whose rgbe words ALSO go to `npeers` (<= 7) other chains:
+ * d_peer_dst_words[k] points at the START of the destination level in peer k's mapped payload.
+ * Asynchronous.
+ */
+int datum_ibl_prefilter_level_peers(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, int level, int levels, int samples, int row_begin, int row_end, uint32_t *d_dst_words, int npeers, uint32_t *const *d_peer_dst_words);
+
+/*
+ * Barrier of the `world` (<= 8) GPUs on the context's stream: d_flags[r] = rank r's flag array
+ * (world 32-bit words, zero-initialised, peer-mapped; d_flags[rank] the local one).  Every call of
+ * a bake uses the next `epoch` (> 0, increasing).  Asynchronous; a peer that never arrives fails
+ * the context after ~10 s instead of hanging the device.
+ */
+int datum_ibl_peer_barrier(datum_ibl_ctx *ctx, int rank, int world, uint32_t *const *d_flags, uint32_t epoch);
+
 /* ---- equirectangular HDR image -> cube: tools/hdr.cpp:331-359, tools/ibl.cpp:283-288 ---- */
 
 /*

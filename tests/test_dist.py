@@ -115,6 +115,18 @@ def _gpu_worker(rank, world, port, w, levels, samples, out_dir):
         cube = torch.from_numpy(synth.synthetic_cube(128, 128, probe=44)).to(engine.device)
         sh = ibl_dist.project_sh9_single_probe(engine, cube, FORMAT_F32, 128, 128)
         np.save(os.path.join(out_dir, "sh_%d.npy" % rank), sh)
+
+        # the same probe through peer-mapped payloads: slabs stored into the peer's chain by the
+        # kernel epilogue, barrier kernel between levels, no collective; twice, to reuse the chains
+        shared = ibl_dist.PeerChain(ctx, w, w, levels)
+        for probe in (45, 43):
+            with torch.cuda.stream(ctx.torch_stream()):
+                shared.chain.copy_(torch.from_numpy(synth.synthetic_chain(w, w, levels, probe=probe).view(np.int32)), non_blocking=False)
+                shared.bake(samples)
+                fused = shared.chain.clone()
+            ctx.synchronize()
+        np.save(os.path.join(out_dir, "fused_%d.npy" % rank), fused.cpu().numpy().view(np.uint32))
+        shared.close()
         ctx.close()
     finally:
         dist.destroy_process_group()
@@ -137,6 +149,10 @@ def test_two_gpus_split_one_probe_over_nccl(tmp_path, ctx):
     assert np.array_equal(a[: offs[1]], want[: offs[1]])
     stats = oracle_lib.word_stats(a[offs[1]:], want[offs[1]:])
     assert oracle_lib.words_within_one_code(stats, 0.99), stats
+
+    # peer stores: the same slabs, the same kernels -> the same words as the all-gather path
+    assert np.array_equal(np.load(tmp_path / "fused_0.npy"), a)
+    assert np.array_equal(np.load(tmp_path / "fused_1.npy"), a)
 
     cube = synth.synthetic_cube(128, 128, probe=44)
     want_sh = oracle_lib.project_sh9(cube, FORMAT_F32, 128, 128)
