@@ -5,10 +5,9 @@
 // depends only on (x, y), not on the face, and its four-atan form cancels
 // catastrophically in fp32 once faces exceed a few hundred texels, so it is
 // evaluated ONCE per (x, y) in fp64 into a table that the context caches per
-// face size.  The projection itself is HBM-bound (16 B/texel RGBA32F, 100 B per
-// (x, y) column of six faces): one thread per (x, y) reads the six face texels
-// with coalesced 16-byte loads, shares the normalisation across the six
-// signed-permutation rays, accumulates 27 sums + the weight sum in registers,
+// face size.  The projection itself streams the slab once (16 B/texel RGBA32F):
+// a CTA takes 1024-texel segments of rows, every thread issues its four 16-byte
+// loads before any arithmetic, accumulates 27 sums + the weight sum in registers,
 // then warp-shuffle and block-reduce in fp64.  Block partials are summed in a
 // fixed order by a second kernel, so the result is run-to-run deterministic.
 
@@ -85,54 +84,105 @@ namespace ibl
   }
 
   constexpr int kSh9Threads = 256;
+  constexpr int kSh9Unroll = 4;                               // texels per thread and work item: four 16-byte loads in flight
+  constexpr int kSh9Segment = kSh9Threads * kSh9Unroll;       // texels of one row a CTA takes at a time
+
+  // face rays as in data/convolve.comp:85-100 (equal to project.comp:27-32's quaternions);
+  // (a, b, c) = (u, v, 1) / |(u, v, 1)|
+  template<int FACE>
+  __device__ __forceinline__ void face_ray(float a, float b, float c, float &rx, float &ry, float &rz)
+  {
+    switch (FACE)
+    {
+      case 0: rx = c;  ry = b;  rz = a;  break;
+      case 1: rx = -c; ry = b;  rz = -a; break;
+      case 2: rx = a;  ry = -c; rz = -b; break;
+      case 3: rx = a;  ry = c;  rz = b;  break;
+      case 4: rx = a;  ry = b;  rz = -c; break;
+      default: rx = -a; ry = b; rz = c;  break;
+    }
+  }
+
+  // One segment of one row of one face: the CTA's threads take texels x0 + j*256 + tid.  All loads of
+  // the segment are issued before the arithmetic of the first texel: memory-level parallelism is what
+  // keeps this kernel near the HBM roofline (16 B per texel against ~64 instructions).
+  template<int FORMAT, int FACE>
+  __device__ __forceinline__ void sh9_row_segment(void const *__restrict__ level0, float const *__restrict__ weights, int w, size_t row_offset, int weight_offset, int x0, float v, float vv1, float two_inv_w, float u_bias, float acc[28])
+  {
+    float r[kSh9Unroll], g[kSh9Unroll], bl[kSh9Unroll], weight[kSh9Unroll];
+
+    #pragma unroll
+    for(int j = 0; j < kSh9Unroll; ++j)
+    {
+      int x = x0 + j * kSh9Threads + (int)threadIdx.x;
+      if (x < w)
+      {
+        load_texel<FORMAT>(level0, row_offset + x, r[j], g[j], bl[j]);
+        weight[j] = __ldg(weights + weight_offset + x);
+      }
+      else
+      {
+        r[j] = g[j] = bl[j] = 0.0f;
+        weight[j] = 0.0f;          // a texel past the row end adds exact zeros
+      }
+    }
+
+    #pragma unroll
+    for(int j = 0; j < kSh9Unroll; ++j)
+    {
+      int x = x0 + j * kSh9Threads + (int)threadIdx.x;
+
+      // project.comp:53-54: u = 2 (x + .5) / w - 1, ray = normalize(rot * (u, v, -1))
+      float u = fmaf((float)x, two_inv_w, u_bias);
+      float inv = rsqrtf(fmaf(u, u, vv1));
+
+      float rx, ry, rz;
+      face_ray<FACE>(u * inv, v * inv, inv, rx, ry, rz);
+
+      sh9_accumulate(acc, weight[j] * r[j], weight[j] * g[j], weight[j] * bl[j], rx, ry, rz);
+      acc[27] += weight[j];
+    }
+  }
 
   template<int FORMAT>
-  __global__ void __launch_bounds__(kSh9Threads) sh9_partial_kernel(void const *__restrict__ level0, float const *__restrict__ weights, int w, int h, int row_begin, int row_end, double *__restrict__ block_partials)
+  __global__ void __launch_bounds__(kSh9Threads, 4) sh9_partial_kernel(void const *__restrict__ level0, float const *__restrict__ weights, int w, int h, int row_begin, int row_end, double *__restrict__ block_partials)
   {
     float acc[28];
     #pragma unroll
     for(int k = 0; k < 28; ++k)
       acc[k] = 0.0f;
 
-    const int pixels = w * h;
     const float inv_w = 1.0f / (float)w, inv_h = 1.0f / (float)h;
+    const float two_inv_w = 2.0f * inv_w, u_bias = inv_w - 1.0f;
 
-    for(int p = blockIdx.x * kSh9Threads + threadIdx.x; p < pixels; p += gridDim.x * kSh9Threads)
+    // work items: (row of the slab, segment of that row) in row order; rows are face-major, so the
+    // slab of a GPU that shares the cube with others is one contiguous range of the level.  (Tried and
+    // measured slower on 4096^2 faces, 0.343 ms as is: item order with the six faces of a table stretch
+    // side by side for L2 reuse of the solid angles, 0.42 ms; the solid angle from a Taylor form instead
+    // of the table, 0.38 ms; five row moments per channel folded once per row, 0.40 ms.)
+    const int segments = (w + kSh9Segment - 1) / kSh9Segment;
+    const long long items = (long long)(row_end - row_begin) * segments;
+
+    for(long long item = blockIdx.x; item < items; item += gridDim.x)
     {
-      int x = p % w, y = p / w;
+      int row = row_begin + (int)(item / segments);
+      int x0 = (int)(item % segments) * kSh9Segment;
+      int face = row / h;
+      int y = row - face * h;
 
-      // project.comp:53-54: uv, and the shared 1/|(+-u, +-v, +-1)| of the six face rays
-      float u = 2.0f * ((float)x + 0.5f) * inv_w - 1.0f;
       float v = 2.0f * ((float)y + 0.5f) * inv_h - 1.0f;
-      float inv = rsqrtf(fmaf(u, u, fmaf(v, v, 1.0f)));
-      float a = u * inv, b = v * inv, c = inv;
+      float vv1 = fmaf(v, v, 1.0f);
+      size_t row_offset = (size_t)row * w;
+      int weight_offset = y * w;
 
-      float weight = __ldg(weights + p);
-
-      #pragma unroll
-      for(int face = 0; face < 6; ++face)
+      switch (face)
       {
-        int row = face * h + y;
-        if (row < row_begin || row >= row_end)
-          continue;
-
-        float r, g, bl;
-        load_texel<FORMAT>(level0, (size_t)row * w + x, r, g, bl);
-
-        // face rays as in data/convolve.comp:85-100 (equal to project.comp:27-32's quaternions)
-        float rx, ry, rz;
-        switch (face)
-        {
-          case 0: rx = c;  ry = b;  rz = a;  break;
-          case 1: rx = -c; ry = b;  rz = -a; break;
-          case 2: rx = a;  ry = -c; rz = -b; break;
-          case 3: rx = a;  ry = c;  rz = b;  break;
-          case 4: rx = a;  ry = b;  rz = -c; break;
-          default: rx = -a; ry = b; rz = c;  break;
-        }
-
-        sh9_accumulate(acc, weight * r, weight * g, weight * bl, rx, ry, rz);
-        acc[27] += weight;
+        case 0: sh9_row_segment<FORMAT, 0>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
+        case 1: sh9_row_segment<FORMAT, 1>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
+        case 2: sh9_row_segment<FORMAT, 2>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
+        case 3: sh9_row_segment<FORMAT, 3>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
+        case 4: sh9_row_segment<FORMAT, 4>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
+        default: sh9_row_segment<FORMAT, 5>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
       }
     }
 
@@ -166,18 +216,22 @@ namespace ibl
     }
   }
 
-  // fixed-order sum of the block partials: deterministic
-  __global__ void __launch_bounds__(32) sh9_combine_kernel(double const *__restrict__ block_partials, int blocks, double *__restrict__ partial)
+  // fixed-order sum of the block partials (warp k sums component k, lanes stride over the blocks,
+  // shuffle tree): deterministic
+  __global__ void __launch_bounds__(28 * 32) sh9_combine_kernel(double const *__restrict__ block_partials, int blocks, double *__restrict__ partial)
   {
-    int k = threadIdx.x;
-    if (k >= 28)
-      return;
+    int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     double v = 0;
-    for(int i = 0; i < blocks; ++i)
+    for(int i = lane; i < blocks; i += 32)
       v += block_partials[(size_t)i * 28 + k];
 
-    partial[k] = v;
+    #pragma unroll
+    for(int offset = 16; offset > 0; offset >>= 1)
+      v += __shfl_down_sync(0xffffffffu, v, offset);
+
+    if (lane == 0)
+      partial[k] = v;
   }
 
   // ---- irradiance cube from SH9: data/lighting.inc:351-366, 371 ---------------------
@@ -250,10 +304,10 @@ namespace ibl
 
   int sh9_partial_blocks(int w, int h, int sm_count)
   {
-    int pixels = w * h;
-    int blocks = (pixels + kSh9Threads - 1) / kSh9Threads;
-    int cap = sm_count * 8;
-    return blocks < cap ? (blocks < 1 ? 1 : blocks) : cap;
+    // upper bound for any slab of the cube: one CTA per (row, segment) item up to 4 resident CTAs per SM
+    long long items = (long long)6 * h * ((w + kSh9Segment - 1) / kSh9Segment);
+    long long cap = (long long)sm_count * 4;
+    return (int)(items < cap ? (items < 1 ? 1 : items) : cap);
   }
 
   cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, double *partial, cudaStream_t stream)
@@ -267,7 +321,7 @@ namespace ibl
     if (err != cudaSuccess)
       return err;
 
-    sh9_combine_kernel<<<1, 32, 0, stream>>>(block_partials, blocks, partial);
+    sh9_combine_kernel<<<1, 28 * 32, 0, stream>>>(block_partials, blocks, partial);
 
     return cudaGetLastError();
   }
