@@ -303,6 +303,42 @@ namespace
     if (row_begin == row_end)
       return 0;
 
+    // tail levels (a few hundred texels): lanes are samples, no record pass.  Variant 80 pins this
+    // kernel for every level (A/B, tests).
+    if ((ctx->prefilter_variant == 0 && (size_t)(row_end - row_begin) * wd <= (size_t)ibl::kTailTexels) || ctx->prefilter_variant == 80)
+    {
+      ibl::PrefilterTailParams p = {};
+      p.src = d_src;
+      p.table = table.d_banded;
+      p.table_count = table.count;
+      p.dst_words = d_dst_words;
+      p.dst_f32 = d_dst_f32;
+      p.peers = npeers;
+      for(int k = 0; k < npeers; ++k)
+        p.peer_words[k] = peer_words[k];
+      p.wd = wd;
+      p.hd = hd;
+      p.row_begin = row_begin;
+      p.row_end = row_end;
+      p.geom = ibl::make_level_geom(ws, hs);
+      for(int f = 0; f < 6; ++f)
+        p.quats[f] = ctx->quats[f];
+      ibl::dn_channel_norms(table.total_weight, p.norm);
+      p.exp_mul = 0x00800000u;
+
+      int slot = record_dominant ? begin_dominant(ctx, (double)(row_end - row_begin) * wd * (double)table.samples) : -1;
+
+      cudaError_t err = ibl::launch_prefilter_tail(p, ctx->sm_count, ctx->stream);
+      if (err != cudaSuccess)
+        return fail_cuda("prefilter_tail", err);
+      ctx->launches += 1;
+
+      if (slot >= 0)
+        cudaEventRecord(ctx->ring_end[slot], ctx->stream);
+
+      return 0;
+    }
+
     // variant 0 and 50..58: the denormal-mantissa kernel wherever a level is wide enough for its
     // 8x4 tiles; 10..27 pin a kernel of prefilter.cu (kept for narrow levels and for A/B timing)
     if ((ctx->prefilter_variant == 0 || ctx->prefilter_variant >= 50) && wd >= 8)

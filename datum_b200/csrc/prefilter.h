@@ -52,6 +52,32 @@ namespace ibl
     int queues, chunk, queued;
   };
 
+  // ---- tail levels (prefilter_dn.cu, prefilter_tail_kernel): a few hundred texels ----
+  //
+  // One CTA per output texel, LANES are samples: the 1024 samples of a texel are one to four steps
+  // deep instead of 32, the four footprint words come straight from the source level (no record pass).
+  struct PrefilterTailParams
+  {
+    uint32_t const *src;      // SOURCE level words (6*ws*hs), tools/ibl.cpp layout
+    float4 const *table;      // banded sample table of this level scaled by kDnTableScale (any order works)
+    int table_count;
+    uint32_t *dst_words;
+    float *dst_f32;
+    uint32_t *peer_words[kMaxPeers];
+    int peers;
+    int wd, hd;
+    int row_begin, row_end;
+    LevelGeom geom;
+    Quatf quats[6];
+    float norm[3];
+    uint32_t exp_mul;
+  };
+
+  // slabs up to this many texels go to the tail kernel
+  constexpr int kTailTexels = 1536;
+
+  cudaError_t launch_prefilter_tail(PrefilterTailParams const &p, int sm_count, cudaStream_t stream);
+
   // variant 0 = pick by slab size and table size; 50..58 = one sample at a time, fixed <warps per tile,
   // table in shared memory, tile queues>; 70..75 = two samples at a time (prefilter_dp_kernel)
   cudaError_t launch_prefilter_dn(PrefilterDnParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid);

@@ -760,6 +760,122 @@ namespace ibl
     }
   }
 
+  // ---- tail levels: lanes are samples ----------------------------------------------------------
+  //
+  // The last levels of a chain hold a few hundred texels: with one texel per lane the machine is
+  // empty and every warp walks its samples one after the other (level 7 of C2: 3 tiles, 32 samples
+  // deep per warp, 14 us for 1e5 texel-samples).  Here a CTA owns ONE texel and its lanes take
+  // consecutive table entries: NW*32 samples per step, warp-shuffle + shared-memory reduction at the
+  // end.  Every sample goes through the cube-face selection (at these roughnesses almost all leave
+  // the face anyway); the four words of a footprint are read from the source level itself (it fits in
+  // L1/L2) and re-laid in registers, so the level needs no record pass: one launch instead of two.
+  // Arithmetic per sample is the one-sample kernel's general path.
+  template<int NW>
+  __global__ void __launch_bounds__(32 * NW) prefilter_tail_kernel(PrefilterTailParams p)
+  {
+    __shared__ float s_red[NW][3];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const int texel = blockIdx.x;
+    const int row = p.row_begin + texel / p.wd;
+    const int x = texel - (texel / p.wd) * p.wd;
+    const int face = row / p.hd;
+    const int y = row - face * p.hd;
+
+    Vec3f N = texel_normal(p.quats[face], x, y, p.wd, p.hd);
+    Vec3f T, B;
+    tangent_frame(N, T, B);
+
+    float acc[3] = { 0.0f, 0.0f, 0.0f };
+
+    for(int s = threadIdx.x; s < p.table_count; s += 32 * NW)
+    {
+      float4 e = __ldg(p.table + s);
+
+      float Lx = fmaf(e.z, N.x, fmaf(e.y, B.x, e.x * T.x));
+      float Ly = fmaf(e.z, N.y, fmaf(e.y, B.y, e.x * T.y));
+      float Lz = fmaf(e.z, N.z, fmaf(e.y, B.z, e.x * T.z));
+
+      float du, dv;
+      uint32_t idx = cube_footprint(p.geom, Lx, Ly, Lz, du, dv);     // top-left texel of the footprint; i <= ws-2, j <= hs-2
+
+      float w[4];
+      footprint_weights(du, dv, e.w, e.z, w);
+
+      uint32_t const *t = p.src + idx;
+      dn_accumulate_tap(pack_dn_word(__ldg(t)), w[0], acc);
+      dn_accumulate_tap(pack_dn_word(__ldg(t + 1)), w[1], acc);
+      dn_accumulate_tap(pack_dn_word(__ldg(t + p.geom.ws)), w[2], acc);
+      dn_accumulate_tap(pack_dn_word(__ldg(t + p.geom.ws + 1)), w[3], acc);
+    }
+
+    #pragma unroll
+    for(int c = 0; c < 3; ++c)
+    {
+      float v = acc[c];
+      #pragma unroll
+      for(int offset = 16; offset > 0; offset >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, offset);
+      if (lane == 0)
+        s_red[warp][c] = v;
+    }
+
+    __syncthreads();
+
+    if (threadIdx.x == 0)
+    {
+      float sum[3] = { 0.0f, 0.0f, 0.0f };
+      #pragma unroll
+      for(int w = 0; w < NW; ++w)
+      {
+        #pragma unroll
+        for(int c = 0; c < 3; ++c)
+          sum[c] += s_red[w][c];
+      }
+
+      // sum/totalweight of ibl.cpp:186, then rgbe() of ibl.cpp:269
+      float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
+      size_t o = (size_t)row * p.wd + x;
+
+      if (p.dst_words || p.peers > 0)
+      {
+        uint32_t word = rgbe_encode(r, g, b);
+
+        if (p.dst_words)
+          p.dst_words[o] = word;
+
+        for(int k = 0; k < p.peers; ++k)
+          p.peer_words[k][o] = word;
+      }
+
+      if (p.dst_f32)
+      {
+        p.dst_f32[3*o + 0] = r;
+        p.dst_f32[3*o + 1] = g;
+        p.dst_f32[3*o + 2] = b;
+      }
+    }
+  }
+
+  cudaError_t launch_prefilter_tail(PrefilterTailParams const &p, int sm_count, cudaStream_t stream)
+  {
+    int texels = (p.row_end - p.row_begin) * p.wd;
+    if (texels <= 0)
+      return cudaSuccess;
+
+    // warps per texel: enough CTAs to cover the machine first, then depth; never more lanes than samples
+    (void)sm_count;
+    if (texels >= 1024 || p.table_count <= 256)
+      prefilter_tail_kernel<8><<<texels, 256, 0, stream>>>(p);
+    else if (texels >= 256 || p.table_count <= 512)
+      prefilter_tail_kernel<16><<<texels, 512, 0, stream>>>(p);
+    else
+      prefilter_tail_kernel<32><<<texels, 1024, 0, stream>>>(p);
+
+    return cudaGetLastError();
+  }
+
   // ---- barrier between the GPUs sharing a probe ------------------------------------------------
   //
   // Runs on the bake's stream right behind a prefilter launch whose epilogue stored the slab into

@@ -94,8 +94,10 @@ def test_host_and_device_entry_points_agree(ctx):
 
 def test_row_slabs_reproduce_the_full_level(ctx):
     """Multi-GPU sharding primitive: a level computed as row slabs equals one full launch.  A
-    slab may pick another warp split than the full level (fp32 sums associate differently), so
-    the comparison is the packed-word criterion plus a 2e-5 bound on the fp32 values."""
+    slab may pick another kernel than the full level (here: slabs of at most 1536 texels go to the
+    tail kernel, whose tangent frame never passes through face-local coordinates and whose sums
+    associate differently), so the comparison is the packed-word criterion plus a 1e-4 bound on the
+    fp32 values — a tenth of the tolerance against the reference."""
     ws, levels, level = 64, 7, 2
     src = synth.synthetic_chain(ws, ws, 1, probe=13)
     d_src = torch.from_numpy(src.view(np.int32)).to(DEV)
@@ -116,7 +118,7 @@ def test_row_slabs_reproduce_the_full_level(ctx):
 
     try:
         full, full_f, slabs, slabs_f = run(0)
-        assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 2e-5
+        assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 1e-4
         stats = oracle_lib.word_stats(slabs.cpu().numpy().view(np.uint32), full.cpu().numpy().view(np.uint32))
         assert oracle_lib.words_within_one_code(stats, 0.995), stats
         # pinned variants (one of each kernel): same warp split; only the same-face sample count of the re-cut tiles differs
@@ -135,7 +137,7 @@ def test_kernel_variants_agree(ctx):
     bits = synth.synthetic_chain(w, w, levels, probe=14, sun=False)
     base = None
     try:
-        for variant in (0, 10, 14, 17, 19, 27, 50, 51, 52, 53, 54, 55, 56, 57, 58, 70, 71, 72, 73, 74):
+        for variant in (0, 10, 14, 17, 19, 27, 50, 51, 52, 53, 54, 55, 56, 57, 58, 70, 71, 72, 73, 74, 80):
             ctx.set_prefilter_variant(variant)
             words, f32 = run_chain_device(ctx, bits, w, w, levels, 1024)
             if base is None:
@@ -243,4 +245,8 @@ def test_launch_counter_counts_our_kernels(ctx):
     before = ctx.launch_count
     bits = synth.synthetic_chain(16, 16, 5)
     ctx.image_buildmips_cube_ibl(16, 16, 5, bits)
-    assert ctx.launch_count - before == 2 * 4      # per level: quad-record build + prefilter
+    assert ctx.launch_count - before == 4          # tail levels (<= 1536 texels): one launch each, no record pass
+    before = ctx.launch_count
+    bits = synth.synthetic_chain(64, 64, 3)
+    ctx.image_buildmips_cube_ibl(64, 64, 3, bits)
+    assert ctx.launch_count - before == 2 + 1      # 32^2 faces: quad-record build + prefilter; 16^2 faces: tail kernel
