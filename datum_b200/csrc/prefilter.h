@@ -74,7 +74,7 @@ namespace ibl
   };
 
   // slabs up to this many texels go to the tail kernel
-  constexpr int kTailTexels = 1536;
+  constexpr int kTailTexels = 6144;
 
   cudaError_t launch_prefilter_tail(PrefilterTailParams const &p, int sm_count, cudaStream_t stream);
 

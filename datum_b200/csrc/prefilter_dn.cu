@@ -774,6 +774,7 @@ namespace ibl
   __global__ void __launch_bounds__(32 * NW) prefilter_tail_kernel(PrefilterTailParams p)
   {
     __shared__ float s_red[NW][3];
+    __shared__ float s_frame[9];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -783,9 +784,22 @@ namespace ibl
     const int face = row / p.hd;
     const int y = row - face * p.hd;
 
-    Vec3f N = texel_normal(p.quats[face], x, y, p.wd, p.hd);
-    Vec3f T, B;
-    tangent_frame(N, T, B);
+    // the texel's frame (exactly rounded divisions and square roots, ~200 instructions) once per CTA
+    if (threadIdx.x == 0)
+    {
+      Vec3f n = texel_normal(p.quats[face], x, y, p.wd, p.hd);
+      Vec3f t, b;
+      tangent_frame(n, t, b);
+      s_frame[0] = t.x; s_frame[1] = t.y; s_frame[2] = t.z;
+      s_frame[3] = b.x; s_frame[4] = b.y; s_frame[5] = b.z;
+      s_frame[6] = n.x; s_frame[7] = n.y; s_frame[8] = n.z;
+    }
+
+    __syncthreads();
+
+    const Vec3f T = { s_frame[0], s_frame[1], s_frame[2] };
+    const Vec3f B = { s_frame[3], s_frame[4], s_frame[5] };
+    const Vec3f N = { s_frame[6], s_frame[7], s_frame[8] };
 
     float acc[3] = { 0.0f, 0.0f, 0.0f };
 
@@ -866,7 +880,9 @@ namespace ibl
 
     // warps per texel: enough CTAs to cover the machine first, then depth; never more lanes than samples
     (void)sm_count;
-    if (texels >= 1024 || p.table_count <= 256)
+    if (texels >= 4096 || p.table_count <= 128)
+      prefilter_tail_kernel<4><<<texels, 128, 0, stream>>>(p);
+    else if (texels >= 1024 || p.table_count <= 256)
       prefilter_tail_kernel<8><<<texels, 256, 0, stream>>>(p);
     else if (texels >= 256 || p.table_count <= 512)
       prefilter_tail_kernel<16><<<texels, 512, 0, stream>>>(p);

@@ -94,7 +94,7 @@ def test_host_and_device_entry_points_agree(ctx):
 
 def test_row_slabs_reproduce_the_full_level(ctx):
     """Multi-GPU sharding primitive: a level computed as row slabs equals one full launch.  A
-    slab may pick another kernel than the full level (here: slabs of at most 1536 texels go to the
+    slab may pick another kernel than the full level (here: slabs of at most 6144 texels go to the
     tail kernel, whose tangent frame never passes through face-local coordinates and whose sums
     associate differently), so the comparison is the packed-word criterion plus a 1e-4 bound on the
     fp32 values — a tenth of the tolerance against the reference."""
@@ -245,8 +245,8 @@ def test_launch_counter_counts_our_kernels(ctx):
     before = ctx.launch_count
     bits = synth.synthetic_chain(16, 16, 5)
     ctx.image_buildmips_cube_ibl(16, 16, 5, bits)
-    assert ctx.launch_count - before == 4          # tail levels (<= 1536 texels): one launch each, no record pass
+    assert ctx.launch_count - before == 4          # tail levels (<= 6144 texels): one launch each, no record pass
     before = ctx.launch_count
-    bits = synth.synthetic_chain(64, 64, 3)
-    ctx.image_buildmips_cube_ibl(64, 64, 3, bits)
-    assert ctx.launch_count - before == 2 + 1      # 32^2 faces: quad-record build + prefilter; 16^2 faces: tail kernel
+    bits = synth.synthetic_chain(128, 128, 3)
+    ctx.image_buildmips_cube_ibl(128, 128, 3, bits)
+    assert ctx.launch_count - before == 2 + 1      # 64^2 faces: quad-record build + prefilter; 32^2 faces: tail kernel
