@@ -485,12 +485,20 @@ extern "C"
   // a quotient that rounds to 1.0 wraps to the opposite edge through fmod2,
   // ibl.cpp:37-38), so the reference's own strict and -ffast-math builds disagree
   // on them.  The parity tests hold texels with a non-zero count to a looser bound.
+  void oracle_edge_ambiguous_counts_rows(int wd, int hd, float roughness, int samples, float eps, int row_begin, int row_end, int32_t *counts, int threads);
+
   void oracle_edge_ambiguous_counts(int wd, int hd, float roughness, int samples, float eps, int32_t *counts, int threads)
+  {
+    oracle_edge_ambiguous_counts_rows(wd, hd, roughness, samples, eps, 0, 6 * hd, counts, threads);
+  }
+
+  // the same for the face-major rows [row_begin, row_end) only; `counts` is indexed from the start of the level
+  void oracle_edge_ambiguous_counts_rows(int wd, int hd, float roughness, int samples, float eps, int row_begin, int row_end, int32_t *counts, int threads)
   {
     Xform rot[6];
     face_rotations(rot);
 
-    parallel_rows(0, 6 * hd, threads, [&](int row)
+    parallel_rows(row_begin, row_end, threads, [&](int row)
     {
       int face = row / hd;
       int y = row % hd;

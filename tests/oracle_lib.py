@@ -38,6 +38,7 @@ def oracle():
         lib.oracle_convolve_dir.argtypes = [c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]
         lib.oracle_trace_samples.argtypes = [c_float, c_int, c_void_p, c_void_p, c_void_p]
         lib.oracle_edge_ambiguous_counts.argtypes = [c_int, c_int, c_float, c_int, c_float, c_void_p, c_int]
+        lib.oracle_edge_ambiguous_counts_rows.argtypes = [c_int, c_int, c_float, c_int, c_float, c_int, c_int, c_void_p, c_int]
         lib.oracle_prefilter_level.argtypes = [c_void_p, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_int]
         lib.oracle_buildmips_cube_ibl.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int]
         lib.oracle_sh9_partial.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
@@ -127,10 +128,14 @@ def buildmips_cube_ibl(width, height, levels, bits, samples=1024, threads=0, wan
     return f32
 
 
-def edge_ambiguous_counts(wd, hd, level, levels, samples=1024, eps=2e-6, threads=0):
+def edge_ambiguous_counts(wd, hd, level, levels, samples=1024, eps=2e-6, threads=0, row_begin=0, row_end=None):
+    """Per texel: samples lying within eps of a cube-face boundary.  With a row range only those
+    rows are evaluated (the others stay 0): the full-size spot checks need a few rows of a big level."""
     counts = np.zeros(6 * hd * wd, np.int32)
     roughness = np.float32(level) / np.float32(levels - 1)
-    oracle().oracle_edge_ambiguous_counts(wd, hd, float(roughness), samples, eps, counts.ctypes.data, threads)
+    if row_end is None:
+        row_end = 6 * hd
+    oracle().oracle_edge_ambiguous_counts_rows(wd, hd, float(roughness), samples, eps, row_begin, row_end, counts.ctypes.data, threads)
     return counts
 
 
