@@ -21,8 +21,11 @@ void image_project_sh9_cube(int width, int height, void const *level0_rgbe, floa
 void image_pack_cube_faces_ibl(unsigned int const *argb, int width, int height, int levels, void *bits);
 void image_set_ibl_samples(int samples);
 void image_buildmips_cube_ibl_batch(int count, int width, int height, int levels, void *const *bits, float *sh);
+void image_pack_irradiance_sh9(int width, int height, void const *level0_rgbe, void *bits);
+void image_pack_irradiance_cube(void const *sh9_bits, int width, int height, void *bits);
 #endif
 
+#include <cstdint>
 #include <cstdlib>
 #include <mutex>
 #include <stdexcept>
@@ -103,6 +106,17 @@ void image_pack_cube_faces_ibl(unsigned int const *argb, int width, int height, 
 void image_buildmips_cube_ibl_batch(int count, int width, int height, int levels, void *const *bits, float *sh)
 {
   check(datum_ibl_bake_probes(context(), count, width, height, levels, g_samples, bits, sh));
+}
+
+void image_pack_irradiance_sh9(int width, int height, void const *level0_rgbe, void *bits)
+{
+  // payload of a 3 x 9 x 1 f32 image == float L[9][3]
+  check(datum_ibl_project_sh9(context(), level0_rgbe, DATUM_IBL_FORMAT_RGBE, width, height, static_cast<float*>(bits)));
+}
+
+void image_pack_irradiance_cube(void const *sh9_bits, int width, int height, void *bits)
+{
+  check(datum_ibl_sh9_irradiance_cube(context(), static_cast<float const*>(sh9_bits), width, height, static_cast<uint32_t*>(bits), nullptr));
 }
 
 void image_set_ibl_samples(int samples)

@@ -17,6 +17,20 @@ void image_pack_watercolor(lml::Color3 const &deepcolor, lml::Color3 const &shal
 // (tools/ibl.cpp:162 hard-codes 1024, which stays the default).
 void image_project_sh9_cube(int width, int height, void const *level0_rgbe, float *sh);
 
+// On-disk form of the probe irradiance (the reference has none — its runtime gets
+// `Irradiance` from data/project.comp only).  Both are ordinary IMAG payloads for write_imag_asset
+// (tools/assetpacker.h:26), so a pack needs no new chunk type:
+//   SH9 ............. width 3, height 9, layers 1, levels 1, PackImageHeader::f32 (src/assetpack.h:89):
+//                     27 floats, byte for byte `Irradiance::L[9][3]` (src/renderer/envmap.h:112-115); a loader
+//                     memcpy's the 108-byte payload into the struct it hands to LightList::push_probe
+//                     (src/renderer/lightlist.cpp:102-112).  image_pack_irradiance_sh9 fills it from level 0
+//                     of a baked (or just ingested) rgbe cube payload.
+//   irradiance cube . width w, height h, layers 6, levels 1, PackImageHeader::rgbe: E(n) of
+//                     data/lighting.inc:351-371 at the texel directions of tools/ibl.cpp:269, the face order
+//                     of every other cube payload; loads through the existing EnvMap path.
+void image_pack_irradiance_sh9(int width, int height, void const *level0_rgbe, void *bits);
+void image_pack_irradiance_cube(void const *sh9_bits, int width, int height, void *bits);
+
 // The body of write_skybox_asset(fout, id, paths) between image loading and
 // write_imag_asset (tools/assetbuilder.cpp:443-465) as one call: `argb` points at six
 // width*height blocks of QImage::Format_ARGB32 pixels (image.bits() after

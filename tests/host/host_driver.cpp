@@ -64,6 +64,19 @@ int main(int argc, char **argv)
       return 0;
     }
 
+    if (mode == "irradiance" && argc == 8)
+    {
+      // a skybox's diffuse side as two more IMAG payloads: SH9 (3 x 9 f32) and an iw x ih irradiance cube (rgbe)
+      int w = atoi(argv[2]), h = atoi(argv[3]), iw = atoi(argv[4]), ih = atoi(argv[5]);
+      std::vector<char> level0((size_t)w * h * 6 * 4);
+      std::ifstream(argv[6], std::ios::binary).read(level0.data(), (std::streamsize)level0.size());
+      std::vector<char> payload(datasize(3, 9, 1, 1) + datasize(iw, ih, 6, 1));
+      image_pack_irradiance_sh9(w, h, level0.data(), payload.data());
+      image_pack_irradiance_cube(payload.data(), iw, ih, payload.data() + datasize(3, 9, 1, 1));
+      std::ofstream(argv[7], std::ios::binary).write(payload.data(), (std::streamsize)payload.size());
+      return 0;
+    }
+
     if (mode == "luts" && argc == 3)
     {
       std::vector<char> payload(2 * datasize(256, 256, 1, 1));

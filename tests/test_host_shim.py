@@ -168,6 +168,26 @@ def test_equirect_pack_matches_oracle(ctx, iw, ih, w, h):
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/tools/ibl.h"), reason="needs the reference tree")
+@pytest.mark.gpu
+def test_irradiance_payloads_through_the_host_shim(ctx, tmp_path):
+    """SURVEY 8 f4: SH9 as a 3x9 f32 IMAG payload (== Irradiance::L[9][3]) and the irradiance cube as a
+    6-layer rgbe IMAG payload, both through the C++ shim, against the fp64 oracle."""
+    import datum_b200
+    w, iw = 32, 8
+    level0 = synth.synthetic_chain(w, w, 1, probe=61, sun=False)
+    (tmp_path / "level0.bin").write_bytes(level0.tobytes())
+    out = run_driver("irradiance", w, w, iw, iw, tmp_path / "level0.bin", tmp_path / "out.bin")
+    assert out.returncode == 0, out.stdout
+    raw = (tmp_path / "out.bin").read_bytes()
+    assert len(raw) == 27 * 4 + 6 * iw * iw * 4
+    sh = np.frombuffer(raw[:108], np.float32).reshape(9, 3)
+    want_sh = oracle_lib.project_sh9(level0, datum_b200.FORMAT_RGBE, w, w)
+    assert np.abs(sh - want_sh).max() <= 1e-4 * np.abs(want_sh).max()
+    cube = np.frombuffer(raw[108:], np.uint32)
+    want_words, _ = ctx.sh9_irradiance_cube(sh, iw, iw)
+    assert np.array_equal(cube, want_words)
+
+
 def test_forwarder_compiles_against_the_reference_headers(tmp_path):
     """the shim copied over tools/ibl.cpp compiles against the reference's OWN
     tools/ibl.h, tools/hdr.h and src/math headers (leap provided by the oracle's stand-in)."""
