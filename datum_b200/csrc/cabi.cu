@@ -964,7 +964,7 @@ extern "C"
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(sh9 partials)", err);
 
-    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, d_partial, ctx->stream);
+    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, d_partial, ctx->sm_count, ctx->stream);
     if (err != cudaSuccess)
       return fail_cuda("sh9_partial", err);
     ctx->launches += 2;

@@ -15,6 +15,7 @@
 #include "ibl_math.cuh"
 
 #include <cuda_runtime.h>
+#include <cstdint>
 
 namespace ibl
 {
@@ -41,8 +42,38 @@ namespace ibl
 
   // ---- projection ----------------------------------------------------------------
 
+  // L2 residency: the texel stream is read once (evict first, do not allocate in L1), the solid-angle
+  // table is read once per face and should survive the stream in between (evict last)
+  __device__ __forceinline__ unsigned long long l2_policy_evict_first()
+  {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+  }
+
+  __device__ __forceinline__ unsigned long long l2_policy_evict_last()
+  {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+  }
+
+  __device__ __forceinline__ float4 ldg_stream(float4 const *ptr, unsigned long long policy)
+  {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy));
+    return v;
+  }
+
+  __device__ __forceinline__ float ldg_keep(float const *ptr, unsigned long long policy)
+  {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(policy));
+    return v;
+  }
+
   template<int FORMAT>
-  __device__ __forceinline__ void load_texel(void const *__restrict__ level0, size_t idx, float &r, float &g, float &b)
+  __device__ __forceinline__ void load_texel(void const *__restrict__ level0, size_t idx, unsigned long long stream_policy, float &r, float &g, float &b)
   {
     if (FORMAT == 0)
     {
@@ -55,31 +86,51 @@ namespace ibl
     }
     else
     {
-      float4 c = __ldg(reinterpret_cast<float4 const *>(level0) + idx);
+      float4 c = ldg_stream(reinterpret_cast<float4 const *>(level0) + idx, stream_policy);
       r = c.x; g = c.y; b = c.z;
     }
   }
 
-  // acc[3*k + c] += weight * color[c] * Y_k(ray), project.comp:64-92
+  // acc[3*k + c] += weight * color[c] * M_k(ray) with the MONOMIALS
+  //     M = 1, y, z, x, xy, yz, z^2, zx, x^2 - y^2
+  // of the basis functions of project.comp:64-92; their constant factors (and the "3 z^2 - 1" of
+  // Y6) are applied once per block in sh9_basis_from_monomials: 11 multiplies less per texel.
   __device__ __forceinline__ void sh9_accumulate(float acc[28], float wr, float wg, float wb, float rx, float ry, float rz)
   {
-    float basis[9];
-    basis[0] = 0.282095f;
-    basis[1] = 0.488603f * ry;
-    basis[2] = 0.488603f * rz;
-    basis[3] = 0.488603f * rx;
-    basis[4] = 1.092548f * rx * ry;
-    basis[5] = 1.092548f * ry * rz;
-    basis[6] = 0.315392f * (3.0f * rz * rz - 1.0f);
-    basis[7] = 1.092548f * rz * rx;
-    basis[8] = 0.546274f * (rx * rx - ry * ry);
+    float mono[9];
+    mono[0] = 1.0f;
+    mono[1] = ry;
+    mono[2] = rz;
+    mono[3] = rx;
+    mono[4] = rx * ry;
+    mono[5] = ry * rz;
+    mono[6] = rz * rz;
+    mono[7] = rz * rx;
+    mono[8] = fmaf(rx, rx, -ry * ry);
+
+    acc[0] += wr; acc[1] += wg; acc[2] += wb;
 
     #pragma unroll
-    for(int k = 0; k < 9; ++k)
+    for(int k = 1; k < 9; ++k)
     {
-      acc[3*k + 0] = fmaf(wr, basis[k], acc[3*k + 0]);
-      acc[3*k + 1] = fmaf(wg, basis[k], acc[3*k + 1]);
-      acc[3*k + 2] = fmaf(wb, basis[k], acc[3*k + 2]);
+      acc[3*k + 0] = fmaf(wr, mono[k], acc[3*k + 0]);
+      acc[3*k + 1] = fmaf(wg, mono[k], acc[3*k + 1]);
+      acc[3*k + 2] = fmaf(wb, mono[k], acc[3*k + 2]);
+    }
+  }
+
+  // monomial sums -> basis sums (fp64, once per block): project.comp:64-92's constants
+  __device__ __forceinline__ double sh9_basis_from_monomials(int k, double const mono[28])
+  {
+    int band = k / 3, c = k - 3 * band;
+    switch (band)
+    {
+      case 0: return 0.282095 * mono[k];
+      case 1: case 2: case 3: return 0.488603 * mono[k];
+      case 4: case 5: case 7: return 1.092548 * mono[k];
+      case 6: return 0.315392 * (3.0 * mono[k] - mono[c]);
+      case 8: return 0.546274 * mono[k];
+      default: return mono[k];     // k == 27: the weight sum
     }
   }
 
@@ -107,7 +158,7 @@ namespace ibl
   // the segment are issued before the arithmetic of the first texel: memory-level parallelism is what
   // keeps this kernel near the HBM roofline (16 B per texel against ~64 instructions).
   template<int FORMAT, int FACE>
-  __device__ __forceinline__ void sh9_row_segment(void const *__restrict__ level0, float const *__restrict__ weights, int w, size_t row_offset, int weight_offset, int x0, float v, float vv1, float two_inv_w, float u_bias, float acc[28])
+  __device__ __forceinline__ void sh9_row_segment(void const *__restrict__ level0, float const *__restrict__ weights, int w, size_t row_offset, int weight_offset, int x0, float v, float vv1, float two_inv_w, float u_bias, unsigned long long stream_policy, unsigned long long keep_policy, float acc[28])
   {
     float r[kSh9Unroll], g[kSh9Unroll], bl[kSh9Unroll], weight[kSh9Unroll];
 
@@ -117,8 +168,12 @@ namespace ibl
       int x = x0 + j * kSh9Threads + (int)threadIdx.x;
       if (x < w)
       {
-        load_texel<FORMAT>(level0, row_offset + x, r[j], g[j], bl[j]);
-        weight[j] = __ldg(weights + weight_offset + x);
+        load_texel<FORMAT>(level0, row_offset + x, stream_policy, r[j], g[j], bl[j]);
+
+        // the solid angle is symmetric in x (and y, see weight_offset): only one quadrant of the table is ever
+        // touched, 17 MB at 4096^2, which the L2 keeps between faces
+        int xs = x < w - 1 - x ? x : w - 1 - x;
+        weight[j] = ldg_keep(weights + weight_offset + xs, keep_policy);
       }
       else
       {
@@ -154,12 +209,14 @@ namespace ibl
 
     const float inv_w = 1.0f / (float)w, inv_h = 1.0f / (float)h;
     const float two_inv_w = 2.0f * inv_w, u_bias = inv_w - 1.0f;
+    const unsigned long long stream_policy = l2_policy_evict_first(), keep_policy = l2_policy_evict_last();
 
     // work items: (row of the slab, segment of that row) in row order; rows are face-major, so the
     // slab of a GPU that shares the cube with others is one contiguous range of the level.  (Tried and
-    // measured slower on 4096^2 faces, 0.343 ms as is: item order with the six faces of a table stretch
-    // side by side for L2 reuse of the solid angles, 0.42 ms; the solid angle from a Taylor form instead
-    // of the table, 0.38 ms; five row moments per channel folded once per row, 0.40 ms.)
+    // measured slower on 4096^2 faces, 0.345 ms as is: item order with the six faces of a table stretch
+    // side by side, 0.42 ms; the solid angle from a Taylor form instead of the table, 0.38 ms; five row
+    // moments per channel folded once per row, 0.40 ms; the texel stream through cp.async.bulk into a
+    // four-stage shared-memory ring with mbarriers, 0.41 ms — profiles/r1_summary.md 0.3.)
     const int segments = (w + kSh9Segment - 1) / kSh9Segment;
     const long long items = (long long)(row_end - row_begin) * segments;
 
@@ -173,16 +230,16 @@ namespace ibl
       float v = 2.0f * ((float)y + 0.5f) * inv_h - 1.0f;
       float vv1 = fmaf(v, v, 1.0f);
       size_t row_offset = (size_t)row * w;
-      int weight_offset = y * w;
+      int weight_offset = (y < h - 1 - y ? y : h - 1 - y) * w;
 
       switch (face)
       {
-        case 0: sh9_row_segment<FORMAT, 0>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
-        case 1: sh9_row_segment<FORMAT, 1>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
-        case 2: sh9_row_segment<FORMAT, 2>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
-        case 3: sh9_row_segment<FORMAT, 3>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
-        case 4: sh9_row_segment<FORMAT, 4>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
-        default: sh9_row_segment<FORMAT, 5>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, acc); break;
+        case 0: sh9_row_segment<FORMAT, 0>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, stream_policy, keep_policy, acc); break;
+        case 1: sh9_row_segment<FORMAT, 1>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, stream_policy, keep_policy, acc); break;
+        case 2: sh9_row_segment<FORMAT, 2>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, stream_policy, keep_policy, acc); break;
+        case 3: sh9_row_segment<FORMAT, 3>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, stream_policy, keep_policy, acc); break;
+        case 4: sh9_row_segment<FORMAT, 4>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, stream_policy, keep_policy, acc); break;
+        default: sh9_row_segment<FORMAT, 5>(level0, weights, w, row_offset, weight_offset, x0, v, vv1, two_inv_w, u_bias, stream_policy, keep_policy, acc); break;
       }
     }
 
@@ -205,6 +262,8 @@ namespace ibl
 
     __syncthreads();
 
+    __shared__ double s_mono[28];
+
     if (threadIdx.x < 28)
     {
       double v = 0;
@@ -212,8 +271,13 @@ namespace ibl
       for(int wi = 0; wi < kSh9Threads / 32; ++wi)
         v += s_partial[wi][threadIdx.x];
 
-      block_partials[(size_t)blockIdx.x * 28 + threadIdx.x] = v;
+      s_mono[threadIdx.x] = v;
     }
+
+    __syncthreads();
+
+    if (threadIdx.x < 28)
+      block_partials[(size_t)blockIdx.x * 28 + threadIdx.x] = sh9_basis_from_monomials(threadIdx.x, s_mono);
   }
 
   // fixed-order sum of the block partials (warp k sums component k, lanes stride over the blocks,
@@ -310,18 +374,21 @@ namespace ibl
     return (int)(items < cap ? (items < 1 ? 1 : items) : cap);
   }
 
-  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, double *partial, cudaStream_t stream)
+  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, double *partial, int sm_count, cudaStream_t stream)
   {
+    int grid = blocks;
+    (void)sm_count;
+
     if (format == 0)
-      sh9_partial_kernel<0><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials);
+      sh9_partial_kernel<0><<<grid, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials);
     else
-      sh9_partial_kernel<1><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials);
+      sh9_partial_kernel<1><<<grid, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials);
 
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess)
       return err;
 
-    sh9_combine_kernel<<<1, 28 * 32, 0, stream>>>(block_partials, blocks, partial);
+    sh9_combine_kernel<<<1, 28 * 32, 0, stream>>>(block_partials, grid, partial);
 
     return cudaGetLastError();
   }
