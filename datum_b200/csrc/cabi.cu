@@ -114,6 +114,7 @@ struct datum_ibl_ctx
   DeviceBuffer<float> sh_weights; // solid angle table
   int sh_weights_w = 0, sh_weights_h = 0;
   DeviceBuffer<double> sh_partials; // block partials + 28 result doubles
+  DeviceBuffer<unsigned int> sh_counter; // "blocks done" ticket of the projection kernel, zero between launches
   DeviceBuffer<unsigned char> staging; // generic device staging for host entry points
   DeviceBuffer<float> sink;
   DeviceBuffer<float> srgb_lut;   // pow(c/255, 2.2) for the 256 channel values (six-image ingest)
@@ -385,6 +386,48 @@ namespace
     return 0;
   }
 
+  // data/project.comp:23-106 for a slab of rows, on `stream` (the context's own, or the upload stream of a
+  // batch so that the projection of probe i+1 runs under the prefilter kernels of probe i).  The scratch
+  // (block partials, ticket) is shared: callers keep their projections on ONE stream at a time.
+  int sh9_partial_on(datum_ibl_ctx *ctx, cudaStream_t stream, void const *d_level0, int format, int width, int height, int row_begin, int row_end, double *d_partial)
+  {
+    if (ctx->sh_weights_w != width || ctx->sh_weights_h != height)
+    {
+      cudaError_t err = ctx->sh_weights.reserve((size_t)width * height);
+      if (err != cudaSuccess)
+        return fail_cuda("cudaMalloc(sh9 weights)", err);
+
+      err = ibl::launch_sh9_weights(ctx->sh_weights.ptr, width, height, ctx->stream);
+      if (err == cudaSuccess && stream != ctx->stream)
+        err = cudaStreamSynchronize(ctx->stream);      // once per face size: the table is built on the context's stream
+      if (err != cudaSuccess)
+        return fail_cuda("sh9_weights", err);
+      ctx->launches += 1;
+
+      ctx->sh_weights_w = width;
+      ctx->sh_weights_h = height;
+    }
+
+    int blocks = ibl::sh9_partial_blocks(width, height, ctx->sm_count);
+
+    cudaError_t err = ctx->sh_partials.reserve((size_t)blocks * 28 + 28);
+    if (err == cudaSuccess && !ctx->sh_counter.ptr)
+    {
+      err = ctx->sh_counter.reserve(1);
+      if (err == cudaSuccess)
+        err = cudaMemsetAsync(ctx->sh_counter.ptr, 0, sizeof(unsigned int), stream);
+    }
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(sh9 partials)", err);
+
+    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, ctx->sh_counter.ptr, d_partial, ctx->sm_count, stream);
+    if (err != cudaSuccess)
+      return fail_cuda("sh9_partial", err);
+    ctx->launches += 1;
+
+    return 0;
+  }
+
   // the copy streams and events of the host entry points, created on first use
   int ensure_pipeline(datum_ibl_ctx *ctx)
   {
@@ -565,6 +608,7 @@ extern "C"
     ctx->queue_heads.release();
     ctx->sh_weights.release();
     ctx->sh_partials.release();
+    ctx->sh_counter.release();
     ctx->staging.release();
     ctx->sink.release();
     ctx->srgb_lut.release();
@@ -707,7 +751,9 @@ extern "C"
       if (err != cudaSuccess)
         return fail_cuda("datum_ibl_bake_probes: upload", err);
 
-      if (sh && datum_ibl_sh9_partial_device(ctx, d_bits, DATUM_IBL_FORMAT_RGBE, width, height, 0, 6 * height, ctx->batch_sh.ptr + (size_t)i * 28))
+      // the projection reads level 0 only: it runs behind the upload on the upload stream, under the
+      // prefilter kernels of the previous probe; the next upload into this payload queues behind it
+      if (sh && sh9_partial_on(ctx, ctx->copy_in, d_bits, DATUM_IBL_FORMAT_RGBE, width, height, 0, 6 * height, ctx->batch_sh.ptr + (size_t)i * 28))
         return 1;
 
       if (run_chain(ctx, width, height, levels, samples, d_bits, nullptr, (uint32_t*)bits[i]))
@@ -724,9 +770,10 @@ extern "C"
     if (sh)
     {
       partials.resize((size_t)count * 28);
-      err = cudaStreamWaitEvent(ctx->copy_out, ctx->ev_computed[(count - 1) & 1], 0);
+      // all projections are on the upload stream: read the results behind the last one
+      err = cudaMemcpyAsync(partials.data(), ctx->batch_sh.ptr, partials.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_in);
       if (err == cudaSuccess)
-        err = cudaMemcpyAsync(partials.data(), ctx->batch_sh.ptr, partials.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_out);
+        err = cudaStreamSynchronize(ctx->copy_in);
       if (err != cudaSuccess)
         return fail_cuda("datum_ibl_bake_probes: sh9 download", err);
     }
@@ -943,33 +990,7 @@ extern "C"
 
     DeviceGuard guard(ctx->device);
 
-    if (ctx->sh_weights_w != width || ctx->sh_weights_h != height)
-    {
-      cudaError_t err = ctx->sh_weights.reserve((size_t)width * height);
-      if (err != cudaSuccess)
-        return fail_cuda("cudaMalloc(sh9 weights)", err);
-
-      err = ibl::launch_sh9_weights(ctx->sh_weights.ptr, width, height, ctx->stream);
-      if (err != cudaSuccess)
-        return fail_cuda("sh9_weights", err);
-      ctx->launches += 1;
-
-      ctx->sh_weights_w = width;
-      ctx->sh_weights_h = height;
-    }
-
-    int blocks = ibl::sh9_partial_blocks(width, height, ctx->sm_count);
-
-    cudaError_t err = ctx->sh_partials.reserve((size_t)blocks * 28 + 28);
-    if (err != cudaSuccess)
-      return fail_cuda("cudaMalloc(sh9 partials)", err);
-
-    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, d_partial, ctx->sm_count, ctx->stream);
-    if (err != cudaSuccess)
-      return fail_cuda("sh9_partial", err);
-    ctx->launches += 2;
-
-    return 0;
+    return sh9_partial_on(ctx, ctx->stream, d_level0, format, width, height, row_begin, row_end, d_partial);
   }
 
   void datum_ibl_sh9_finish(double const *partial, float *sh)

@@ -8,8 +8,8 @@
 // face size.  The projection itself streams the slab once (16 B/texel RGBA32F):
 // a CTA takes 1024-texel segments of rows, every thread issues its four 16-byte
 // loads before any arithmetic, accumulates 27 sums + the weight sum in registers,
-// then warp-shuffle and block-reduce in fp64.  Block partials are summed in a
-// fixed order by a second kernel, so the result is run-to-run deterministic.
+// then warp-shuffle and block-reduce in fp64.  Block partials are summed in block
+// order by whichever block finishes last, so the result is run-to-run deterministic.
 
 #include "sh9.h"
 #include "ibl_math.cuh"
@@ -200,7 +200,7 @@ namespace ibl
   }
 
   template<int FORMAT>
-  __global__ void __launch_bounds__(kSh9Threads, 4) sh9_partial_kernel(void const *__restrict__ level0, float const *__restrict__ weights, int w, int h, int row_begin, int row_end, double *__restrict__ block_partials)
+  __global__ void __launch_bounds__(kSh9Threads, 4) sh9_partial_kernel(void const *__restrict__ level0, float const *__restrict__ weights, int w, int h, int row_begin, int row_end, double *__restrict__ block_partials, unsigned int *__restrict__ done_counter, double *__restrict__ partial)
   {
     float acc[28];
     #pragma unroll
@@ -278,24 +278,57 @@ namespace ibl
 
     if (threadIdx.x < 28)
       block_partials[(size_t)blockIdx.x * 28 + threadIdx.x] = sh9_basis_from_monomials(threadIdx.x, s_mono);
-  }
 
-  // fixed-order sum of the block partials (warp k sums component k, lanes stride over the blocks,
-  // shuffle tree): deterministic
-  __global__ void __launch_bounds__(28 * 32) sh9_combine_kernel(double const *__restrict__ block_partials, int blocks, double *__restrict__ partial)
-  {
-    int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- the block that finishes last sums the block partials, in block order: deterministic, and one
+    //      launch instead of two (a separate 1-CTA combine kernel cost 7.5 us, as much as a 256^2 cube) ----
+    __shared__ bool s_last;
 
-    double v = 0;
-    for(int i = lane; i < blocks; i += 32)
-      v += block_partials[(size_t)i * 28 + k];
+    __threadfence();
+    __syncthreads();
 
-    #pragma unroll
-    for(int offset = 16; offset > 0; offset >>= 1)
-      v += __shfl_down_sync(0xffffffffu, v, offset);
+    if (threadIdx.x == 0)
+    {
+      unsigned int ticket = atomicAdd(done_counter, 1u);
+      s_last = ticket == gridDim.x - 1;
+    }
 
-    if (lane == 0)
-      partial[k] = v;
+    __syncthreads();
+
+    if (!s_last)
+      return;
+
+    __threadfence();
+
+    // thread (k, part): component k over the blocks part, part + kParts, ...; then the parts in order
+    constexpr int kParts = kSh9Threads / 28;              // 9
+    __shared__ double s_part[kParts][28];
+
+    if (threadIdx.x < kParts * 28)
+    {
+      int k = threadIdx.x % 28, part = threadIdx.x / 28;
+      double v = 0;
+
+      #pragma unroll 8
+      for(int i = part; i < (int)gridDim.x; i += kParts)
+        v += __ldcg(block_partials + (size_t)i * 28 + k);
+
+      s_part[part][k] = v;
+    }
+
+    __syncthreads();
+
+    if (threadIdx.x < 28)
+    {
+      double v = 0;
+      #pragma unroll
+      for(int part = 0; part < kParts; ++part)
+        v += s_part[part][threadIdx.x];
+
+      partial[threadIdx.x] = v;
+    }
+
+    if (threadIdx.x == 0)
+      *done_counter = 0;      // ready for the next launch on this stream
   }
 
   // ---- irradiance cube from SH9: data/lighting.inc:351-366, 371 ---------------------
@@ -374,21 +407,14 @@ namespace ibl
     return (int)(items < cap ? (items < 1 ? 1 : items) : cap);
   }
 
-  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, double *partial, int sm_count, cudaStream_t stream)
+  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, unsigned int *done_counter, double *partial, int sm_count, cudaStream_t stream)
   {
-    int grid = blocks;
     (void)sm_count;
 
     if (format == 0)
-      sh9_partial_kernel<0><<<grid, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials);
+      sh9_partial_kernel<0><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial);
     else
-      sh9_partial_kernel<1><<<grid, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials);
-
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess)
-      return err;
-
-    sh9_combine_kernel<<<1, 28 * 32, 0, stream>>>(block_partials, grid, partial);
+      sh9_partial_kernel<1><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial);
 
     return cudaGetLastError();
   }

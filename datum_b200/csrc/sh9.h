@@ -13,8 +13,9 @@ namespace ibl
 
   int sh9_partial_blocks(int w, int h, int sm_count);
 
-  // block_partials: blocks*28 doubles of scratch; partial: 28 doubles (27 sums + weight sum)
-  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, double *partial, int sm_count, cudaStream_t stream);
+  // block_partials: blocks*28 doubles of scratch; done_counter: one zero-initialised word the kernel
+  // leaves at zero; partial: 28 doubles (27 sums + weight sum).  One launch.
+  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, unsigned int *done_counter, double *partial, int sm_count, cudaStream_t stream);
 
   cudaError_t launch_sh9_irradiance(Sh9Coefficients const &sh, int w, int h, uint32_t *words, float *f32, int sm_count, cudaStream_t stream);
 }
