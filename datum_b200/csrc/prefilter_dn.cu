@@ -947,6 +947,51 @@ namespace ibl
 
   namespace
   {
+    // dynamic shared memory opt-in + resident CTAs per SM of one kernel instantiation, remembered per
+    // (device, shared-memory size): the two runtime calls cost more host time than the launch itself
+    template<typename Kernel>
+    cudaError_t resident_ctas(Kernel kernel, int threads, size_t smem, int *resident)
+    {
+      struct Entry { int device; size_t smem; int resident; };
+      thread_local static Entry cache[8] = {};
+      thread_local static int used = 0;
+      thread_local static size_t opted_in[16] = {};      // per device: the opt-in only ever grows
+
+      int device = 0;
+      cudaError_t err = cudaGetDevice(&device);
+      if (err != cudaSuccess)
+        return err;
+
+      for(int i = 0; i < used; ++i)
+        if (cache[i].device == device && cache[i].smem == smem)
+        {
+          *resident = cache[i].resident;
+          return cudaSuccess;
+        }
+
+      if (device < 0 || device >= 16 || smem > opted_in[device])
+      {
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess)
+          return err;
+        if (device >= 0 && device < 16)
+          opted_in[device] = smem;
+      }
+
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(resident, kernel, threads, smem);
+      if (err != cudaSuccess)
+        return err;
+      if (*resident < 1)
+        return cudaErrorLaunchOutOfResources;
+
+      // when the table is full overwrite round-robin
+      cache[used < 8 ? used : (int)(smem % 8)] = Entry{ device, smem, *resident };
+      if (used < 8)
+        used += 1;
+
+      return cudaSuccess;
+    }
+
     template<int NW, int UNROLL, int MINB, bool SMEM_TABLE, bool QUEUES>
     cudaError_t launch_dn(PrefilterDnParams p, int sm_count, cudaStream_t stream, int *launched_grid)
     {
@@ -959,16 +1004,10 @@ namespace ibl
 
       size_t smem = (SMEM_TABLE ? (size_t)p.table_count * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
 
-      cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (err != cudaSuccess)
-        return err;
-
       int resident = 0;
-      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 32 * NW, smem);
+      cudaError_t err = resident_ctas(kernel, 32 * NW, smem, &resident);
       if (err != cudaSuccess)
         return err;
-      if (resident < 1)
-        return cudaErrorLaunchOutOfResources;
 
       int grid = p.tiles < sm_count * resident ? p.tiles : sm_count * resident;
       if (grid < 1)
@@ -1002,16 +1041,10 @@ namespace ibl
 
       size_t smem = (SMEM_TABLE ? (size_t)p.bands * kSampleBand * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
 
-      cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (err != cudaSuccess)
-        return err;
-
       int resident = 0;
-      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 32 * NW, smem);
+      cudaError_t err = resident_ctas(kernel, 32 * NW, smem, &resident);
       if (err != cudaSuccess)
         return err;
-      if (resident < 1)
-        return cudaErrorLaunchOutOfResources;
 
       int grid = p.tiles < sm_count * resident ? p.tiles : sm_count * resident;
       if (grid < 1)
