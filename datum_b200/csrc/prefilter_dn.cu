@@ -1087,12 +1087,8 @@ namespace ibl
       // the one-sample kernel when the biased record index could wrap
       if (texels >= 32u * 148u * 8u)
         variant = big_table ? 71 : 70;
-      else if (texels >= 32u * 148u * 2u)
-        variant = big_table ? 73 : 72;
-      else if (texels >= 32u * 48u)
-        variant = big_table ? 56 : 55;
       else
-        variant = big_table ? 58 : 57;
+        variant = big_table ? 73 : 72;      // slabs of at most kTailTexels never get here (prefilter_tail_kernel)
     }
 
     // two samples at a time; when the biased index could wrap, the same shape one sample at a time
