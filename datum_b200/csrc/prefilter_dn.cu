@@ -1092,6 +1092,9 @@ namespace ibl
     }
 
     // two samples at a time; when the biased index could wrap, the same shape one sample at a time
+    if (variant >= 81 && variant <= 83 && !pair_kernel_usable(p))
+      variant = variant == 83 ? 53 : 51;
+
     if (variant >= 70 && variant <= 79 && !pair_kernel_usable(p))
     {
       static const int fallback[10] = { 51, 52, 53, 54, 50, 51, 51, 51, 51, 53 };
@@ -1111,6 +1114,9 @@ namespace ibl
       case 77: return launch_dp<4, 8, true, true, 3>(p, sm_count, stream, launched_grid);
       case 78: return launch_dp<4, 8, true, true, 4>(p, sm_count, stream, launched_grid);
       case 79: return launch_dp<8, 4, true, false, 2>(p, sm_count, stream, launched_grid);
+      case 81: return launch_dp<4, 9, true, true>(p, sm_count, stream, launched_grid);
+      case 82: return launch_dp<4, 10, true, true>(p, sm_count, stream, launched_grid);
+      case 83: return launch_dp<8, 5, true, false>(p, sm_count, stream, launched_grid);
       //                        NW UNR MINB SMEM  QUEUES
       case 50: return launch_dn<4, 4, 8, true, false>(p, sm_count, stream, launched_grid);
       case 51: return launch_dn<4, 4, 8, true, true>(p, sm_count, stream, launched_grid);

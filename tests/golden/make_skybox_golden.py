@@ -1,5 +1,7 @@
-"""Regenerates tests/golden/skybox64.npz: BASELINE config 1 (the reference's bundled
-data/skybox_{rt,lf,dn,up,fr,bk}.jpg cube) reduced 8x to 64^2 faces so that it fits a fixture.
+"""Regenerates tests/golden/skybox64.npz and skybox256.npz: BASELINE config 1 (the reference's
+bundled data/skybox_{rt,lf,dn,up,fr,bk}.jpg cube) reduced 8x to 64^2 faces (the whole chain fits a
+small fixture) and 2x to 256^2 faces (level 1 then runs the benchmark's dominant launch shape; the
+fixture holds the faces as 8-bit RGB and the levels >= 1 the UNMODIFIED reference produced, ~25 s).
 
 Runs in the authoring container only (needs /root/reference and PIL).  Steps, mirroring
 write_skybox_asset(fout, id, paths) (tools/assetbuilder.cpp:416-470):
@@ -28,23 +30,40 @@ import oracle_lib  # noqa: E402
 
 ORDER = ("rt", "lf", "dn", "up", "fr", "bk")   # tools/assetbuilder.cpp:876
 W, LEVELS = 64, 7
+W_BIG, LEVELS_BIG = 256, 8
+
+
+def reduced_faces(w):
+    faces = np.zeros((6, w, w), np.uint32)
+    for f, name in enumerate(ORDER):
+        rgb = np.asarray(Image.open("/root/reference/data/skybox_%s.jpg" % name).convert("RGB"), np.float64)
+        k = rgb.shape[0] // w
+        small = rgb.reshape(w, k, w, k, 3).mean(axis=(1, 3)).round().astype(np.uint32)
+        faces[f] = 0xFF000000 | small[..., 0] << 16 | small[..., 1] << 8 | small[..., 2]
+    return faces
+
+
+def reference_chain(faces, levels):
+    w = faces.shape[2]
+    total = sum(6 * (w >> i) ** 2 for i in range(levels))
+    chain = np.zeros(total, np.uint32)
+    chain[: 6 * w * w] = oracle_lib.ingest_cube_argb32(faces)
+    oracle_lib.ref().ref_image_buildmips_cube_ibl(w, w, levels, chain.ctypes.data)
+    return chain
 
 
 def main():
-    faces = np.zeros((6, W, W), np.uint32)
-    for f, name in enumerate(ORDER):
-        rgb = np.asarray(Image.open("/root/reference/data/skybox_%s.jpg" % name).convert("RGB"), np.float64)
-        k = rgb.shape[0] // W
-        small = rgb.reshape(W, k, W, k, 3).mean(axis=(1, 3)).round().astype(np.uint32)
-        faces[f] = 0xFF000000 | small[..., 0] << 16 | small[..., 1] << 8 | small[..., 2]
-
-    total = sum(6 * (W >> i) ** 2 for i in range(LEVELS))
-    chain = np.zeros(total, np.uint32)
-    chain[: 6 * W * W] = oracle_lib.ingest_cube_argb32(faces)
-    oracle_lib.ref().ref_image_buildmips_cube_ibl(W, W, LEVELS, chain.ctypes.data)
-
+    faces = reduced_faces(W)
+    chain = reference_chain(faces, LEVELS)
     path = os.path.join(HERE, "skybox64.npz")
     np.savez_compressed(path, faces_argb=faces, chain=chain)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+    faces = reduced_faces(W_BIG)
+    chain = reference_chain(faces, LEVELS_BIG)
+    rgb = np.stack([(faces >> 16) & 0xFF, (faces >> 8) & 0xFF, faces & 0xFF], axis=-1).astype(np.uint8)
+    path = os.path.join(HERE, "skybox256.npz")
+    np.savez_compressed(path, faces_rgb=rgb, levels=chain[6 * W_BIG * W_BIG:])
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
