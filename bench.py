@@ -126,6 +126,18 @@ def run_reference_arm(args):
     return 0
 
 
+def hbm_side(bytes_per_launch, ms_per_launch):
+    """The same launch against the HBM roof (it is nowhere near it: the prefilter is FP32-bound)."""
+    peak, source = 6650.0, "fallback of B200_PROFILING.md"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, source = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    achieved = bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else 0.0
+    return {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": source}
+
+
 # ---- clock sampling during the timed region ---------------------------------------------
 
 class ClockSampler:
@@ -337,6 +349,7 @@ def run_ours(args):
             "flop_per_texel_sample": FLOP_PER_TEXEL_SAMPLE, "texel_samples_per_launch": dom_ts,
             "launches_timed": dom_n, "ms_per_launch": dom_ms,
             "traffic": 25.2e6, "traffic_source": "dram__bytes_read+write of one ncu --set full capture (profiles/)",
+            "hbm": hbm_side(25.2e6, dom_ms),
         },
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
     }
