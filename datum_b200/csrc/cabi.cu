@@ -687,12 +687,18 @@ extern "C"
     if (err != cudaSuccess)
       return fail_cuda("cudaMemcpyAsync(level 0)", err);
 
-    if (run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr, (uint32_t*)bits))
-      return 1;
+    int failed = run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr, (uint32_t*)bits);
 
+    // also after a failure: nothing may stay in flight that reads or writes the caller's payload
     err = cudaStreamSynchronize(ctx->stream);
-    if (err == cudaSuccess && ctx->copy_out)
-      err = cudaStreamSynchronize(ctx->copy_out);
+    if (ctx->copy_out)
+    {
+      cudaError_t err2 = cudaStreamSynchronize(ctx->copy_out);
+      if (err == cudaSuccess)
+        err = err2;
+    }
+    if (failed)
+      return 1;
     if (err != cudaSuccess)
       return fail_cuda("datum_ibl_buildmips_cube_ibl", err);
 
@@ -734,6 +740,15 @@ extern "C"
 
     uint32_t *slots[2] = { ctx->chain.ptr, ctx->chain2.ptr };
 
+    // a failure in the middle leaves copies from and to the caller's payloads in flight: drain them first
+    auto drain = [ctx](int status)
+    {
+      cudaStreamSynchronize(ctx->copy_in);
+      cudaStreamSynchronize(ctx->stream);
+      cudaStreamSynchronize(ctx->copy_out);
+      return status;
+    };
+
     for(int i = 0; i < count; ++i)
     {
       int k = i & 1;
@@ -749,21 +764,21 @@ extern "C"
       if (err == cudaSuccess)
         err = cudaStreamWaitEvent(ctx->stream, ctx->ev_uploaded[k], 0);
       if (err != cudaSuccess)
-        return fail_cuda("datum_ibl_bake_probes: upload", err);
+        return drain(fail_cuda("datum_ibl_bake_probes: upload", err));
 
       // the projection reads level 0 only: it runs behind the upload on the upload stream, under the
       // prefilter kernels of the previous probe; the next upload into this payload queues behind it
       if (sh && sh9_partial_on(ctx, ctx->copy_in, d_bits, DATUM_IBL_FORMAT_RGBE, width, height, 0, 6 * height, ctx->batch_sh.ptr + (size_t)i * 28))
-        return 1;
+        return drain(1);
 
       if (run_chain(ctx, width, height, levels, samples, d_bits, nullptr, (uint32_t*)bits[i]))
-        return 1;
+        return drain(1);
 
       err = cudaEventRecord(ctx->ev_computed[k], ctx->stream);
       if (err == cudaSuccess)
         err = cudaEventRecord(ctx->ev_downloaded[k], ctx->copy_out);
       if (err != cudaSuccess)
-        return fail_cuda("datum_ibl_bake_probes: download", err);
+        return drain(fail_cuda("datum_ibl_bake_probes: download", err));
     }
 
     std::vector<double> partials;
@@ -775,7 +790,7 @@ extern "C"
       if (err == cudaSuccess)
         err = cudaStreamSynchronize(ctx->copy_in);
       if (err != cudaSuccess)
-        return fail_cuda("datum_ibl_bake_probes: sh9 download", err);
+        return drain(fail_cuda("datum_ibl_bake_probes: sh9 download", err));
     }
 
     err = cudaStreamSynchronize(ctx->copy_out);
