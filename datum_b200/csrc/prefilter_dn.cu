@@ -575,7 +575,7 @@ namespace ibl
     gather_pair<EXP_ALU>(p, base, fa * p.geom.face_size, fb * p.geom.face_size, fu, fv, e, acc);
   }
 
-  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU>
+  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU, int DEPTH = 1>
   __global__ void __launch_bounds__(32 * NW, MINB) prefilter_dp_kernel(PrefilterDnParams p)
   {
     extern __shared__ float4 smem[];
@@ -603,7 +603,7 @@ namespace ibl
     constexpr int PER = kSampleBand / NW;        // entries of a band per warp: an arc of the ring
     constexpr int PAIRS = PER / 2;
     static_assert(PER >= 2 && PER % 2 == 0, "a warp takes whole pairs of every band");
-    constexpr int BAND_UNROLL = PAIRS >= 2 ? 1 : 2;
+    constexpr int BAND_UNROLL = (PAIRS >= 2 ? 1 : 2) * DEPTH;     // DEPTH 2: twice the footprint loads in flight per warp (A/B)
 
     // records, moved back by the bias of the magic-add integers
     uint4 const *biased = opaque(p.records - (size_t)p.geom.bias);
@@ -1029,10 +1029,10 @@ namespace ibl
 
   namespace
   {
-    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0>
+    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0, int DEPTH = 1>
     cudaError_t launch_dp(PrefilterDnParams p, int sm_count, cudaStream_t stream, int *launched_grid)
     {
-      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU>;
+      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU, DEPTH>;
 
       int rows = p.row_end - p.row_begin;
       int tiles_x = (p.wd + 7) / 8, tiles_y = (rows + 3) / 4;
@@ -1092,7 +1092,7 @@ namespace ibl
     }
 
     // two samples at a time; when the biased index could wrap, the same shape one sample at a time
-    if (variant >= 81 && variant <= 83 && !pair_kernel_usable(p))
+    if (variant >= 81 && variant <= 86 && !pair_kernel_usable(p))
       variant = variant == 83 ? 53 : 51;
 
     if (variant >= 70 && variant <= 79 && !pair_kernel_usable(p))
@@ -1117,6 +1117,9 @@ namespace ibl
       case 81: return launch_dp<4, 9, true, true>(p, sm_count, stream, launched_grid);
       case 82: return launch_dp<4, 10, true, true>(p, sm_count, stream, launched_grid);
       case 83: return launch_dp<8, 5, true, false>(p, sm_count, stream, launched_grid);
+      case 84: return launch_dp<4, 6, true, true, 0, 2>(p, sm_count, stream, launched_grid);
+      case 85: return launch_dp<4, 8, true, true, 0, 2>(p, sm_count, stream, launched_grid);
+      case 86: return launch_dp<4, 5, true, true, 0, 2>(p, sm_count, stream, launched_grid);
       //                        NW UNR MINB SMEM  QUEUES
       case 50: return launch_dn<4, 4, 8, true, false>(p, sm_count, stream, launched_grid);
       case 51: return launch_dn<4, 4, 8, true, true>(p, sm_count, stream, launched_grid);
