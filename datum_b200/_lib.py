@@ -34,6 +34,7 @@ SIGNATURES = {
     "datum_ibl_peer_open": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
     "datum_ibl_peer_close": (c_int, [c_void_p, c_void_p]),
     "datum_ibl_sh9_partial_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "datum_ibl_sh9_partial_peers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "datum_ibl_sh9_finish": (None, [c_void_p, c_void_p]),
     "datum_ibl_project_sh9": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "datum_ibl_sh9_irradiance_cube": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -389,7 +389,7 @@ namespace
   // data/project.comp:23-106 for a slab of rows, on `stream` (the context's own, or the upload stream of a
   // batch so that the projection of probe i+1 runs under the prefilter kernels of probe i).  The scratch
   // (block partials, ticket) is shared: callers keep their projections on ONE stream at a time.
-  int sh9_partial_on(datum_ibl_ctx *ctx, cudaStream_t stream, void const *d_level0, int format, int width, int height, int row_begin, int row_end, double *d_partial)
+  int sh9_partial_on(datum_ibl_ctx *ctx, cudaStream_t stream, void const *d_level0, int format, int width, int height, int row_begin, int row_end, double *d_partial, ibl::Sh9Peers const &peers = ibl::Sh9Peers())
   {
     if (ctx->sh_weights_w != width || ctx->sh_weights_h != height)
     {
@@ -420,7 +420,7 @@ namespace
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(sh9 partials)", err);
 
-    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, ctx->sh_counter.ptr, d_partial, ctx->sm_count, stream);
+    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, ctx->sh_counter.ptr, d_partial, peers, ctx->sm_count, stream);
     if (err != cudaSuccess)
       return fail_cuda("sh9_partial", err);
     ctx->launches += 1;
@@ -1006,6 +1006,31 @@ extern "C"
     DeviceGuard guard(ctx->device);
 
     return sh9_partial_on(ctx, ctx->stream, d_level0, format, width, height, row_begin, row_end, d_partial);
+  }
+
+  int datum_ibl_sh9_partial_peers(datum_ibl_ctx *ctx, void const *d_level0, int format, int width, int height, int row_begin, int row_end, int rank, int world, double *const *d_slots)
+  {
+    if (!ctx || !d_level0 || !d_slots)
+      return fail("datum_ibl_sh9_partial_peers: null argument");
+    if (width < 1 || height < 1 || (format != DATUM_IBL_FORMAT_RGBE && format != DATUM_IBL_FORMAT_F32))
+      return fail("datum_ibl_sh9_partial_peers: bad width/height/format");
+    if (row_begin < 0 || row_end > 6 * height || row_begin > row_end)
+      return fail("datum_ibl_sh9_partial_peers: row range outside the cube");
+    if (world < 1 || world > DATUM_IBL_MAX_PEERS + 1 || rank < 0 || rank >= world)
+      return fail("datum_ibl_sh9_partial_peers: bad rank/world");
+
+    ibl::Sh9Peers peers = {};
+    for(int r = 0; r < world; ++r)
+    {
+      if (!d_slots[r])
+        return fail("datum_ibl_sh9_partial_peers: null slot array");
+      if (r != rank)
+        peers.slots[peers.count++] = d_slots[r] + (size_t)rank * 28;
+    }
+
+    DeviceGuard guard(ctx->device);
+
+    return sh9_partial_on(ctx, ctx->stream, d_level0, format, width, height, row_begin, row_end, d_slots[rank] + (size_t)rank * 28, peers);
   }
 
   void datum_ibl_sh9_finish(double const *partial, float *sh)

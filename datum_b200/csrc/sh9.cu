@@ -200,7 +200,7 @@ namespace ibl
   }
 
   template<int FORMAT>
-  __global__ void __launch_bounds__(kSh9Threads, 4) sh9_partial_kernel(void const *__restrict__ level0, float const *__restrict__ weights, int w, int h, int row_begin, int row_end, double *__restrict__ block_partials, unsigned int *__restrict__ done_counter, double *__restrict__ partial)
+  __global__ void __launch_bounds__(kSh9Threads, 4) sh9_partial_kernel(void const *__restrict__ level0, float const *__restrict__ weights, int w, int h, int row_begin, int row_end, double *__restrict__ block_partials, unsigned int *__restrict__ done_counter, double *__restrict__ partial, Sh9Peers peers)
   {
     float acc[28];
     #pragma unroll
@@ -325,6 +325,10 @@ namespace ibl
         v += s_part[part][threadIdx.x];
 
       partial[threadIdx.x] = v;
+
+      // a cube shared by several GPUs: the slab's sums go straight into every peer's array
+      for(int k = 0; k < peers.count; ++k)
+        peers.slots[k][threadIdx.x] = v;
     }
 
     if (threadIdx.x == 0)
@@ -407,14 +411,14 @@ namespace ibl
     return (int)(items < cap ? (items < 1 ? 1 : items) : cap);
   }
 
-  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, unsigned int *done_counter, double *partial, int sm_count, cudaStream_t stream)
+  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, unsigned int *done_counter, double *partial, Sh9Peers const &peers, int sm_count, cudaStream_t stream)
   {
     (void)sm_count;
 
     if (format == 0)
-      sh9_partial_kernel<0><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial);
+      sh9_partial_kernel<0><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial, peers);
     else
-      sh9_partial_kernel<1><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial);
+      sh9_partial_kernel<1><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial, peers);
 
     return cudaGetLastError();
   }

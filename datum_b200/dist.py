@@ -220,6 +220,64 @@ class PeerChain:
         self.bases = []
 
 
+class PeerSh9:
+    """SH9 of one cube shared by the GPUs of the group without a collective: every rank's (world x 28)
+    array of partial sums is mapped into every process; the projection kernel's last block stores the
+    slab's sums into row [rank] of all of them, a barrier kernel follows, and every rank adds the rows
+    in rank order (deterministic, the same bits on every rank)."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, ctx, group=None):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.group = group
+        self.dist, self.rank, self.world = _world(group)
+        if self.world > 8:
+            raise ValueError("a cube is shared by at most 8 GPUs (one NVSwitch domain)")
+        self.epoch = 0
+        self.local, handle = ctx.peer_alloc(self.FLAG_BYTES + 8 * 28 * self.world)
+        self.bases = [None] * self.world
+        self.bases[self.rank] = self.local
+        if self.world > 1:
+            handles = [None] * self.world
+            self.dist.all_gather_object(handles, handle, group=group)
+            for r in range(self.world):
+                if r != self.rank:
+                    self.bases[r] = ctx.peer_open(handles[r])
+        self.rows = torch.as_tensor(_DeviceArray(self.local + self.FLAG_BYTES, 28 * self.world, "<f8"), device=torch.device("cuda", ctx.device)).view(self.world, 28)
+
+    def project(self, level0, fmt, width, height):
+        """data/project.comp:23-106; returns float32 [9][3] (the same on every rank)."""
+        begin, end = split_rows(6 * height, self.world)[self.rank]
+        slots = [base + self.FLAG_BYTES for base in self.bases]
+        if self.world > 1:
+            self.epoch += 1
+            self.ctx.peer_barrier(self.rank, self.world, self.bases, self.epoch)     # nobody still reads the previous result
+        self.ctx.sh9_partial_peers(level0, fmt, width, height, begin, end, self.rank, self.world, slots)
+        if self.world > 1:
+            self.epoch += 1
+            self.ctx.peer_barrier(self.rank, self.world, self.bases, self.epoch)
+        self.ctx.synchronize()
+        rows = self.rows.cpu().numpy()
+        total = np.zeros(28, np.float64)
+        for r in range(self.world):
+            total += rows[r]
+        return self.ctx.sh9_finish(total)
+
+    def close(self):
+        self.ctx.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        self.rows = None
+        for r in range(self.world):
+            if r != self.rank and self.bases[r] is not None:
+                self.ctx.peer_close(self.bases[r])
+        self.ctx.peer_free(self.local)
+        self.bases = []
+
+
 def project_sh9_single_probe(engine, level0, fmt, width, height, group=None):
     """data/project.comp:23-106 for ONE level-0 cube shared by all ranks: rows split,
     28 partial sums all-reduced (the only collective), normalised on every rank."""

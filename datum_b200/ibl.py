@@ -256,6 +256,14 @@ class IblContext:
         out_ptr = _device_pointer(d_partial, 28 * 8, "d_partial", self.device)
         self._check(self._lib.datum_ibl_sh9_partial_device(self._handle, src_ptr, fmt, width, height, row_begin, row_end, out_ptr))
 
+    def sh9_partial_peers(self, d_level0, fmt, width, height, row_begin, row_end, rank, world, slot_addresses):
+        """sh9_partial_device whose 28 sums also go to row [rank] of every peer's (world x 28) float64 array
+        (addresses by rank, peer_alloc / peer_open); asynchronous."""
+        texel_bytes = 4 if fmt == FORMAT_RGBE else 16
+        src_ptr = _device_pointer(d_level0, 6 * width * height * texel_bytes, "d_level0", self.device)
+        slots = (ctypes.c_void_p * world)(*slot_addresses)
+        self._check(self._lib.datum_ibl_sh9_partial_peers(self._handle, src_ptr, fmt, width, height, row_begin, row_end, rank, world, slots))
+
     def sh9_finish(self, partial):
         """data/project.comp:99-105 on the 28 (all-reduced) partial sums -> float32 [9][3]."""
         partial = np.ascontiguousarray(partial, dtype=np.float64)

@@ -186,6 +186,14 @@ int datum_ibl_ingest_cube_argb32_ibl(datum_ibl_ctx *ctx, int width, int height, 
  */
 int datum_ibl_sh9_partial_device(datum_ibl_ctx *ctx, void const *d_level0, int format, int width, int height, int row_begin, int row_end, double *d_partial);
 
+/*
+ * The same for a cube shared by `world` (<= 8) GPUs of a node without a collective: d_slots[r] is rank r's
+ * peer-mapped array of world x 28 doubles (datum_ibl_peer_alloc / _open; d_slots[rank] the local one).  The
+ * slab's 28 sums are written to row [rank] of EVERY array by the block that finishes last (NVLink peer
+ * stores); after a datum_ibl_peer_barrier every rank holds all rows and adds them in rank order.  Asynchronous.
+ */
+int datum_ibl_sh9_partial_peers(datum_ibl_ctx *ctx, void const *d_level0, int format, int width, int height, int row_begin, int row_end, int rank, int world, double *const *d_slots);
+
 /* data/project.comp:99-105: sh[k] = partial[k] * 4*pi / partial[27]; host arithmetic on 28 numbers */
 void datum_ibl_sh9_finish(double const *partial, float *sh);
 

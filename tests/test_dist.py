@@ -127,6 +127,12 @@ def _gpu_worker(rank, world, port, w, levels, samples, out_dir):
             ctx.synchronize()
         np.save(os.path.join(out_dir, "fused_%d.npy" % rank), fused.cpu().numpy().view(np.uint32))
         shared.close()
+
+        # the projection the same way: partial sums stored into the peer's array by the kernel, barrier kernel
+        peer_sh = ibl_dist.PeerSh9(ctx)
+        peer_sh.project(torch.from_numpy(synth.synthetic_cube(128, 128, probe=46)).to(engine.device), FORMAT_F32, 128, 128)
+        np.save(os.path.join(out_dir, "sh_peer_%d.npy" % rank), peer_sh.project(cube, FORMAT_F32, 128, 128))
+        peer_sh.close()
         ctx.close()
     finally:
         dist.destroy_process_group()
@@ -159,3 +165,6 @@ def test_two_gpus_split_one_probe_over_nccl(tmp_path, ctx):
     for rank in range(2):
         got = np.load(tmp_path / ("sh_%d.npy" % rank))
         assert np.abs(got - want_sh).max() <= 1e-4 * np.abs(want_sh).max()
+        peer = np.load(tmp_path / ("sh_peer_%d.npy" % rank))
+        assert np.abs(peer - want_sh).max() <= 1e-4 * np.abs(want_sh).max()
+    assert np.array_equal(np.load(tmp_path / "sh_peer_0.npy"), np.load(tmp_path / "sh_peer_1.npy"))   # rows added in rank order on every rank

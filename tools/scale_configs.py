@@ -147,9 +147,28 @@ if "c5" in configs:
 
     ms = timed(project, reps=5)
     ms_kernel = timed(lambda: ctx.sh9_partial_device(cube, datum_b200.FORMAT_F32, w, w, begin, end, out), reps=5)
+
+    # the same without a collective: partial sums stored into the peers' arrays by the kernel + barrier kernel
+    peer_sh = ibl_dist.PeerSh9(ctx)
+    slots = [base + peer_sh.FLAG_BYTES for base in peer_sh.bases]
+
+    def project_peers():
+        if world > 1:
+            peer_sh.epoch += 1
+            ctx.peer_barrier(rank, world, peer_sh.bases, peer_sh.epoch)
+        ctx.sh9_partial_peers(cube, datum_b200.FORMAT_F32, w, w, begin, end, rank, world, slots)
+        if world > 1:
+            peer_sh.epoch += 1
+            ctx.peer_barrier(rank, world, peer_sh.bases, peer_sh.epoch)
+
+    ms_peers = timed(project_peers, reps=5)
+    sh_peers = peer_sh.project(cube, datum_b200.FORMAT_F32, w, w)
+    sh_nccl = ibl_dist.project_sh9_single_probe(engine, cube, datum_b200.FORMAT_F32, w, w)
+    peers_match = float(np.abs(sh_peers - sh_nccl).max() / np.abs(sh_nccl).max())
+    peer_sh.close()
     rows = end - begin
     emit({"config": "C5", "workload": "SH9 of one %d^2 RGBA32F cube, %d rows per GPU, all-reduce of 28 doubles" % (w, rows),
-          "n_gpus": world, "texels": 6 * w * w, "ms": ms, "ms_kernels_only": ms_kernel,
+          "n_gpus": world, "texels": 6 * w * w, "ms": ms, "ms_kernels_only": ms_kernel, "ms_peer_stores": ms_peers, "peer_stores_vs_nccl_max_rel": peers_match,
           "texels_per_s": 6 * w * w / ms * 1e3, "hbm_gb_per_s_per_gpu_kernels_only": rows * w * 16 / (ms_kernel * 1e-3) / 1e9})
 
 ctx.close()
