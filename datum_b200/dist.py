@@ -221,10 +221,12 @@ class PeerChain:
 
 
 class PeerSh9:
-    """SH9 of one cube shared by the GPUs of the group without a collective: every rank's (world x 28)
-    array of partial sums is mapped into every process; the projection kernel's last block stores the
-    slab's sums into row [rank] of all of them, a barrier kernel follows, and every rank adds the rows
-    in rank order (deterministic, the same bits on every rank)."""
+    """SH9 of one cube shared by the GPUs of the group without a collective: every rank's arrays of
+    (world x 28) partial sums are mapped into every process; the projection kernel's last block stores
+    the slab's sums into row [rank] of all of them, ONE barrier kernel follows, and every rank adds the
+    rows in rank order (deterministic, the same bits on every rank).  Two arrays alternate between
+    calls: a fast rank may already be storing the next projection while a slow one still reads this
+    one, and it cannot get two projections ahead because of the barrier in between."""
 
     FLAG_BYTES = 256
 
@@ -237,7 +239,8 @@ class PeerSh9:
         if self.world > 8:
             raise ValueError("a cube is shared by at most 8 GPUs (one NVSwitch domain)")
         self.epoch = 0
-        self.local, handle = ctx.peer_alloc(self.FLAG_BYTES + 8 * 28 * self.world)
+        self.array_bytes = 8 * 28 * self.world
+        self.local, handle = ctx.peer_alloc(self.FLAG_BYTES + 2 * self.array_bytes)
         self.bases = [None] * self.world
         self.bases[self.rank] = self.local
         if self.world > 1:
@@ -246,21 +249,25 @@ class PeerSh9:
             for r in range(self.world):
                 if r != self.rank:
                     self.bases[r] = ctx.peer_open(handles[r])
-        self.rows = torch.as_tensor(_DeviceArray(self.local + self.FLAG_BYTES, 28 * self.world, "<f8"), device=torch.device("cuda", ctx.device)).view(self.world, 28)
+        device = torch.device("cuda", ctx.device)
+        self.rows = [torch.as_tensor(_DeviceArray(self.local + self.FLAG_BYTES + k * self.array_bytes, 28 * self.world, "<f8"), device=device).view(self.world, 28) for k in range(2)]
+
+    def enqueue(self, level0, fmt, width, height):
+        """Projection kernel + barrier on the context's stream; returns the index of the array that will hold the rows."""
+        begin, end = split_rows(6 * height, self.world)[self.rank]
+        self.epoch += 1
+        which = self.epoch & 1
+        slots = [base + self.FLAG_BYTES + which * self.array_bytes for base in self.bases]
+        self.ctx.sh9_partial_peers(level0, fmt, width, height, begin, end, self.rank, self.world, slots)
+        if self.world > 1:
+            self.ctx.peer_barrier(self.rank, self.world, self.bases, self.epoch)
+        return which
 
     def project(self, level0, fmt, width, height):
         """data/project.comp:23-106; returns float32 [9][3] (the same on every rank)."""
-        begin, end = split_rows(6 * height, self.world)[self.rank]
-        slots = [base + self.FLAG_BYTES for base in self.bases]
-        if self.world > 1:
-            self.epoch += 1
-            self.ctx.peer_barrier(self.rank, self.world, self.bases, self.epoch)     # nobody still reads the previous result
-        self.ctx.sh9_partial_peers(level0, fmt, width, height, begin, end, self.rank, self.world, slots)
-        if self.world > 1:
-            self.epoch += 1
-            self.ctx.peer_barrier(self.rank, self.world, self.bases, self.epoch)
+        which = self.enqueue(level0, fmt, width, height)
         self.ctx.synchronize()
-        rows = self.rows.cpu().numpy()
+        rows = self.rows[which].cpu().numpy()
         total = np.zeros(28, np.float64)
         for r in range(self.world):
             total += rows[r]

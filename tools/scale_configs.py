@@ -150,16 +150,9 @@ if "c5" in configs:
 
     # the same without a collective: partial sums stored into the peers' arrays by the kernel + barrier kernel
     peer_sh = ibl_dist.PeerSh9(ctx)
-    slots = [base + peer_sh.FLAG_BYTES for base in peer_sh.bases]
 
     def project_peers():
-        if world > 1:
-            peer_sh.epoch += 1
-            ctx.peer_barrier(rank, world, peer_sh.bases, peer_sh.epoch)
-        ctx.sh9_partial_peers(cube, datum_b200.FORMAT_F32, w, w, begin, end, rank, world, slots)
-        if world > 1:
-            peer_sh.epoch += 1
-            ctx.peer_barrier(rank, world, peer_sh.bases, peer_sh.epoch)
+        peer_sh.enqueue(cube, datum_b200.FORMAT_F32, w, w)
 
     ms_peers = timed(project_peers, reps=5)
     sh_peers = peer_sh.project(cube, datum_b200.FORMAT_F32, w, w)
