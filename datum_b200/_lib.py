@@ -4,7 +4,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdatum_ibl_cuda.so")
+# DATUM_IBL_CUDA_LIB: another build of the same C ABI (the tools build with the A/B kernel variants,
+# tools/ab/libdatum_ibl_cuda_ab.so); never set by the product, the tests or the benchmark
+LIB_PATH = os.environ.get("DATUM_IBL_CUDA_LIB") or os.path.join(_HERE, "lib", "libdatum_ibl_cuda.so")
 
 _lib = None
 
@@ -27,14 +29,15 @@ SIGNATURES = {
     "datum_ibl_bake_probes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p]),
     "datum_ibl_buildmips_cube_ibl_device": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "datum_ibl_prefilter_level_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "datum_ibl_prefilter_level_peers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, ctypes.POINTER(c_void_p)]),
+    "datum_ibl_prefilter_level_peers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.c_uint32]),
     "datum_ibl_peer_barrier": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.c_uint32]),
+    "datum_ibl_set_peer_timeout_ms": (c_int, [c_void_p, c_int]),
     "datum_ibl_peer_alloc": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
     "datum_ibl_peer_free": (c_int, [c_void_p, c_void_p]),
     "datum_ibl_peer_open": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
     "datum_ibl_peer_close": (c_int, [c_void_p, c_void_p]),
     "datum_ibl_sh9_partial_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "datum_ibl_sh9_partial_peers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "datum_ibl_sh9_partial_peers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.c_uint32]),
     "datum_ibl_sh9_finish": (None, [c_void_p, c_void_p]),
     "datum_ibl_project_sh9": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "datum_ibl_sh9_irradiance_cube": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -2,6 +2,9 @@
 
     python -m datum_b200.build            # CUDA library + C++ host shim
     python -m datum_b200.build --oracle   # also the test-only oracle / oracle/_ref
+    python -m datum_b200.build --ab       # also the TOOLS build with the A/B kernel variants of the
+                                          # tuning history (tools/ab/libdatum_ibl_cuda_ab.so; not shipped,
+                                          # loaded only when DATUM_IBL_CUDA_LIB points at it)
 
 Everything is compiled in-tree so the built .so files travel with the source
 snapshot to the GPU box.  nvcc cross-compiles sm_100a without a GPU present.
@@ -20,7 +23,9 @@ LIBDIR = os.path.join(ROOT, "datum_b200", "lib")
 CUDA_LIB = os.path.join(LIBDIR, "libdatum_ibl_cuda.so")
 HOST_LIB = os.path.join(LIBDIR, "libdatum_ibl_host.so")
 
-CUDA_SOURCES = ["cabi.cu", "prefilter.cu", "prefilter_dn.cu", "sh9.cu", "luts.cu", "resample.cu", "ibl_tables.cpp"]
+CUDA_SOURCES = ["cabi.cu", "multi.cu", "prefilter_dn.cu", "sh9.cu", "luts.cu", "resample.cu", "ibl_tables.cpp"]
+AB_DIR = os.path.join(ROOT, "tools", "ab")
+AB_LIB = os.path.join(AB_DIR, "libdatum_ibl_cuda_ab.so")
 CUDA_HEADERS = ["ibl_math.cuh", "ibl_tables.h", "prefilter.h", "sh9.h", "luts.h", "resample.h"]
 
 NVCC_FLAGS = [
@@ -72,6 +77,16 @@ def build_cuda(force=False):
     return CUDA_LIB
 
 
+def build_ab(force=False):
+    """The same C ABI with every A/B kernel variant compiled in (-DDATUM_IBL_AB_VARIANTS) plus the
+    round-1 first kernel (tools/ab/prefilter.cu).  For tools/level_times.py and friends only."""
+    sources = [os.path.join(CSRC, s) for s in CUDA_SOURCES if os.path.exists(os.path.join(CSRC, s))] + [os.path.join(AB_DIR, "prefilter.cu")]
+    deps = sources + [os.path.join(CSRC, h) for h in CUDA_HEADERS] + [os.path.join(ROOT, "include", "datum_ibl_cuda.h")]
+    if force or _stale(AB_LIB, deps):
+        _run([_nvcc()] + NVCC_FLAGS + ["-DDATUM_IBL_AB_VARIANTS", "-o", AB_LIB] + sources, "nvcc_build_ab.log")
+    return AB_LIB
+
+
 def build_host(force=False):
     """C++ host shim that keeps the reference's tools/ibl.h signatures."""
     sources = [os.path.join(HOST, s) for s in ("ibl.cpp", "hdr.cpp")]
@@ -95,13 +110,15 @@ def build_oracle():
     return proc.stdout
 
 
-def build_all(force=False, oracle=False):
+def build_all(force=False, oracle=False, ab=False):
     build_cuda(force)
     build_host(force)
     if oracle:
         build_oracle()
+    if ab:
+        build_ab(force)
 
 
 if __name__ == "__main__":
-    build_all(force="--force" in sys.argv, oracle="--oracle" in sys.argv)
+    build_all(force="--force" in sys.argv, oracle="--oracle" in sys.argv, ab="--ab" in sys.argv)
     print("built:", CUDA_LIB)

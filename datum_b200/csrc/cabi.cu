@@ -14,9 +14,11 @@
 #include "luts.h"
 #include "resample.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -111,6 +113,10 @@ struct datum_ibl_ctx
   cudaEvent_t ev_level[16] = {};  // level L of the current chain is complete (its download starts behind it)
   DeviceBuffer<uint4> records;    // quad records of the current source level
   DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
+  DeviceBuffer<unsigned int> peer_ticket; // "CTAs done" counter of launches that signal peers, zero between launches
+  bool peer_wait_pending = false; // a stream wait on a peer's arrival is queued: synchronize() watches the clock
+  unsigned int *peer_wait_word = nullptr; // the local arrival counters ([2]) those waits look at
+  int peer_timeout_ms = 60000;
   DeviceBuffer<float> sh_weights; // solid angle table
   int sh_weights_w = 0, sh_weights_h = 0;
   DeviceBuffer<double> sh_partials; // block partials + 28 result doubles
@@ -158,6 +164,15 @@ namespace
     return true;
   }
 
+  void free_table(DeviceTable &t)
+  {
+    if (t.d_entries) cudaFree(t.d_entries);
+    if (t.d_banded) cudaFree(t.d_banded);
+    if (t.d_band_min) cudaFree(t.d_band_min);
+    if (t.d_pairs) cudaFree(t.d_pairs);
+    t = DeviceTable();
+  }
+
   int get_tables(datum_ibl_ctx *ctx, int levels, int samples, std::vector<DeviceTable> **out)
   {
     auto key = std::make_pair(levels, samples);
@@ -178,7 +193,11 @@ namespace
 
         cudaError_t err = cudaMalloc(&t.d_entries, sizeof(float4) * (size_t)(t.count > 0 ? t.count : 1));
         if (err != cudaSuccess)
+        {
+          for(auto &b : built)
+            free_table(b);
           return fail_cuda("cudaMalloc(sample table)", err);
+        }
 
         static_assert(sizeof(ibl::SampleEntry) == sizeof(float4), "table entry layout");
 
@@ -209,7 +228,11 @@ namespace
         if (err == cudaSuccess)
           err = cudaStreamSynchronize(ctx->stream); // `host` and `banded` die at the end of this iteration
         if (err != cudaSuccess)
+        {
+          for(auto &b : built)
+            free_table(b);
           return fail_cuda("upload(sample table)", err);
+        }
       }
 
       it = ctx->tables.emplace(key, std::move(built)).first;
@@ -238,8 +261,38 @@ namespace
     return slot;
   }
 
-  // levels at least 8 texels wide: denormal-mantissa kernel (prefilter_dn.cu)
-  int run_level_dn(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant, int npeers = 0, uint32_t *const *peer_words = nullptr)
+  // the GPUs sharing a probe: where this slab's words also go, and whom to tell when all are stored
+  struct PeerTargets
+  {
+    int count = 0;
+    uint32_t *words[ibl::kMaxPeers] = {};
+    unsigned int *arrive[ibl::kMaxPeers] = {};   // null: no signal from the kernel
+  };
+
+  int fill_signal(datum_ibl_ctx *ctx, PeerTargets const &peers, ibl::PeerSignal &signal)
+  {
+    signal = ibl::PeerSignal();
+    if (peers.count == 0 || !peers.arrive[0])
+      return 0;
+
+    if (!ctx->peer_ticket.ptr)
+    {
+      cudaError_t err = ctx->peer_ticket.reserve(1);
+      if (err == cudaSuccess)
+        err = cudaMemsetAsync(ctx->peer_ticket.ptr, 0, sizeof(unsigned int), ctx->stream);
+      if (err != cudaSuccess)
+        return fail_cuda("cudaMalloc(peer ticket)", err);
+    }
+
+    signal.count = peers.count;
+    for(int k = 0; k < peers.count; ++k)
+      signal.arrive[k] = peers.arrive[k];
+    signal.ticket = ctx->peer_ticket.ptr;
+    return 0;
+  }
+
+  // slabs of more than kTailTexels texels of a level at least a tile wide: denormal-mantissa kernels (prefilter_dn.cu)
+  int run_level_dn(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant, PeerTargets const &peers)
   {
     int wd = ws >> 1, hd = hs >> 1;
 
@@ -263,9 +316,11 @@ namespace
     p.bands = table.bands;
     p.dst_words = d_dst_words;
     p.dst_f32 = d_dst_f32;
-    p.peers = npeers;
-    for(int k = 0; k < npeers; ++k)
-      p.peer_words[k] = peer_words[k];
+    p.peers = peers.count;
+    for(int k = 0; k < peers.count; ++k)
+      p.peer_words[k] = peers.words[k];
+    if (fill_signal(ctx, peers, p.signal))
+      return 1;
     p.wd = wd;
     p.hd = hd;
     p.row_begin = row_begin;
@@ -291,7 +346,7 @@ namespace
   }
 
   // one level on the context's stream: records of the source level, then the prefilter slab
-  int run_level(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant = false, int npeers = 0, uint32_t *const *peer_words = nullptr)
+  int run_level(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant = false, PeerTargets const &peers = PeerTargets())
   {
     int wd = ws >> 1, hd = hs >> 1;
 
@@ -304,9 +359,11 @@ namespace
     if (row_begin == row_end)
       return 0;
 
-    // tail levels (a few hundred texels): lanes are samples, no record pass.  Variant 80 pins this
-    // kernel for every level (A/B, tests).
-    if ((ctx->prefilter_variant == 0 && (size_t)(row_end - row_begin) * wd <= (size_t)ibl::kTailTexels) || ctx->prefilter_variant == 80)
+    // Small slabs (a few hundred to a few thousand texels) and levels narrower than the 8x4 tiles of
+    // the big kernels: lanes are samples, no record pass.  Variant 80 pins this kernel for every level.
+    bool tail = (size_t)(row_end - row_begin) * wd <= (size_t)ibl::kTailTexels || wd < 8;
+
+    if ((ctx->prefilter_variant == 0 && tail) || ctx->prefilter_variant == 80 || (ctx->prefilter_variant >= 50 && wd < 8))
     {
       ibl::PrefilterTailParams p = {};
       p.src = d_src;
@@ -314,9 +371,11 @@ namespace
       p.table_count = table.count;
       p.dst_words = d_dst_words;
       p.dst_f32 = d_dst_f32;
-      p.peers = npeers;
-      for(int k = 0; k < npeers; ++k)
-        p.peer_words[k] = peer_words[k];
+      p.peers = peers.count;
+      for(int k = 0; k < peers.count; ++k)
+        p.peer_words[k] = peers.words[k];
+      if (fill_signal(ctx, peers, p.signal))
+        return 1;
       p.wd = wd;
       p.hd = hd;
       p.row_begin = row_begin;
@@ -340,13 +399,13 @@ namespace
       return 0;
     }
 
-    // variant 0 and 50..58: the denormal-mantissa kernel wherever a level is wide enough for its
-    // 8x4 tiles; 10..27 pin a kernel of prefilter.cu (kept for narrow levels and for A/B timing)
-    if ((ctx->prefilter_variant == 0 || ctx->prefilter_variant >= 50) && wd >= 8)
-      return run_level_dn(ctx, d_src, ws, hs, table, row_begin, row_end, d_dst_words, d_dst_f32, record_dominant, npeers, peer_words);
+    if (ctx->prefilter_variant == 0 || ctx->prefilter_variant >= 50)
+      return run_level_dn(ctx, d_src, ws, hs, table, row_begin, row_end, d_dst_words, d_dst_f32, record_dominant, peers);
 
-    if (npeers > 0)
-      return fail("prefilter: peer stores need a level at least 8 texels wide (narrow levels are computed by every GPU)");
+#ifdef DATUM_IBL_AB_VARIANTS
+    // 10..27 pin a kernel of tools/ab/prefilter.cu (the tools build only, A/B timing)
+    if (peers.count > 0)
+      return fail("prefilter: the A/B kernels do not store to peers");
 
     cudaError_t err = ctx->records.reserve((size_t)6 * ws * hs);
     if (err != cudaSuccess)
@@ -375,7 +434,7 @@ namespace
 
     int slot = record_dominant ? begin_dominant(ctx, (double)(row_end - row_begin) * wd * (double)table.samples) : -1;
 
-    err = ibl::launch_prefilter_level(p, ctx->prefilter_variant >= 50 ? 0 : ctx->prefilter_variant, ctx->sm_count, ctx->stream, nullptr);
+    err = ibl::launch_prefilter_level(p, ctx->prefilter_variant, ctx->sm_count, ctx->stream, nullptr);
     if (err != cudaSuccess)
       return fail_cuda("prefilter_level", err);
     ctx->launches += 1;
@@ -384,6 +443,9 @@ namespace
       cudaEventRecord(ctx->ring_end[slot], ctx->stream);
 
     return 0;
+#else
+    return fail("prefilter: variants 1..49 exist only in the tools build (python -m datum_b200.build --ab)");
+#endif
   }
 
   // data/project.comp:23-106 for a slab of rows, on `stream` (the context's own, or the upload stream of a
@@ -425,6 +487,69 @@ namespace
       return fail_cuda("sh9_partial", err);
     ctx->launches += 1;
 
+    return 0;
+  }
+
+  // ---- arrival counters of the GPUs that share a probe ------------------------------------------
+  //
+  // Flag block of a rank = two 32-bit counters (zeroed at allocation).  Event e (1, 2, 3, ... in the
+  // same order on every rank) uses counter e & 1: every other rank adds 1 to it when its part of the
+  // event is stored (the last CTA of the producing launch, or the signal kernel), and the rank's own
+  // stream waits until the counter has seen (world - 1) arrivals for each event of that parity so far.
+  // Alternating the counters keeps a fast rank's arrival for event e + 1 out of the count of event e
+  // (it cannot reach e + 2 before everybody passed e).  The wait is a stream memory operation
+  // (cuStreamWaitValue32): no kernel launch, no SM occupied while waiting.
+  uint32_t arrivals_expected(uint32_t epoch, int world)
+  {
+    return ((epoch + (epoch & 1u)) / 2u) * (uint32_t)(world - 1);
+  }
+
+  typedef CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+  StreamWaitValue32 stream_wait_value32()
+  {
+    static StreamWaitValue32 fn = [] {
+      void *ptr = nullptr;
+      cudaDriverEntryPointQueryResult found;
+      if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &ptr, cudaEnableDefault, &found) != cudaSuccess || found != cudaDriverEntryPointSuccess)
+        ptr = nullptr;
+      return reinterpret_cast<StreamWaitValue32>(ptr);
+    }();
+    return fn;
+  }
+
+  int wait_for_arrivals(datum_ibl_ctx *ctx, uint32_t *d_own_flags, uint32_t epoch, int world)
+  {
+    if (world <= 1)
+      return 0;
+
+    StreamWaitValue32 wait = stream_wait_value32();
+    if (!wait)
+      return fail("peer wait: the driver does not export cuStreamWaitValue32");
+
+    CUresult res = wait((CUstream)ctx->stream, (CUdeviceptr)(uintptr_t)(d_own_flags + (epoch & 1u)), arrivals_expected(epoch, world), CU_STREAM_WAIT_VALUE_GEQ);
+    if (res != CUDA_SUCCESS)
+      return fail("peer wait: cuStreamWaitValue32 failed (" + std::to_string((int)res) + ")");
+
+    ctx->peer_wait_pending = true;
+    ctx->peer_wait_word = reinterpret_cast<unsigned int*>(d_own_flags);
+    return 0;
+  }
+
+  int signal_arrival(datum_ibl_ctx *ctx, int rank, int world, uint32_t *const *d_flags, uint32_t epoch)
+  {
+    ibl::PeerSignal signal = {};
+    for(int r = 0; r < world; ++r)
+      if (r != rank)
+        signal.arrive[signal.count++] = reinterpret_cast<unsigned int*>(d_flags[r] + (epoch & 1u));
+
+    if (signal.count == 0)
+      return 0;
+
+    cudaError_t err = ibl::launch_peer_signal(signal, ctx->stream);
+    if (err != cudaSuccess)
+      return fail_cuda("peer_signal", err);
+    ctx->launches += 1;
     return 0;
   }
 
@@ -534,8 +659,10 @@ extern "C"
     if (err != cudaSuccess)
       return fail_cuda("cudaGetDeviceProperties", err);
 
-    if (prop.major < 10)
-      return fail(std::string("datum_ibl_create: kernels are built for sm_100a only, device is ") + prop.name);
+    // the library carries sm_100a code only (arch-specific, no PTX fallback): any other device would
+    // fail at the first launch with "no kernel image"
+    if (prop.major != 10 || prop.minor != 0)
+      return fail(std::string("datum_ibl_create: kernels are built for sm_100a (compute capability 10.0) only, device is ") + prop.name + " (" + std::to_string(prop.major) + "." + std::to_string(prop.minor) + ")");
 
     datum_ibl_ctx *ctx = new datum_ibl_ctx;
     ctx->device = device;
@@ -577,17 +704,7 @@ extern "C"
 
     for(auto &entry : ctx->tables)
       for(auto &t : entry.second)
-      {
-        if (t.d_entries)
-          cudaFree(t.d_entries);
-        if (t.d_banded)
-          cudaFree(t.d_banded);
-        if (t.d_band_min)
-          cudaFree(t.d_band_min);
-        if (t.d_pairs)
-          cudaFree(t.d_pairs);
-
-      }
+        free_table(t);
 
     ctx->chain.release();
     ctx->chain2.release();
@@ -633,8 +750,43 @@ extern "C"
       return fail("null context");
 
     DeviceGuard guard(ctx->device);
+
+    // Waits on peers' arrivals are queued on the stream: a peer that died would hang it for good.
+    // Poll with a deadline instead; on expiry satisfy every queued wait from the host (the counters
+    // only ever count up to a few thousand: 2^30 passes any GEQ test), let the stream drain and
+    // report a recoverable error.
+    if (ctx->peer_wait_pending && ctx->peer_timeout_ms > 0)
+    {
+      auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(ctx->peer_timeout_ms);
+      cudaError_t state;
+      while ((state = cudaStreamQuery(ctx->stream)) == cudaErrorNotReady)
+      {
+        if (std::chrono::steady_clock::now() > deadline)
+        {
+          const unsigned int release[2] = { 0x40000000u, 0x40000000u };
+          cudaMemcpy(ctx->peer_wait_word, release, sizeof(release), cudaMemcpyHostToDevice);
+          cudaStreamSynchronize(ctx->stream);
+          ctx->peer_wait_pending = false;
+          return fail("datum_ibl_synchronize: a GPU sharing this probe did not arrive within " + std::to_string(ctx->peer_timeout_ms) + " ms; the waits were released and the results of this bake are invalid");
+        }
+      }
+      ctx->peer_wait_pending = false;
+      if (state != cudaSuccess)
+        return fail_cuda("cudaStreamQuery", state);
+    }
+
     cudaError_t err = cudaStreamSynchronize(ctx->stream);
+    ctx->peer_wait_pending = false;
     return err == cudaSuccess ? 0 : fail_cuda("cudaStreamSynchronize", err);
+  }
+
+  int datum_ibl_set_peer_timeout_ms(datum_ibl_ctx *ctx, int milliseconds)
+  {
+    if (!ctx || milliseconds < 0)
+      return fail("datum_ibl_set_peer_timeout_ms: bad argument");
+
+    ctx->peer_timeout_ms = milliseconds;
+    return 0;
   }
 
   uint64_t datum_ibl_launch_count(datum_ibl_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -821,17 +973,29 @@ extern "C"
     return run_level(ctx, d_src, ws, hs, (*tables)[level], row_begin, row_end, d_dst_words, d_dst_f32);
   }
 
-  int datum_ibl_prefilter_level_peers(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, int level, int levels, int samples, int row_begin, int row_end, uint32_t *d_dst_words, int npeers, uint32_t *const *d_peer_dst_words)
+  int datum_ibl_prefilter_level_peers(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, int level, int levels, int samples, int row_begin, int row_end, int rank, int world, uint32_t *const *d_dst_words, uint32_t *const *d_flags, uint32_t epoch)
   {
-    if (!ctx || !d_src || (npeers > 0 && !d_peer_dst_words))
+    if (!ctx || !d_src || !d_dst_words)
       return fail("datum_ibl_prefilter_level_peers: null argument");
     if (levels < 2 || levels > 16 || level < 1 || level >= levels || samples < 1)
       return fail("datum_ibl_prefilter_level_peers: bad level/levels/samples");
-    if (npeers < 0 || npeers > DATUM_IBL_MAX_PEERS)
-      return fail("datum_ibl_prefilter_level_peers: at most 7 peers");
-    for(int k = 0; k < npeers; ++k)
-      if (!d_peer_dst_words[k])
-        return fail("datum_ibl_prefilter_level_peers: null peer pointer");
+    if (world < 1 || world > DATUM_IBL_MAX_PEERS + 1 || rank < 0 || rank >= world)
+      return fail("datum_ibl_prefilter_level_peers: bad rank/world (at most 8 GPUs share a probe)");
+    if (d_flags && epoch == 0)
+      return fail("datum_ibl_prefilter_level_peers: epochs start at 1");
+
+    PeerTargets peers;
+    for(int r = 0; r < world; ++r)
+    {
+      if (!d_dst_words[r] || (d_flags && !d_flags[r]))
+        return fail("datum_ibl_prefilter_level_peers: null pointer for a rank");
+      if (r != rank)
+      {
+        peers.words[peers.count] = d_dst_words[r];
+        peers.arrive[peers.count] = d_flags ? reinterpret_cast<unsigned int*>(d_flags[r] + (epoch & 1u)) : nullptr;
+        peers.count += 1;
+      }
+    }
 
     DeviceGuard guard(ctx->device);
 
@@ -839,7 +1003,16 @@ extern "C"
     if (get_tables(ctx, levels, samples, &tables))
       return 1;
 
-    return run_level(ctx, d_src, ws, hs, (*tables)[level], row_begin, row_end, d_dst_words, nullptr, false, npeers, d_peer_dst_words);
+    if (row_begin == row_end && d_flags)
+    {
+      // an empty slab still has to arrive
+      if (signal_arrival(ctx, rank, world, d_flags, epoch))
+        return 1;
+    }
+    else if (run_level(ctx, d_src, ws, hs, (*tables)[level], row_begin, row_end, d_dst_words[rank], nullptr, false, peers))
+      return 1;
+
+    return d_flags ? wait_for_arrivals(ctx, d_flags[rank], epoch, world) : 0;
   }
 
   int datum_ibl_peer_barrier(datum_ibl_ctx *ctx, int rank, int world, uint32_t *const *d_flags, uint32_t epoch)
@@ -849,22 +1022,16 @@ extern "C"
     if (world < 1 || world > DATUM_IBL_MAX_PEERS + 1 || rank < 0 || rank >= world || epoch == 0)
       return fail("datum_ibl_peer_barrier: bad rank/world/epoch");
 
-    ibl::PeerFlags flags = {};
     for(int r = 0; r < world; ++r)
-    {
       if (!d_flags[r])
         return fail("datum_ibl_peer_barrier: null flag array");
-      flags.ptr[r] = d_flags[r];
-    }
 
     DeviceGuard guard(ctx->device);
 
-    cudaError_t err = ibl::launch_peer_barrier(flags, rank, world, epoch, ctx->stream);
-    if (err != cudaSuccess)
-      return fail_cuda("peer_barrier", err);
-    ctx->launches += 1;
+    if (signal_arrival(ctx, rank, world, d_flags, epoch))
+      return 1;
 
-    return 0;
+    return wait_for_arrivals(ctx, d_flags[rank], epoch, world);
   }
 
   int datum_ibl_peer_alloc(datum_ibl_ctx *ctx, size_t bytes, void **d_ptr, void *handle)
@@ -1008,7 +1175,7 @@ extern "C"
     return sh9_partial_on(ctx, ctx->stream, d_level0, format, width, height, row_begin, row_end, d_partial);
   }
 
-  int datum_ibl_sh9_partial_peers(datum_ibl_ctx *ctx, void const *d_level0, int format, int width, int height, int row_begin, int row_end, int rank, int world, double *const *d_slots)
+  int datum_ibl_sh9_partial_peers(datum_ibl_ctx *ctx, void const *d_level0, int format, int width, int height, int row_begin, int row_end, int rank, int world, double *const *d_slots, uint32_t *const *d_flags, uint32_t epoch)
   {
     if (!ctx || !d_level0 || !d_slots)
       return fail("datum_ibl_sh9_partial_peers: null argument");
@@ -1018,19 +1185,28 @@ extern "C"
       return fail("datum_ibl_sh9_partial_peers: row range outside the cube");
     if (world < 1 || world > DATUM_IBL_MAX_PEERS + 1 || rank < 0 || rank >= world)
       return fail("datum_ibl_sh9_partial_peers: bad rank/world");
+    if (d_flags && epoch == 0)
+      return fail("datum_ibl_sh9_partial_peers: epochs start at 1");
 
     ibl::Sh9Peers peers = {};
     for(int r = 0; r < world; ++r)
     {
-      if (!d_slots[r])
-        return fail("datum_ibl_sh9_partial_peers: null slot array");
+      if (!d_slots[r] || (d_flags && !d_flags[r]))
+        return fail("datum_ibl_sh9_partial_peers: null pointer for a rank");
       if (r != rank)
-        peers.slots[peers.count++] = d_slots[r] + (size_t)rank * 28;
+      {
+        peers.slots[peers.count] = d_slots[r] + (size_t)rank * 28;
+        peers.arrive[peers.count] = d_flags ? reinterpret_cast<unsigned int*>(d_flags[r] + (epoch & 1u)) : nullptr;
+        peers.count += 1;
+      }
     }
 
     DeviceGuard guard(ctx->device);
 
-    return sh9_partial_on(ctx, ctx->stream, d_level0, format, width, height, row_begin, row_end, d_slots[rank] + (size_t)rank * 28, peers);
+    if (sh9_partial_on(ctx, ctx->stream, d_level0, format, width, height, row_begin, row_end, d_slots[rank] + (size_t)rank * 28, peers))
+      return 1;
+
+    return d_flags ? wait_for_arrivals(ctx, d_flags[rank], epoch, world) : 0;
   }
 
   void datum_ibl_sh9_finish(double const *partial, float *sh)

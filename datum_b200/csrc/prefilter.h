@@ -8,6 +8,8 @@
 
 namespace ibl
 {
+#ifdef DATUM_IBL_AB_VARIANTS
+  // the round-1 first kernel (tools/ab/prefilter.cu): only in the tools build, for A/B timing
   struct PrefilterParams
   {
     uint4 const *records;    // quad records of the SOURCE level (6*ws*hs)
@@ -23,10 +25,20 @@ namespace ibl
     float norm;              // kAccScale / total weight
     int tiles_x, tiles;      // filled by the launcher
   };
+#endif
 
   // ---- denormal-mantissa kernel (prefilter_dn.cu): every level at least 8 texels wide ----
 
   constexpr int kMaxPeers = 7;      // one probe split over at most 8 GPUs (one NVSwitch domain)
+
+  // Arrival counters of the GPUs that share a probe: the CTA of a launch that finishes last bumps
+  // arrive[k] (a word in peer k's flag block, mapped here) once every store of the launch is out.
+  struct PeerSignal
+  {
+    unsigned int *arrive[kMaxPeers];
+    int count;               // 0: nobody to tell
+    unsigned int *ticket;    // "CTAs done" counter of this context, zero between launches
+  };
   constexpr int kSampleBand = 16;   // entries per band of the banded sample table (ibl_tables.h)
 
   struct PrefilterDnParams
@@ -41,6 +53,7 @@ namespace ibl
     float *dst_f32;           // destination level base, fp32 rgb triples before quantisation (may be null)
     uint32_t *peer_words[kMaxPeers]; // the same destination level in the chains of other GPUs (NVLink peer stores)
     int peers;                // how many of them: the epilogue writes every word to dst_words and to each peer
+    PeerSignal signal;        // whom to tell when the whole slab is stored
     int wd, hd;               // destination level size
     int row_begin, row_end;   // slab of the 6*hd face-major rows to compute
     LevelGeom geom;           // source level addressing constants
@@ -65,6 +78,7 @@ namespace ibl
     float *dst_f32;
     uint32_t *peer_words[kMaxPeers];
     int peers;
+    PeerSignal signal;
     int wd, hd;
     int row_begin, row_end;
     LevelGeom geom;
@@ -82,21 +96,16 @@ namespace ibl
   // table in shared memory, tile queues>; 70..75 = two samples at a time (prefilter_dp_kernel)
   cudaError_t launch_prefilter_dn(PrefilterDnParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid);
 
-  // Barrier between the GPUs that share one probe, on the stream: rank `rank` publishes `epoch` into
-  // slot [rank] of every peer's flag array (flags[r] = rank r's array of `world` words) and waits until
-  // its own array holds `epoch` in every slot.  Traps (loudly failing the context) after ~10 s.
-  struct PeerFlags
-  {
-    uint32_t *ptr[kMaxPeers + 1];   // by rank, own array included (host array of device pointers, passed by value)
-  };
-
-  cudaError_t launch_peer_barrier(PeerFlags const &flags, int rank, int world, uint32_t epoch, cudaStream_t stream);
+  // the arrival signal alone, for the barrier at the start of a shared bake (one tiny launch)
+  cudaError_t launch_peer_signal(PeerSignal const &s, cudaStream_t stream);
 
   // also zeroes the `ncounters` tile queue heads for the prefilter launch that follows
   cudaError_t launch_build_dn_records(uint32_t const *src, uint4 *rec, int ws, int hs, int *counters, int ncounters, int sm_count, cudaStream_t stream);
 
+#ifdef DATUM_IBL_AB_VARIANTS
   // variant 0 = pick by slab size; 1..15 = fixed <tile width, texels per lane, warps per tile>
   cudaError_t launch_prefilter_level(PrefilterParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid);
 
   cudaError_t launch_build_quad_records(uint32_t const *src, uint4 *records, int ws, int hs, int sm_count, cudaStream_t stream);
+#endif
 }

@@ -2,7 +2,8 @@
 //
 // Replaces the triple loop of tools/ibl.cpp:263-272 and the per-texel sample loop of
 // tools/ibl.cpp:160-187 (reference paths relative to /root/reference).  This is the kernel the
-// library uses for every level at least 8 texels wide; narrower levels go to prefilter.cu.
+// library uses for every slab of more than kTailTexels texels; smaller slabs and levels narrower
+// than a tile go to prefilter_tail_kernel below.
 //
 // What one bilinear tap costs decides the speed of this loop (profiles/): the first kernel
 // (prefilter.cu) turned each 9-bit mantissa into a float with shift + mask logic, six ALU-pipe ops
@@ -100,6 +101,35 @@ namespace ibl
     }
   }
 
+
+  // ---- "this launch has stored everything" -----------------------------------------------------
+  //
+  // One probe shared by several GPUs: the epilogues above store every word into the peers' chains.
+  // The CTA that finishes LAST (ticket counter) bumps an arrival counter in every peer's flag block
+  // with a system-scope release; the peers' streams wait on their own counter (a stream memory
+  // operation, no kernel) before the next level reads the words.  Every thread fences its own
+  // stores before the ticket, the last CTA fences again behind it (cumulativity).
+  __device__ __forceinline__ void signal_peers_when_last(PeerSignal const &s)
+  {
+    if (s.count <= 0)
+      return;
+
+    __threadfence_system();
+    __syncthreads();
+
+    if (threadIdx.x == 0)
+    {
+      unsigned int ticket = atomicAdd(s.ticket, 1u);
+      if (ticket == gridDim.x - 1)
+      {
+        __threadfence_system();
+        for(int k = 0; k < s.count; ++k)
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" :: "l"(s.arrive[k]) : "memory");
+        *s.ticket = 0;        // ready for the next launch on this stream
+      }
+    }
+  }
+
   // ---- one sample of one texel -------------------------------------------------------
 
   struct TexelFrame
@@ -181,17 +211,38 @@ namespace ibl
   // Tiles of 8x4 texels are numbered in 4x4-blocked order over the slab.  With QUEUES the first
   // `queued` tiles are cut into one contiguous chunk per SM (queue index = %smid) and the rest form
   // a common pool that evens out the tail: a group takes tiles from its SM's chunk, then from the pool.
+  //
+  // %smid values are not guaranteed to be contiguous, and under MPS limits, green contexts or a
+  // concurrent kernel an SM may host no CTA of this launch at all: once its own chunk and the pool are
+  // empty a group therefore makes one stealing pass over every other chunk before it gives up, so
+  // every tile is computed whatever the placement of the CTAs (the pass costs p.queues atomics per
+  // CTA at the very end of a launch).
   __device__ __forceinline__ int next_tile(PrefilterDnParams const &p, uint32_t smid)
   {
-    if ((int)smid < p.queues)
-    {
-      int k = atomicAdd(p.counters + smid, 1);
-      if (k < p.chunk)
-        return (int)smid * p.chunk + k;
-    }
+    const int own = (int)(smid % (uint32_t)p.queues);
+
+    int k = atomicAdd(p.counters + own, 1);
+    if (k < p.chunk)
+      return own * p.chunk + k;
 
     int tile = p.queued + atomicAdd(p.counters + p.queues, 1);
-    return tile < p.tiles ? tile : -1;
+    if (tile < p.tiles)
+      return tile;
+
+    for(int i = 1; i < p.queues; ++i)
+    {
+      int q = own + i < p.queues ? own + i : own + i - p.queues;
+
+      // a drained chunk costs one read; only chunks that still hold tiles are bumped
+      if (*(volatile int const *)(p.counters + q) >= p.chunk)
+        continue;
+
+      k = atomicAdd(p.counters + q, 1);
+      if (k < p.chunk)
+        return q * p.chunk + k;
+    }
+
+    return -1;
   }
 
   // tile number -> texel of this lane; false when the lane's texel is outside the slab
@@ -416,6 +467,8 @@ namespace ibl
 
       __syncthreads();   // s_red and s_tile are reused by the next tile
     }
+
+    signal_peers_when_last(p.signal);
   }
 
   // ---- two samples at a time --------------------------------------------------------------
@@ -758,6 +811,8 @@ namespace ibl
 
       __syncthreads();
     }
+
+    signal_peers_when_last(p.signal);
   }
 
   // ---- tail levels: lanes are samples ----------------------------------------------------------
@@ -870,6 +925,8 @@ namespace ibl
         p.dst_f32[3*o + 2] = b;
       }
     }
+
+    signal_peers_when_last(p.signal);
   }
 
   cudaError_t launch_prefilter_tail(PrefilterTailParams const &p, int sm_count, cudaStream_t stream)
@@ -892,40 +949,17 @@ namespace ibl
     return cudaGetLastError();
   }
 
-  // ---- barrier between the GPUs sharing a probe ------------------------------------------------
-  //
-  // Runs on the bake's stream right behind a prefilter launch whose epilogue stored the slab into
-  // the peers' chains.  Stream order puts those stores before this kernel; the system-scope fence
-  // and release store publish them, the acquire loads of the waiting side order its next level
-  // behind them.
-  __global__ void peer_barrier_kernel(PeerFlags flags, int rank, int world, uint32_t epoch)
+  // ---- arrival signal without a producing launch (the barrier at the start of a shared bake) ------
+  __global__ void peer_signal_kernel(PeerSignal s)
   {
-    int r = threadIdx.x;
-    if (r >= world)
-      return;
-
     __threadfence_system();
-
-    uint32_t *theirs = flags.ptr[r] + rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(theirs), "r"(epoch) : "memory");
-
-    uint32_t const *mine = flags.ptr[rank] + r;
-    long long start = clock64();
-    for(;;)
-    {
-      uint32_t seen;
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-      if ((int)(seen - epoch) >= 0)
-        break;
-      if (clock64() - start > 20000000000ll)   // ~10 s: a peer is gone; fail the context instead of hanging the GPU
-        __trap();
-      __nanosleep(200);
-    }
+    if ((int)threadIdx.x < s.count)
+      asm volatile("red.release.sys.global.add.u32 [%0], 1;" :: "l"(s.arrive[threadIdx.x]) : "memory");
   }
 
-  cudaError_t launch_peer_barrier(PeerFlags const &flags, int rank, int world, uint32_t epoch, cudaStream_t stream)
+  cudaError_t launch_peer_signal(PeerSignal const &s, cudaStream_t stream)
   {
-    peer_barrier_kernel<<<1, 32, 0, stream>>>(flags, rank, world, epoch);
+    peer_signal_kernel<<<1, 32, 0, stream>>>(s);
     return cudaGetLastError();
   }
 
@@ -1097,17 +1131,26 @@ namespace ibl
 
     if (variant >= 70 && variant <= 79 && !pair_kernel_usable(p))
     {
-      static const int fallback[10] = { 51, 52, 53, 54, 50, 51, 51, 51, 51, 53 };
+      static const int fallback[10] = { 51, 52, 53, 54, 51, 51, 51, 51, 51, 53 };
       variant = fallback[variant - 70];
     }
 
     switch (variant)
     {
+      // the shapes the library picks by itself (and the one-sample forms they hand over to)
       //                        NW MINB SMEM  QUEUES
       case 70: return launch_dp<4, 8, true, true>(p, sm_count, stream, launched_grid);
       case 71: return launch_dp<4, 8, false, true>(p, sm_count, stream, launched_grid);
       case 72: return launch_dp<8, 4, true, false>(p, sm_count, stream, launched_grid);
       case 73: return launch_dp<8, 4, false, false>(p, sm_count, stream, launched_grid);
+      //                        NW UNR MINB SMEM  QUEUES
+      case 51: return launch_dn<4, 4, 8, true, true>(p, sm_count, stream, launched_grid);
+      case 52: return launch_dn<4, 4, 8, false, true>(p, sm_count, stream, launched_grid);
+      case 53: return launch_dn<8, 2, 4, true, false>(p, sm_count, stream, launched_grid);
+      case 54: return launch_dn<8, 2, 4, false, false>(p, sm_count, stream, launched_grid);
+
+#ifdef DATUM_IBL_AB_VARIANTS
+      // A/B shapes of the tuning history (profiles/): only in the tools build (datum_b200.build --ab)
       case 74: return launch_dp<4, 8, true, false>(p, sm_count, stream, launched_grid);
       case 75: return launch_dp<4, 8, true, true, 1>(p, sm_count, stream, launched_grid);
       case 76: return launch_dp<4, 8, true, true, 2>(p, sm_count, stream, launched_grid);
@@ -1120,12 +1163,7 @@ namespace ibl
       case 84: return launch_dp<4, 6, true, true, 0, 2>(p, sm_count, stream, launched_grid);
       case 85: return launch_dp<4, 8, true, true, 0, 2>(p, sm_count, stream, launched_grid);
       case 86: return launch_dp<4, 5, true, true, 0, 2>(p, sm_count, stream, launched_grid);
-      //                        NW UNR MINB SMEM  QUEUES
       case 50: return launch_dn<4, 4, 8, true, false>(p, sm_count, stream, launched_grid);
-      case 51: return launch_dn<4, 4, 8, true, true>(p, sm_count, stream, launched_grid);
-      case 52: return launch_dn<4, 4, 8, false, true>(p, sm_count, stream, launched_grid);
-      case 53: return launch_dn<8, 2, 4, true, false>(p, sm_count, stream, launched_grid);
-      case 54: return launch_dn<8, 2, 4, false, false>(p, sm_count, stream, launched_grid);
       case 55: return launch_dn<16, 1, 2, true, false>(p, sm_count, stream, launched_grid);
       case 56: return launch_dn<16, 1, 2, false, false>(p, sm_count, stream, launched_grid);
       case 57: return launch_dn<32, 1, 1, true, false>(p, sm_count, stream, launched_grid);
@@ -1136,6 +1174,7 @@ namespace ibl
       case 63: return launch_dn<4, 2, 8, true, true>(p, sm_count, stream, launched_grid);
       case 64: return launch_dn<8, 2, 5, true, true>(p, sm_count, stream, launched_grid);
       case 65: return launch_dn<4, 4, 10, true, true>(p, sm_count, stream, launched_grid);
+#endif
       default: return cudaErrorInvalidValue;
     }
   }

@@ -331,6 +331,16 @@ namespace ibl
         peers.slots[k][threadIdx.x] = v;
     }
 
+    // ... and the peers' streams are told (they wait on their arrival counter, no kernel in between)
+    if (peers.count > 0 && peers.arrive[0])
+    {
+      __threadfence_system();
+      __syncthreads();
+
+      if ((int)threadIdx.x < peers.count)
+        asm volatile("red.release.sys.global.add.u32 [%0], 1;" :: "l"(peers.arrive[threadIdx.x]) : "memory");
+    }
+
     if (threadIdx.x == 0)
       *done_counter = 0;      // ready for the next launch on this stream
   }

@@ -13,8 +13,9 @@ namespace ibl
   struct Sh9Peers
   {
     double *slots[7];
+    unsigned int *arrive[7];   // arrival counter in each peer's flag block, bumped once the row is stored (null: no signal)
     int count;
-  }; // [k][rgb], the layout of Irradiance::L (src/renderer/envmap.h:112-115)
+  };
 
   // fp64 solid-angle table of data/project.comp:56-60, w*h floats
   cudaError_t launch_sh9_weights(float *weights, int w, int h, cudaStream_t stream);

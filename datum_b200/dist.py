@@ -45,7 +45,11 @@ def shard_probes(count, rank, world):
     return list(range(rank, count, world))
 
 
-def plan_single_probe(width, height, levels, world, min_split_texels=6 * 32 * 32):
+# Levels of at most this many texels are computed by every GPU instead of being exchanged.
+MIN_SPLIT_TEXELS = 6 * 16 * 16
+
+
+def plan_single_probe(width, height, levels, world, min_split_texels=MIN_SPLIT_TEXELS):
     """Per level >= 1: how the 6*(h>>L) destination rows are shared.
 
     A level is split when its row count divides evenly by the world size (equal
@@ -104,7 +108,7 @@ def _world(group):
     return dist, dist.get_rank(group), dist.get_world_size(group)
 
 
-def bake_single_probe(engine, chain, width, height, levels, samples=1024, group=None, min_split_texels=6 * 32 * 32):
+def bake_single_probe(engine, chain, width, height, levels, samples=1024, group=None, min_split_texels=MIN_SPLIT_TEXELS):
     """tools/ibl.cpp:242-279 for ONE probe shared by all ranks of `group`.
 
     `chain` is the payload tensor on the engine's device (int32 words, level 0
@@ -148,7 +152,7 @@ class PeerChain:
     torch.distributed (all_gather_object: plumbing, not data path), and every rank
     maps its peers' allocations.  bake() then needs no collective: the prefilter
     kernel's epilogue stores each slab into all chains over NVLink and a one-CTA
-    barrier kernel on the same stream separates the levels."""
+    stream memory wait on the arrival counters separates the levels."""
 
     FLAG_BYTES = 256
 
@@ -184,11 +188,12 @@ class PeerChain:
         self.epoch += 1
         self.ctx.peer_barrier(self.rank, self.world, self.bases, self.epoch)
 
-    def bake(self, samples=1024, min_split_texels=6 * 32 * 32):
+    def bake(self, samples=1024, min_split_texels=MIN_SPLIT_TEXELS):
         """tools/ibl.cpp:242-279 for the probe whose level 0 every rank has put into `self.chain`;
-        on return (asynchronously, on the context's stream) every rank holds the whole chain."""
+        on return (asynchronously, on the context's stream) every rank holds the whole chain.
+        One launch per split level: the kernel stores its slab into every chain, its last CTA tells
+        the peers, the stream waits for their arrivals."""
         plan = plan_single_probe(self.width, self.height, self.levels, self.world, min_split_texels)
-        others = [r for r in range(self.world) if r != self.rank]
 
         # nobody may still be reading the previous probe out of this chain, or lag a whole bake behind
         if self.world > 1:
@@ -197,14 +202,15 @@ class PeerChain:
         for step in plan:
             level = step["level"]
             src = self.chain_address(self.rank) + 4 * self.offs[level - 1]
-            dst = self.chain_address(self.rank) + 4 * self.offs[level]
             begin, end = step["ranges"][self.rank]
-            peers = [self.chain_address(r) + 4 * self.offs[level] for r in others] if step["split"] else []
-
-            self.ctx.prefilter_level_peers(src, step["ws"], step["hs"], level, self.levels, samples, begin, end, dst, peers)
 
             if step["split"]:
-                self.barrier()
+                self.epoch += 1
+                dst = [self.chain_address(r) + 4 * self.offs[level] for r in range(self.world)]
+                self.ctx.prefilter_level_peers(src, step["ws"], step["hs"], level, self.levels, samples, begin, end, self.rank, self.world, dst, self.bases, self.epoch)
+            else:
+                dst = self.chain_address(self.rank) + 4 * self.offs[level]
+                self.ctx.prefilter_level_peers(src, step["ws"], step["hs"], level, self.levels, samples, begin, end, 0, 1, [dst])
 
         return self.chain
 
@@ -253,14 +259,14 @@ class PeerSh9:
         self.rows = [torch.as_tensor(_DeviceArray(self.local + self.FLAG_BYTES + k * self.array_bytes, 28 * self.world, "<f8"), device=device).view(self.world, 28) for k in range(2)]
 
     def enqueue(self, level0, fmt, width, height):
-        """Projection kernel + barrier on the context's stream; returns the index of the array that will hold the rows."""
+        """ONE launch on the context's stream (the projection kernel's last block stores the rows and
+        tells the peers) + the stream's wait for their arrivals; returns the index of the array that
+        will hold the rows."""
         begin, end = split_rows(6 * height, self.world)[self.rank]
         self.epoch += 1
         which = self.epoch & 1
         slots = [base + self.FLAG_BYTES + which * self.array_bytes for base in self.bases]
-        self.ctx.sh9_partial_peers(level0, fmt, width, height, begin, end, self.rank, self.world, slots)
-        if self.world > 1:
-            self.ctx.peer_barrier(self.rank, self.world, self.bases, self.epoch)
+        self.ctx.sh9_partial_peers(level0, fmt, width, height, begin, end, self.rank, self.world, slots, self.bases if self.world > 1 else None, self.epoch)
         return which
 
     def project(self, level0, fmt, width, height):

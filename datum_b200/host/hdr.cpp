@@ -73,7 +73,9 @@ HDRImage load_hdr(std::string const &path)
     if (starts_with_nocase(line, "format", 6))
     {
       auto fields = fields_of(line, "=");
-      if (fields.size() != 2 && fields[1] != "32-bit_rle_rgbe") // same (lenient) test as hdr.cpp:99
+      // tools/hdr.cpp:99 tests `size != 2 && fields[1] != ...`, which indexes past a one-field line and
+      // never rejects a two-field one; a file parser on untrusted input does not keep that quirk
+      if (fields.size() != 2 || fields[1] != "32-bit_rle_rgbe")
         throw std::runtime_error("Unsupported hdr file format");
     }
 
@@ -121,7 +123,7 @@ HDRImage load_hdr(std::string const &path)
       while (position < image.width)
       {
         int count = fin.get();
-        if (count < 0)
+        if (count <= 0)                       // end of file, or a zero-length run that would never advance
           throw std::runtime_error("hdr parse error");
 
         if (count > 128)

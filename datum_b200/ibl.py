@@ -145,6 +145,16 @@ class IblContext:
     def synchronize(self):
         self._check(self._lib.datum_ibl_synchronize(self._handle))
 
+    def _after_torch(self):
+        """The context's stream is its own (non-blocking) stream: before a *_device entry point reads or
+        writes caller tensors, make it wait for whatever torch has queued on its CURRENT stream (the
+        producers of those tensors: a torch.zeros, a copy_, ...).  Free when the caller already works
+        under `with torch.cuda.stream(ctx.torch_stream())`."""
+        import torch
+        current = torch.cuda.current_stream(self.device)
+        if current.cuda_stream != self.stream_pointer:
+            self.torch_stream().wait_event(current.record_event())
+
     @property
     def launch_count(self):
         return int(self._lib.datum_ibl_launch_count(self._handle))
@@ -197,12 +207,15 @@ class IblContext:
         return sh
 
     def buildmips_cube_ibl_device(self, width, height, levels, d_bits, samples=1024, d_f32=None):
-        """Same chain on a device-resident payload (int32/uint32 CUDA tensor); asynchronous.
+        """Same chain on a device-resident payload (int32/uint32 CUDA tensor); asynchronous on the
+        context's stream, ordered BEHIND the work torch has queued on its current stream; results are
+        ready after ctx.synchronize() (or for torch work issued under ctx.torch_stream()).
         d_f32: optional float32 CUDA tensor receiving the pre-quantisation rgb of levels >= 1."""
         total = image_datasize(width, height, 6, levels)
         level0 = width * height * 6 * 4
         bits_ptr = _device_pointer(d_bits, total, "d_bits", self.device)
         f32_ptr = _device_pointer(d_f32, (total - level0) * 3, "d_f32", self.device)
+        self._after_torch()
         self._check(self._lib.datum_ibl_buildmips_cube_ibl_device(self._handle, width, height, levels, samples, bits_ptr, f32_ptr))
 
     def prefilter_level_device(self, d_src, ws, hs, level, levels, samples, row_begin, row_end, d_dst_words=None, d_dst_f32=None):
@@ -211,6 +224,7 @@ class IblContext:
         src_ptr = _device_pointer(d_src, 6 * ws * hs * 4, "d_src", self.device)
         words_ptr = _device_pointer(d_dst_words, out_texels * 4, "d_dst_words", self.device)
         f32_ptr = _device_pointer(d_dst_f32, out_texels * 12, "d_dst_f32", self.device)
+        self._after_torch()
         self._check(self._lib.datum_ibl_prefilter_level_device(self._handle, src_ptr, ws, hs, level, levels, samples, row_begin, row_end, words_ptr, f32_ptr))
 
     # ---- SH9: data/project.comp:23-106 ----
@@ -237,32 +251,42 @@ class IblContext:
     def peer_close(self, address):
         self._check(self._lib.datum_ibl_peer_close(self._handle, ctypes.c_void_p(address)))
 
-    def prefilter_level_peers(self, src_address, ws, hs, level, levels, samples, row_begin, row_end, dst_address, peer_dst_addresses):
-        """prefilter_level_device on raw device addresses whose words also go to the same level of the
-        peers' payloads (addresses of the START of the destination level in each mapped chain)."""
-        n = len(peer_dst_addresses)
-        peers = (ctypes.c_void_p * max(n, 1))(*peer_dst_addresses)
-        self._check(self._lib.datum_ibl_prefilter_level_peers(self._handle, ctypes.c_void_p(src_address), ws, hs, level, levels, samples, row_begin, row_end, ctypes.c_void_p(dst_address), n, peers))
+    def prefilter_level_peers(self, src_address, ws, hs, level, levels, samples, row_begin, row_end, rank, world, dst_addresses, flag_addresses=None, epoch=0):
+        """prefilter_level_device on raw device addresses for rank `rank` of `world` GPUs sharing the probe:
+        dst_addresses[r] = START of the destination level in rank r's payload as mapped here; every word of the
+        slab goes to all of them.  With flag_addresses (flag blocks by rank) and epoch > 0 the launch signals
+        the peers when it is complete and the stream then waits for theirs."""
+        dst = (ctypes.c_void_p * world)(*dst_addresses)
+        flags = (ctypes.c_void_p * world)(*flag_addresses) if flag_addresses is not None else None
+        self._check(self._lib.datum_ibl_prefilter_level_peers(self._handle, ctypes.c_void_p(src_address), ws, hs, level, levels, samples, row_begin, row_end, rank, world, dst, flags, epoch))
 
     def peer_barrier(self, rank, world, flag_addresses, epoch):
-        """Barrier of the GPUs sharing a probe, on the context's stream (flag_addresses by rank)."""
+        """Barrier of the GPUs sharing a probe, on the context's stream (flag blocks by rank)."""
         flags = (ctypes.c_void_p * world)(*flag_addresses)
         self._check(self._lib.datum_ibl_peer_barrier(self._handle, rank, world, flags, epoch))
+
+    def set_peer_timeout_ms(self, milliseconds):
+        """How long synchronize() lets the stream wait for a peer's arrival before it gives up (default 60 s)."""
+        self._check(self._lib.datum_ibl_set_peer_timeout_ms(self._handle, int(milliseconds)))
 
     def sh9_partial_device(self, d_level0, fmt, width, height, row_begin, row_end, d_partial):
         """28 partial sums (27 coefficients + weight) into a float64 CUDA tensor; asynchronous."""
         texel_bytes = 4 if fmt == FORMAT_RGBE else 16
         src_ptr = _device_pointer(d_level0, 6 * width * height * texel_bytes, "d_level0", self.device)
         out_ptr = _device_pointer(d_partial, 28 * 8, "d_partial", self.device)
+        self._after_torch()
         self._check(self._lib.datum_ibl_sh9_partial_device(self._handle, src_ptr, fmt, width, height, row_begin, row_end, out_ptr))
 
-    def sh9_partial_peers(self, d_level0, fmt, width, height, row_begin, row_end, rank, world, slot_addresses):
+    def sh9_partial_peers(self, d_level0, fmt, width, height, row_begin, row_end, rank, world, slot_addresses, flag_addresses=None, epoch=0):
         """sh9_partial_device whose 28 sums also go to row [rank] of every peer's (world x 28) float64 array
-        (addresses by rank, peer_alloc / peer_open); asynchronous."""
+        (addresses by rank, peer_alloc / peer_open); with flag blocks and an epoch the launch signals the peers
+        and the stream waits for theirs.  Asynchronous."""
         texel_bytes = 4 if fmt == FORMAT_RGBE else 16
         src_ptr = _device_pointer(d_level0, 6 * width * height * texel_bytes, "d_level0", self.device)
+        self._after_torch()
         slots = (ctypes.c_void_p * world)(*slot_addresses)
-        self._check(self._lib.datum_ibl_sh9_partial_peers(self._handle, src_ptr, fmt, width, height, row_begin, row_end, rank, world, slots))
+        flags = (ctypes.c_void_p * world)(*flag_addresses) if flag_addresses is not None else None
+        self._check(self._lib.datum_ibl_sh9_partial_peers(self._handle, src_ptr, fmt, width, height, row_begin, row_end, rank, world, slots, flags, epoch))
 
     def sh9_finish(self, partial):
         """data/project.comp:99-105 on the 28 (all-reduced) partial sums -> float32 [9][3]."""

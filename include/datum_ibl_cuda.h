@@ -53,7 +53,7 @@ int datum_ibl_synchronize(datum_ibl_ctx *ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t datum_ibl_launch_count(datum_ibl_ctx *ctx);
 
-/* prefilter kernel variant: 0 = automatic (default), 1.. = fixed tile shape (tuning/benchmarks) */
+/* prefilter kernel variant: 0 = automatic (default); 51-54, 70-73, 80 pin one of the shipped kernels (tests); others exist in the tools build only */
 int datum_ibl_set_prefilter_variant(datum_ibl_ctx *ctx, int variant);
 
 /* bytes of a `levels`-deep cube chain; tools/assetpacker.cpp:488-497 with layers = 6 */
@@ -106,34 +106,46 @@ int datum_ibl_prefilter_level_device(datum_ibl_ctx *ctx, uint32_t const *d_src, 
  * level every destination row is independent, but level L reads all of level L-1
  * (tools/ibl.cpp:249, 274): the GPUs sharing a probe each compute a slab of rows and need the
  * whole level before the next one.  Here the prefilter kernel's epilogue writes its slab into
- * every peer's payload over NVLink (peer stores), and a one-CTA barrier kernel on the same stream
- * separates the levels: compute and exchange are one launch, no collective library call.
+ * every peer's payload over NVLink (peer stores); the CTA of the launch that finishes last then
+ * bumps an arrival counter in every peer's flag block, and each GPU's stream waits on its own
+ * counter with a stream memory operation (cuStreamWaitValue32) before the next level: compute,
+ * exchange and synchronisation are ONE kernel launch per level, no collective library call.
  *
- * datum_ibl_peer_alloc: device memory other processes can map; `handle` receives the 64 bytes of
- * its cudaIpcMemHandle_t, to be sent to the peers by any means (torch.distributed in dist.py).
- * datum_ibl_peer_open / _close: map / unmap a peer's allocation in this process.
+ * Flag block: DATUM_IBL_PEER_FLAG_BYTES zeroed bytes owned by each rank (the first two 32-bit
+ * words are the arrival counters), peer-mapped like the payload.  An "event" is one exchange or
+ * barrier; every rank issues the same events in the same order with epochs 1, 2, 3, ...
+ *
+ * datum_ibl_peer_alloc: zeroed device memory other PROCESSES can map; `handle` receives the 64
+ * bytes of its cudaIpcMemHandle_t, to be sent to the peers by any means (torch.distributed in
+ * dist.py).  datum_ibl_peer_open / _close: map / unmap a peer's allocation in this process.
+ * Inside ONE process use the device-list entry points below instead (plain peer access).
  */
 #define DATUM_IBL_MAX_PEERS 7
 #define DATUM_IBL_IPC_HANDLE_BYTES 64
+#define DATUM_IBL_PEER_FLAG_BYTES 256
 int datum_ibl_peer_alloc(datum_ibl_ctx *ctx, size_t bytes, void **d_ptr, void *handle);
 int datum_ibl_peer_free(datum_ibl_ctx *ctx, void *d_ptr);
 int datum_ibl_peer_open(datum_ibl_ctx *ctx, void const *handle, void **d_ptr);
 int datum_ibl_peer_close(datum_ibl_ctx *ctx, void *d_ptr);
 
 /*
- * datum_ibl_prefilter_level_device whose rgbe words ALSO go to `npeers` (<= 7) other chains:
- * d_peer_dst_words[k] points at the START of the destination level in peer k's mapped payload.
- * Asynchronous.
+ * datum_ibl_prefilter_level_device for rank `rank` of `world` (<= 8) GPUs sharing the probe:
+ * d_dst_words[r] points at the START of the destination level in rank r's payload as mapped HERE
+ * (r == rank: the local one); every rgbe word of the slab goes to all of them.  With d_flags
+ * (by rank, may be NULL) and epoch > 0 the launch also signals its completion to the peers and the
+ * context's stream then waits for the arrivals of all peers: after this call has been issued on every
+ * rank, work queued behind it sees the complete level.  Asynchronous.
  */
-int datum_ibl_prefilter_level_peers(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, int level, int levels, int samples, int row_begin, int row_end, uint32_t *d_dst_words, int npeers, uint32_t *const *d_peer_dst_words);
+int datum_ibl_prefilter_level_peers(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, int level, int levels, int samples, int row_begin, int row_end, int rank, int world, uint32_t *const *d_dst_words, uint32_t *const *d_flags, uint32_t epoch);
 
 /*
- * Barrier of the `world` (<= 8) GPUs on the context's stream: d_flags[r] = rank r's flag array
- * (world 32-bit words, zero-initialised, peer-mapped; d_flags[rank] the local one).  Every call of
- * a bake uses the next `epoch` (> 0, increasing).  Asynchronous; a peer that never arrives fails
- * the context after ~10 s instead of hanging the device.
+ * Barrier of the `world` (<= 8) GPUs on the context's stream (one tiny signal launch + a stream
+ * wait): d_flags[r] = rank r's flag block (d_flags[rank] the local one).  Asynchronous.  A peer that
+ * never arrives is detected by datum_ibl_synchronize (datum_ibl_set_peer_timeout_ms, default 60 s),
+ * which releases the waits and returns an error; no device-side trap.
  */
 int datum_ibl_peer_barrier(datum_ibl_ctx *ctx, int rank, int world, uint32_t *const *d_flags, uint32_t epoch);
+int datum_ibl_set_peer_timeout_ms(datum_ibl_ctx *ctx, int milliseconds);
 
 /* ---- equirectangular HDR image -> cube: tools/hdr.cpp:331-359, tools/ibl.cpp:283-288 ---- */
 
@@ -188,11 +200,12 @@ int datum_ibl_sh9_partial_device(datum_ibl_ctx *ctx, void const *d_level0, int f
 
 /*
  * The same for a cube shared by `world` (<= 8) GPUs of a node without a collective: d_slots[r] is rank r's
- * peer-mapped array of world x 28 doubles (datum_ibl_peer_alloc / _open; d_slots[rank] the local one).  The
- * slab's 28 sums are written to row [rank] of EVERY array by the block that finishes last (NVLink peer
- * stores); after a datum_ibl_peer_barrier every rank holds all rows and adds them in rank order.  Asynchronous.
+ * peer-mapped array of world x 28 doubles (d_slots[rank] the local one).  The slab's 28 sums are written to
+ * row [rank] of EVERY array by the block that finishes last (NVLink peer stores), which then signals the
+ * peers' flag blocks (d_flags, epoch as above; NULL: no signal, no wait); the stream waits for all arrivals,
+ * after which every rank holds all rows and adds them in rank order.  One launch.  Asynchronous.
  */
-int datum_ibl_sh9_partial_peers(datum_ibl_ctx *ctx, void const *d_level0, int format, int width, int height, int row_begin, int row_end, int rank, int world, double *const *d_slots);
+int datum_ibl_sh9_partial_peers(datum_ibl_ctx *ctx, void const *d_level0, int format, int width, int height, int row_begin, int row_end, int rank, int world, double *const *d_slots, uint32_t *const *d_flags, uint32_t epoch);
 
 /* data/project.comp:99-105: sh[k] = partial[k] * 4*pi / partial[27]; host arithmetic on 28 numbers */
 void datum_ibl_sh9_finish(double const *partial, float *sh);

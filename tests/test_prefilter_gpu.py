@@ -164,8 +164,8 @@ def test_row_slabs_reproduce_the_full_level(ctx):
         assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 1e-4
         stats = oracle_lib.word_stats(slabs.cpu().numpy().view(np.uint32), full.cpu().numpy().view(np.uint32))
         assert oracle_lib.words_within_one_code(stats, 0.995), stats
-        # pinned variants (one of each kernel): same warp split; only the same-face sample count of the re-cut tiles differs
-        for variant in (17, 53):
+        # pinned variants (one-sample and pair kernel): same warp split; only the same-face sample count of the re-cut tiles differs
+        for variant in (53, 72):
             full, full_f, slabs, slabs_f = run(variant)
             assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 5e-6
             assert (full == slabs).float().mean().item() >= 0.999
@@ -180,7 +180,7 @@ def test_kernel_variants_agree(ctx):
     bits = synth.synthetic_chain(w, w, levels, probe=14, sun=False)
     base = None
     try:
-        for variant in (0, 10, 14, 17, 19, 27, 50, 51, 52, 53, 54, 55, 56, 57, 58, 70, 71, 72, 73, 74, 80):
+        for variant in (0, 51, 52, 53, 54, 70, 71, 72, 73, 80):     # every kernel shape the product library ships
             ctx.set_prefilter_variant(variant)
             words, f32 = run_chain_device(ctx, bits, w, w, levels, 1024)
             if base is None:
@@ -228,7 +228,7 @@ def test_directions_on_cube_edges_stay_inside_the_face(ctx):
     src = synth.synthetic_chain(ws, ws, 1, probe=21, sun=False)
     d_src = torch.from_numpy(src.view(np.int32)).to(DEV)
     wd = ws // 2
-    for variant in (0, 19):
+    for variant in (0, 52):
         ctx.set_prefilter_variant(variant)
         try:
             out = torch.zeros(6 * wd * wd, dtype=torch.int32, device=DEV)

@@ -1,10 +1,13 @@
-// datum_b200 — GGX prefilter of one cube-map mip level, first kernel (sm_100a).
+// datum_b200 — GGX prefilter of one cube-map mip level, the FIRST kernel of round 1 (sm_100a).
 //
-// Replaces the triple loop of tools/ibl.cpp:263-272 and the per-texel sample
+// NOT part of libdatum_ibl_cuda.so: no default path reaches it since prefilter_dn.cu replaced its
+// six-logic-op tap decode and prefilter_tail_kernel took over the narrow levels.  It is compiled
+// only into the tools build (python -m datum_b200.build --ab -> tools/ab/libdatum_ibl_cuda_ab.so,
+// -DDATUM_IBL_AB_VARIANTS), where variants 10..27 stay selectable for A/B timing against the
+// shipped kernels (profiles/r1_summary.md).
+//
+// Same job: the triple loop of tools/ibl.cpp:263-272 and the per-texel sample
 // loop of tools/ibl.cpp:160-187 (reference paths relative to /root/reference).
-// The library uses it for levels narrower than 8 texels (its tiles may be cut in
-// linear texel order); wider levels run prefilter_dn.cu, which replaced this
-// kernel's six-logic-op tap decode.  Variants 10..27 stay selectable for A/B timing.
 //
 // Work decomposition
 //   tile      = 32*TPT output texels (TW x 32/TW lanes, TPT texels per lane)
@@ -21,8 +24,8 @@
 // 2x2 bilinear footprint, and the biased-mantissa accumulation of ibl_math.cuh.
 // No tensor cores: nothing here is a dense contraction.
 
-#include "prefilter.h"
-#include "ibl_math.cuh"
+#include "../../datum_b200/csrc/prefilter.h"
+#include "../../datum_b200/csrc/ibl_math.cuh"
 
 #include <cuda_runtime.h>
 
