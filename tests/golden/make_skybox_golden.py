@@ -1,7 +1,8 @@
-"""Regenerates tests/golden/skybox64.npz and skybox256.npz: BASELINE config 1 (the reference's
+"""Regenerates tests/golden/skybox64.npz, skybox256.npz and skybox512.npz: BASELINE config 1 (the reference's
 bundled data/skybox_{rt,lf,dn,up,fr,bk}.jpg cube) reduced 8x to 64^2 faces (the whole chain fits a
 small fixture) and 2x to 256^2 faces (level 1 then runs the benchmark's dominant launch shape; the
-fixture holds the faces as 8-bit RGB and the levels >= 1 the UNMODIFIED reference produced, ~25 s).
+fixture holds the faces as 8-bit RGB and the levels >= 1 the UNMODIFIED reference produced, ~25 s),
+and at its NATIVE 512^2 faces x 8 levels (tools/assetbuilder.cpp:416-470 as shipped; same fixture form).
 
 Runs in the authoring container only (needs /root/reference and PIL).  Steps, mirroring
 write_skybox_asset(fout, id, paths) (tools/assetbuilder.cpp:416-470):
@@ -31,6 +32,7 @@ import oracle_lib  # noqa: E402
 ORDER = ("rt", "lf", "dn", "up", "fr", "bk")   # tools/assetbuilder.cpp:876
 W, LEVELS = 64, 7
 W_BIG, LEVELS_BIG = 256, 8
+W_NATIVE, LEVELS_NATIVE = 512, 8     # tools/assetbuilder.cpp:434-437: the images' own size, 8 levels
 
 
 def reduced_faces(w):
@@ -65,6 +67,18 @@ def main():
     path = os.path.join(HERE, "skybox256.npz")
     np.savez_compressed(path, faces_rgb=rgb, levels=chain[6 * W_BIG * W_BIG:])
     print("wrote", path, os.path.getsize(path), "bytes")
+
+    # BASELINE config 1 at NATIVE size: the six 512^2 images as decoded, the whole bake by the unmodified
+    # reference (one thread, ~100-130 s: the number BASELINE.md extrapolated); `seconds` records it
+    import time
+    faces = reduced_faces(W_NATIVE)
+    t0 = time.perf_counter()
+    chain = reference_chain(faces, LEVELS_NATIVE)
+    seconds = time.perf_counter() - t0
+    rgb = np.stack([(faces >> 16) & 0xFF, (faces >> 8) & 0xFF, faces & 0xFF], axis=-1).astype(np.uint8)
+    path = os.path.join(HERE, "skybox512.npz")
+    np.savez_compressed(path, faces_rgb=rgb, levels=chain[6 * W_NATIVE * W_NATIVE:], reference_seconds=np.float64(seconds))
+    print("wrote", path, os.path.getsize(path), "bytes; reference bake (strict build, one thread) took %.1f s" % seconds)
 
 
 if __name__ == "__main__":
