@@ -11,6 +11,7 @@ but every compute entry point raises if the CUDA library or a GPU is missing.
 
 from .ibl import (  # noqa: F401
     IblContext,
+    MultiContext,
     IblError,
     FORMAT_RGBE,
     FORMAT_F32,

@@ -24,6 +24,7 @@ SIGNATURES = {
     "datum_ibl_synchronize": (c_int, [c_void_p]),
     "datum_ibl_launch_count": (ctypes.c_uint64, [c_void_p]),
     "datum_ibl_set_prefilter_variant": (c_int, [c_void_p, c_int]),
+    "datum_ibl_set_tuning": (c_int, [c_void_p, ctypes.c_char_p, c_int]),
     "datum_ibl_chain_bytes": (c_size_t, [c_int, c_int, c_int]),
     "datum_ibl_buildmips_cube_ibl": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "datum_ibl_bake_probes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p]),
@@ -36,6 +37,15 @@ SIGNATURES = {
     "datum_ibl_peer_free": (c_int, [c_void_p, c_void_p]),
     "datum_ibl_peer_open": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
     "datum_ibl_peer_close": (c_int, [c_void_p, c_void_p]),
+    "datum_ibl_multi_create": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_void_p)]),
+    "datum_ibl_multi_destroy": (None, [c_void_p]),
+    "datum_ibl_multi_device_count": (c_int, [c_void_p]),
+    "datum_ibl_multi_context": (c_void_p, [c_void_p, c_int]),
+    "datum_ibl_multi_buildmips_cube_ibl": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "datum_ibl_multi_bake_probes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p]),
+    "datum_ibl_multi_project_sh9": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "datum_ibl_buildmips_cube_ibl_devices": (c_int, [c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_int, c_void_p]),
+    "datum_ibl_bake_probes_devices": (c_int, [c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p]),
     "datum_ibl_sh9_partial_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "datum_ibl_sh9_partial_peers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.c_uint32]),
     "datum_ibl_sh9_finish": (None, [c_void_p, c_void_p]),

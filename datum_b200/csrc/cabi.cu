@@ -27,10 +27,15 @@
 #include <utility>
 #include <vector>
 
+#include "cabi_internal.h"
+
 namespace
 {
   thread_local std::string g_last_error;
+}
 
+namespace ibl_cabi
+{
   int fail(std::string const &what)
   {
     g_last_error = what;
@@ -42,6 +47,12 @@ namespace
     g_last_error = std::string(where) + ": " + cudaGetErrorString(err);
     return 1;
   }
+}
+
+namespace
+{
+  using ibl_cabi::fail;
+  using ibl_cabi::fail_cuda;
 
   struct DeviceTable
   {
@@ -113,6 +124,11 @@ struct datum_ibl_ctx
   cudaEvent_t ev_level[16] = {};  // level L of the current chain is complete (its download starts behind it)
   DeviceBuffer<uint4> records;    // quad records of the current source level
   DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
+  DeviceBuffer<float> split_partials; // partial sums of sample-split tiles (prefilter_dn.cu)
+  DeviceBuffer<int> split_done;       // their per-tile tickets, zero between launches
+  int prefilter_parts_all = 0, prefilter_parts_pool = 0;   // 0 = automatic
+  int prefilter_no_steal = 0;
+  int sh9_kernel = 0, sh9_rows_per_item = 0;   // A/B: 0 = column strips / automatic run length
   DeviceBuffer<unsigned int> peer_ticket; // "CTAs done" counter of launches that signal peers, zero between launches
   bool peer_wait_pending = false; // a stream wait on a peer's arrival is queued: synchronize() watches the clock
   unsigned int *peer_wait_word = nullptr; // the local arrival counters ([2]) those waits look at
@@ -302,12 +318,29 @@ namespace
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(quad records)", err);
 
+    size_t partial_floats = 0, done_ints = 0;
+    ibl::prefilter_split_scratch(row_end - row_begin, wd, ctx->sm_count, &partial_floats, &done_ints);
+    err = ctx->split_partials.reserve(partial_floats);
+    if (err == cudaSuccess && done_ints > ctx->split_done.capacity)
+    {
+      err = ctx->split_done.reserve(done_ints);
+      if (err == cudaSuccess)
+        err = cudaMemsetAsync(ctx->split_done.ptr, 0, ctx->split_done.capacity * sizeof(int), ctx->stream);   // the kernel leaves them at zero
+    }
+    if (err != cudaSuccess)
+      return fail_cuda("cudaMalloc(split scratch)", err);
+
     err = ibl::launch_build_dn_records(d_src, ctx->records.ptr, ws, hs, ctx->queue_heads.ptr, ctx->sm_count + 1, ctx->sm_count, ctx->stream);
     if (err != cudaSuccess)
       return fail_cuda("build_dn_records", err);
     ctx->launches += 1;
 
     ibl::PrefilterDnParams p = {};
+    p.partials = ctx->split_partials.ptr;
+    p.tile_done = ctx->split_done.ptr;
+    p.parts_all = ctx->prefilter_parts_all;
+    p.parts_pool = ctx->prefilter_parts_pool;
+    p.no_steal = ctx->prefilter_no_steal;
     p.records = ctx->records.ptr;
     p.table = table.d_banded;
     p.table_pairs = table.d_pairs;
@@ -482,7 +515,7 @@ namespace
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(sh9 partials)", err);
 
-    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, ctx->sh_counter.ptr, d_partial, peers, ctx->sm_count, stream);
+    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, ctx->sh_counter.ptr, d_partial, peers, ctx->sm_count, stream, ctx->sh9_kernel, ctx->sh9_rows_per_item);
     if (err != cudaSuccess)
       return fail_cuda("sh9_partial", err);
     ctx->launches += 1;
@@ -723,6 +756,9 @@ extern "C"
       if (ctx->ev_level[k]) cudaEventDestroy(ctx->ev_level[k]);
     ctx->records.release();
     ctx->queue_heads.release();
+    ctx->split_partials.release();
+    ctx->split_done.release();
+    ctx->peer_ticket.release();
     ctx->sh_weights.release();
     ctx->sh_partials.release();
     ctx->sh_counter.release();
@@ -793,10 +829,33 @@ extern "C"
 
   int datum_ibl_set_prefilter_variant(datum_ibl_ctx *ctx, int variant)
   {
-    if (!ctx || variant < 0 || variant > 99)
+    // kernel shape + 100 * (shares per tile of a slab too small for the tile queues) + 1000 * (shares per tile
+    // of the pool behind the queues) + 10000 * (no tile stealing, A/B); 0 in a field = automatic
+    if (!ctx || variant < 0 || variant > 19999)
       return fail("datum_ibl_set_prefilter_variant: bad argument");
 
-    ctx->prefilter_variant = variant;
+    ctx->prefilter_variant = variant % 100;
+    ctx->prefilter_parts_all = (variant / 100) % 10;
+    ctx->prefilter_parts_pool = (variant / 1000) % 10;
+    ctx->prefilter_no_steal = variant / 10000;
+    return 0;
+  }
+
+  int datum_ibl_set_tuning(datum_ibl_ctx *ctx, const char *key, int value)
+  {
+    if (!ctx || !key || value < 0)
+      return fail("datum_ibl_set_tuning: bad argument");
+
+    std::string k = key;
+    if (k == "prefilter_variant")
+      return datum_ibl_set_prefilter_variant(ctx, value);
+    if (k == "sh9_kernel" && value <= 1)
+      ctx->sh9_kernel = value;
+    else if (k == "sh9_rows_per_item" && value <= 4096)
+      ctx->sh9_rows_per_item = value;
+    else
+      return fail("datum_ibl_set_tuning: unknown key or value out of range: " + k);
+
     return 0;
   }
 

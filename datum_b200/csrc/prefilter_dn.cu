@@ -214,32 +214,55 @@ namespace ibl
   //
   // %smid values are not guaranteed to be contiguous, and under MPS limits, green contexts or a
   // concurrent kernel an SM may host no CTA of this launch at all: once its own chunk and the pool are
-  // empty a group therefore makes one stealing pass over every other chunk before it gives up, so
-  // every tile is computed whatever the placement of the CTAs (the pass costs p.queues atomics per
-  // CTA at the very end of a launch).
-  __device__ __forceinline__ int next_tile(PrefilterDnParams const &p, uint32_t smid)
+  // empty a group therefore looks through every other chunk before it gives up, so every tile is
+  // computed whatever the placement of the CTAs.  The look is made by the 32 lanes of the group's first
+  // warp side by side (148 dependent L2 reads by one thread cost ~20 us per call, measured as +5 % on a
+  // whole level; 5 rounds of 32 cost under 1 us).  Called by all lanes of warp 0; every lane gets the unit.
+  __device__ __forceinline__ int next_tile(PrefilterDnParams const &p, uint32_t smid, int lane)
   {
     const int own = (int)(smid % (uint32_t)p.queues);
 
-    int k = atomicAdd(p.counters + own, 1);
-    if (k < p.chunk)
-      return own * p.chunk + k;
+    int unit = -1;
 
-    int tile = p.queued + atomicAdd(p.counters + p.queues, 1);
-    if (tile < p.tiles)
-      return tile;
-
-    for(int i = 1; i < p.queues; ++i)
+    if (lane == 0)
     {
-      int q = own + i < p.queues ? own + i : own + i - p.queues;
+      int k = atomicAdd(p.counters + own, 1);
+      if (k < p.chunk)
+        unit = own * p.chunk + k;
+      else
+      {
+        int u = p.queued + atomicAdd(p.counters + p.queues, 1);
+        if (u < p.units)
+          unit = u;
+      }
+    }
+
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+
+    if (unit >= 0 || p.no_steal)
+      return unit;
+
+    for(int base = 1; base < p.queues; base += 32)
+    {
+      int i = base + lane;
+      int q = own + i;
+      if (q >= p.queues)
+        q -= p.queues;
 
       // a drained chunk costs one read; only chunks that still hold tiles are bumped
-      if (*(volatile int const *)(p.counters + q) >= p.chunk)
-        continue;
+      bool holds = i < p.queues && *(volatile int const *)(p.counters + q) < p.chunk;
 
-      k = atomicAdd(p.counters + q, 1);
-      if (k < p.chunk)
-        return q * p.chunk + k;
+      for(unsigned candidates = __ballot_sync(0xffffffffu, holds); candidates != 0u; candidates &= candidates - 1u)
+      {
+        int src = __ffs(candidates) - 1;
+        int k = -1;
+        if (lane == src)
+          k = atomicAdd(p.counters + q, 1);
+        k = __shfl_sync(0xffffffffu, k, src);
+
+        if (k < p.chunk)
+          return __shfl_sync(0xffffffffu, q, src) * p.chunk + k;
+      }
     }
 
     return -1;
@@ -299,8 +322,12 @@ namespace ibl
       int tile;
       if (QUEUES)
       {
-        if (tid == 0)
-          *s_tile = next_tile(p, smid);
+        if (warp == 0)
+        {
+          int next = next_tile(p, smid, lane);
+          if (lane == 0)
+            *s_tile = next;
+        }
         __syncthreads();
         tile = *s_tile;
       }
@@ -663,23 +690,37 @@ namespace ibl
 
     for(int it = 0; ; ++it)
     {
-      int tile;
+      int unit;
       if (QUEUES)
       {
-        if (tid == 0)
-          *s_tile = next_tile(p, smid);
+        if (warp == 0)
+        {
+          int next = next_tile(p, smid, lane);
+          if (lane == 0)
+            *s_tile = next;
+        }
         __syncthreads();
-        tile = *s_tile;
+        unit = *s_tile;
       }
       else
       {
-        tile = (int)blockIdx.x + it * (int)gridDim.x;
-        if (tile >= p.tiles)
-          tile = -1;
+        unit = (int)blockIdx.x + it * (int)gridDim.x;
+        if (unit >= p.units)
+          unit = -1;
       }
 
-      if (tile < 0)
+      if (unit < 0)
         break;
+
+      // whole tile, or one of `parts` interleaved shares of a tile's bands
+      int tile = unit, part = 0, parts = 1;
+      if (unit >= p.queued)
+      {
+        int u = unit - p.queued;
+        tile = p.queued + u / p.parts;
+        part = u - (tile - p.queued) * p.parts;
+        parts = p.parts;
+      }
 
       int x, row;
       bool valid = tile_texel(p, tile, lane, x, row);
@@ -729,13 +770,13 @@ namespace ibl
       acc.bb = 0ull;
 
       float4 const *tw = table + warp * PER;   // entry index == float4 index in the pair-interleaved table
-      int band = 0;
+      int band = part;
 
       {
         uint4 const *base = opaque(biased + (size_t)face * p.geom.face_size);
 
         #pragma unroll BAND_UNROLL
-        for(; band < n_same; ++band)
+        for(; band < n_same; band += parts)
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
@@ -751,7 +792,7 @@ namespace ibl
         st.N = from_face_local(face, Vec3f{ st.N.x * p.geom.inv_hw, st.N.y * p.geom.inv_hh, st.N.z });
 
         #pragma unroll BAND_UNROLL
-        for(; band < p.bands; ++band)
+        for(; band < p.bands; band += parts)
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
@@ -782,7 +823,43 @@ namespace ibl
             sum[c] += s_red[(w * 3 + c) * 32 + lane];
         }
 
-        if (valid)
+        // a share of a tile: the sums of all shares meet in global memory, the share that arrives last
+        // adds them in share order (deterministic whatever the arrival order) and finishes the texels
+        bool finish = true;
+        if (parts > 1)
+        {
+          float *mine = p.partials + (size_t)(unit - p.queued) * 96;
+          #pragma unroll
+          for(int c = 0; c < 3; ++c)
+            __stcg(mine + c * 32 + lane, sum[c]);
+
+          __threadfence();
+
+          int ticket = 0;
+          if (lane == 0)
+            ticket = atomicAdd(p.tile_done + (tile - p.queued), 1);
+          ticket = __shfl_sync(0xffffffffu, ticket, 0);
+
+          finish = ticket == parts - 1;
+          if (finish)
+          {
+            __threadfence();
+
+            float const *all = p.partials + (size_t)(tile - p.queued) * p.parts * 96;
+            sum[0] = sum[1] = sum[2] = 0.0f;
+            for(int k = 0; k < parts; ++k)
+            {
+              #pragma unroll
+              for(int c = 0; c < 3; ++c)
+                sum[c] += __ldcg(all + (k * 3 + c) * 32 + lane);
+            }
+
+            if (lane == 0)
+              p.tile_done[tile - p.queued] = 0;      // ready for the next launch on this stream
+          }
+        }
+
+        if (valid && finish)
         {
           // sum/totalweight of ibl.cpp:186, then rgbe() of ibl.cpp:269
           float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
@@ -1051,6 +1128,8 @@ namespace ibl
       p.queues = sm_count;
       p.chunk = (p.tiles - p.tiles / 8) / sm_count;
       p.queued = p.chunk * sm_count;
+      p.units = p.tiles;      // the one-sample kernel only knows whole tiles
+      p.parts = 1;
 
       kernel<<<grid, 32 * NW, smem, stream>>>(p);
 
@@ -1080,13 +1159,40 @@ namespace ibl
       if (err != cudaSuccess)
         return err;
 
-      int grid = p.tiles < sm_count * resident ? p.tiles : sm_count * resident;
-      if (grid < 1)
-        grid = 1;
+      const int slots = sm_count * resident;
 
       p.queues = sm_count;
-      p.chunk = (p.tiles - p.tiles / 8) / sm_count;
-      p.queued = p.chunk * sm_count;
+
+      if (QUEUES)
+      {
+        // 7/8 of the tiles as whole tiles in per-SM chunks, then the pool that evens out the end of the
+        // launch.  Pool tiles in 2, 4 or 8 shares were measured (profiles/r2_summary.md): no gain on the
+        // 512^2 -> 256^2 level, 2 % on the next one; whole tiles stay the default.
+        p.chunk = (p.tiles - p.tiles / 8) / sm_count;
+        p.queued = p.chunk * sm_count;
+        p.parts = p.parts_pool > 0 ? p.parts_pool : 1;
+      }
+      else
+      {
+        // A slab that does not fill the machine several times over could run every tile in shares so
+        // that the last wave is short.  Measured on 768 tiles for 592 resident CTAs: 2 shares -5 %,
+        // 4 shares +11 %, 8 shares +38 % (every share repeats the tile set-up, and a half-empty SM runs
+        // its CTAs faster than a full one anyway): whole tiles unless asked otherwise.
+        p.chunk = 0;
+        p.queued = 0;
+        p.parts = p.parts_all > 0 ? p.parts_all : 1;
+      }
+
+      if (p.parts > p.bands)
+        p.parts = p.bands > 0 ? p.bands : 1;
+      if (!p.partials || !p.tile_done)
+        p.parts = 1;
+
+      p.units = p.queued + (p.tiles - p.queued) * p.parts;
+
+      int grid = p.units < slots ? p.units : slots;
+      if (grid < 1)
+        grid = 1;
 
       kernel<<<grid, 32 * NW, smem, stream>>>(p);
 
@@ -1101,6 +1207,21 @@ namespace ibl
     {
       return p.table_pairs != nullptr && (unsigned long long)p.geom.bias + 6ull * p.geom.face_size <= 0xFFFFFFFFull;
     }
+  }
+
+  // slabs of at least this many texels take their tiles from per-SM queues (and only split the pool)
+  constexpr size_t kQueuedTexels = 32u * 148u * 8u;
+
+  void prefilter_split_scratch(int rows, int wd, int sm_count, size_t *partial_floats, size_t *done_ints)
+  {
+    // upper bound for any split the launchers choose: 8 shares of every tile that can be split
+    int tiles_x = (wd + 7) / 8, tiles_y = (rows + 3) / 4;
+    size_t tiles = (size_t)((tiles_x + 3) / 4) * ((tiles_y + 3) / 4) * 16;
+    size_t split = tiles;
+    if ((size_t)rows * wd >= kQueuedTexels)
+      split = tiles - ((tiles - tiles / 8) / sm_count) * sm_count;     // the pool behind the per-SM chunks
+    *partial_floats = split * 8 * 96;
+    *done_ints = split;
   }
 
   cudaError_t launch_prefilter_dn(PrefilterDnParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid)
@@ -1119,7 +1240,7 @@ namespace ibl
       // the two biggest classes work on two samples at a time (prefilter_dp_kernel; measured on C2:
       // level 1 885 -> 862 us, level 2 277 -> 262, level 3 96 -> 88); launch_prefilter_dn falls back to
       // the one-sample kernel when the biased record index could wrap
-      if (texels >= 32u * 148u * 8u)
+      if (texels >= kQueuedTexels)
         variant = big_table ? 71 : 70;
       else
         variant = big_table ? 73 : 72;      // slabs of at most kTailTexels never get here (prefilter_tail_kernel)

@@ -6,10 +6,11 @@
 // catastrophically in fp32 once faces exceed a few hundred texels, so it is
 // evaluated ONCE per (x, y) in fp64 into a table that the context caches per
 // face size.  The projection itself streams the slab once (16 B/texel RGBA32F):
-// a CTA takes 1024-texel segments of rows, every thread issues its four 16-byte
-// loads before any arithmetic, accumulates 27 sums + the weight sum in registers,
-// then warp-shuffle and block-reduce in fp64.  Block partials are summed in block
-// order by whichever block finishes last, so the result is run-to-run deterministic.
+// a thread owns one column of a face for a run of rows, keeps eight 16-byte loads in
+// flight and accumulates six row moments per channel, folded into the 27 sums once per
+// run (sh9_columns_kernel); then warp-shuffle and block-reduce in fp64.  Block partials
+// are summed in block order by whichever block finishes last, so the result is run-to-run
+// deterministic.  The first kernel (row segments, 27 FMAs per texel) stays for A/B.
 
 #include "sh9.h"
 #include "ibl_math.cuh"
@@ -345,6 +346,273 @@ namespace ibl
       *done_counter = 0;      // ready for the next launch on this stream
   }
 
+  // ---- projection, column strips (the kernel in use) ------------------------------------------------
+  //
+  // The row-segment kernel above spends ~84 instructions per texel (27 accumulating FMAs with three
+  // distinct register operands, the monomials, the ray, item bookkeeping every four texels) and sits
+  // where the instruction-issue and HBM roofs meet: 0.71 of the measured copy bandwidth with exactly
+  // the algorithmic traffic.  Here a thread owns ONE COLUMN x of a face for a run of rows.  With
+  // (a, b, c) = (u, v, 1)/|(u, v, 1)| every basis monomial is a product of at most two of a, b, c, and
+  // u is a constant of the thread, so per channel six row moments carry everything:
+  //     M0 = sum q      M1 = sum q i      M2 = sum q i v      M3 = sum q i^2      M4 = sum q i^2 v      M5 = sum q i^2 v^2
+  // (q = solid angle x colour, i = 1/|(u, v, 1)|): 4 products + 5 FMAs + 1 add per channel instead of
+  // 8 + 9 FMAs, ~34 instructions per texel.  At the end of a run the 18 moments are folded into the 27
+  // monomial sums with the thread's powers of u and the face's axis permutation (once per run, not per
+  // texel).  Loads: eight rows of the column in flight per thread before any arithmetic (16-byte texel,
+  // 4-byte solid angle), a warp reads 512 contiguous bytes of each row.
+  constexpr int kSh9ColThreads = 256;
+  constexpr int kSh9ColUnroll = 8;
+
+  // 18 moments + the thread's u -> monomial sums of one channel triple, per face (data/convolve.comp:85-100)
+  template<int FACE>
+  __device__ __forceinline__ void sh9_fold(float const M[6][3], float u, float acc[28])
+  {
+    const float uu = u * u;
+
+    #pragma unroll
+    for(int ch = 0; ch < 3; ++ch)
+    {
+      // sums of q times: 1, a, b, c, aa, ab, ac, bb, bc, cc
+      float s1 = M[0][ch];
+      float sa = u * M[1][ch], sb = M[2][ch], sc = M[1][ch];
+      float saa = uu * M[3][ch], sab = u * M[4][ch], sac = u * M[3][ch], sbb = M[5][ch], sbc = M[4][ch], scc = M[3][ch];
+
+      // ray = (rx, ry, rz) as signed picks of (a, b, c); monomials y, z, x, xy, yz, zz, zx, xx - yy
+      float y, z, x, xy, yz, zz, zx, xxyy;
+      switch (FACE)
+      {
+        case 0:  x = sc;  y = sb;  z = sa;  xy = sbc;  yz = sab;  zz = saa; zx = sac;  xxyy = scc - sbb; break;   // ( c,  b,  a)
+        case 1:  x = -sc; y = sb;  z = -sa; xy = -sbc; yz = -sab; zz = saa; zx = sac;  xxyy = scc - sbb; break;   // (-c,  b, -a)
+        case 2:  x = sa;  y = -sc; z = -sb; xy = -sac; yz = sbc;  zz = sbb; zx = -sab; xxyy = saa - scc; break;   // ( a, -c, -b)
+        case 3:  x = sa;  y = sc;  z = sb;  xy = sac;  yz = sbc;  zz = sbb; zx = sab;  xxyy = saa - scc; break;   // ( a,  c,  b)
+        case 4:  x = sa;  y = sb;  z = -sc; xy = sab;  yz = -sbc; zz = scc; zx = -sac; xxyy = saa - sbb; break;   // ( a,  b, -c)
+        default: x = -sa; y = sb;  z = sc;  xy = -sab; yz = sbc;  zz = scc; zx = -sac; xxyy = saa - sbb; break;   // (-a,  b,  c)
+      }
+
+      acc[0 + ch] += s1;
+      acc[3 + ch] += y;
+      acc[6 + ch] += z;
+      acc[9 + ch] += x;
+      acc[12 + ch] += xy;
+      acc[15 + ch] += yz;
+      acc[18 + ch] += zz;
+      acc[21 + ch] += zx;
+      acc[24 + ch] += xxyy;
+    }
+  }
+
+  __device__ __forceinline__ void sh9_fold_face(int face, float const M[6][3], float u, float acc[28])
+  {
+    switch (face)
+    {
+      case 0: sh9_fold<0>(M, u, acc); break;
+      case 1: sh9_fold<1>(M, u, acc); break;
+      case 2: sh9_fold<2>(M, u, acc); break;
+      case 3: sh9_fold<3>(M, u, acc); break;
+      case 4: sh9_fold<4>(M, u, acc); break;
+      default: sh9_fold<5>(M, u, acc); break;
+    }
+  }
+
+  template<int FORMAT>
+  __global__ void __launch_bounds__(kSh9ColThreads, 2) sh9_columns_kernel(void const *__restrict__ level0, float const *__restrict__ weights, int w, int h, int row_begin, int row_end, int rows_per_item, double *__restrict__ block_partials, unsigned int *__restrict__ done_counter, double *__restrict__ partial, Sh9Peers peers)
+  {
+    float acc[28];
+    #pragma unroll
+    for(int k = 0; k < 28; ++k)
+      acc[k] = 0.0f;
+
+    const float inv_w = 1.0f / (float)w, inv_h = 1.0f / (float)h;
+    const unsigned long long stream_policy = l2_policy_evict_first(), keep_policy = l2_policy_evict_last();
+
+    // work items: (run of rows_per_item rows of the slab, block of 256 columns), column blocks fastest so that
+    // the CTAs in flight read neighbouring 4 KB pieces of the same rows
+    const int col_blocks = (w + kSh9ColThreads - 1) / kSh9ColThreads;
+    const int runs = (row_end - row_begin + rows_per_item - 1) / rows_per_item;
+    const long long items = (long long)runs * col_blocks;
+
+    for(long long item = blockIdx.x; item < items; item += gridDim.x)
+    {
+      const int run = (int)(item / col_blocks);
+      const int x = (int)(item - (long long)run * col_blocks) * kSh9ColThreads + (int)threadIdx.x;
+      const bool live = x < w;
+
+      // project.comp:53: u = 2 (x + .5) / w - 1
+      const float u = live ? 2.0f * ((float)x + 0.5f) * inv_w - 1.0f : 0.0f;
+      const float uu1 = fmaf(u, u, 1.0f);
+      const int xs = x < w - 1 - x ? x : w - 1 - x;      // the solid angle is symmetric in x and y: one quadrant of the table is ever touched
+
+      int row = row_begin + run * rows_per_item;
+      const int run_end = min(row + rows_per_item, row_end);
+
+      // a run may cross into the next face (faces are stacked in the row index): one fold per face piece
+      while (row < run_end)
+      {
+        const int face = row / h;
+        const int piece_end = min(run_end, (face + 1) * h);
+
+        float M[6][3];
+        #pragma unroll
+        for(int k = 0; k < 6; ++k)
+          M[k][0] = M[k][1] = M[k][2] = 0.0f;
+        float wsum = 0.0f;
+
+        for(; row < piece_end; row += kSh9ColUnroll)
+        {
+          float r[kSh9ColUnroll], g[kSh9ColUnroll], bl[kSh9ColUnroll], weight[kSh9ColUnroll];
+
+          #pragma unroll
+          for(int j = 0; j < kSh9ColUnroll; ++j)
+          {
+            const int rj = row + j;
+            if (live && rj < piece_end)
+            {
+              const int y = rj - face * h;
+              const int ys = y < h - 1 - y ? y : h - 1 - y;
+              load_texel<FORMAT>(level0, (size_t)rj * w + x, stream_policy, r[j], g[j], bl[j]);
+              weight[j] = ldg_keep(weights + (size_t)ys * w + xs, keep_policy);
+            }
+            else
+            {
+              r[j] = g[j] = bl[j] = 0.0f;
+              weight[j] = 0.0f;          // a texel past the piece adds exact zeros
+            }
+          }
+
+          #pragma unroll
+          for(int j = 0; j < kSh9ColUnroll; ++j)
+          {
+            // project.comp:53-54: v = 2 (y + .5) / h - 1, ray = normalize(rot * (u, v, -1))
+            const int y = row + j - face * h;
+            const float v = 2.0f * ((float)y + 0.5f) * inv_h - 1.0f;
+            const float i1 = rsqrtf(fmaf(v, v, uu1));
+            const float i1v = i1 * v;
+            const float i2 = i1 * i1;
+            const float i2v = i2 * v;
+            const float i2vv = i2v * v;
+
+            const float q[3] = { weight[j] * r[j], weight[j] * g[j], weight[j] * bl[j] };
+
+            #pragma unroll
+            for(int ch = 0; ch < 3; ++ch)
+            {
+              M[0][ch] += q[ch];
+              M[1][ch] = fmaf(q[ch], i1, M[1][ch]);
+              M[2][ch] = fmaf(q[ch], i1v, M[2][ch]);
+              M[3][ch] = fmaf(q[ch], i2, M[3][ch]);
+              M[4][ch] = fmaf(q[ch], i2v, M[4][ch]);
+              M[5][ch] = fmaf(q[ch], i2vv, M[5][ch]);
+            }
+            wsum += weight[j];
+          }
+        }
+
+        row = piece_end;
+        sh9_fold_face(face, M, u, acc);
+        acc[27] += wsum;
+      }
+    }
+
+    // ---- warp shuffle reduction in fp64, then across the block's warps (as in the row-segment kernel) ----
+    __shared__ double s_partial[kSh9ColThreads / 32][28];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    #pragma unroll
+    for(int k = 0; k < 28; ++k)
+    {
+      double v = (double)acc[k];
+      #pragma unroll
+      for(int offset = 16; offset > 0; offset >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, offset);
+
+      if (lane == 0)
+        s_partial[warp][k] = v;
+    }
+
+    __syncthreads();
+
+    __shared__ double s_mono[28];
+
+    if (threadIdx.x < 28)
+    {
+      double v = 0;
+      #pragma unroll
+      for(int wi = 0; wi < kSh9ColThreads / 32; ++wi)
+        v += s_partial[wi][threadIdx.x];
+
+      s_mono[threadIdx.x] = v;
+    }
+
+    __syncthreads();
+
+    if (threadIdx.x < 28)
+      block_partials[(size_t)blockIdx.x * 28 + threadIdx.x] = sh9_basis_from_monomials(threadIdx.x, s_mono);
+
+    // ---- the block that finishes last sums the block partials, in block order: deterministic, one launch ----
+    __shared__ bool s_last;
+
+    __threadfence();
+    __syncthreads();
+
+    if (threadIdx.x == 0)
+    {
+      unsigned int ticket = atomicAdd(done_counter, 1u);
+      s_last = ticket == gridDim.x - 1;
+    }
+
+    __syncthreads();
+
+    if (!s_last)
+      return;
+
+    __threadfence();
+
+    constexpr int kParts = kSh9ColThreads / 28;              // 9
+    __shared__ double s_part[kParts][28];
+
+    if (threadIdx.x < kParts * 28)
+    {
+      int k = threadIdx.x % 28, part = threadIdx.x / 28;
+      double v = 0;
+
+      #pragma unroll 8
+      for(int i = part; i < (int)gridDim.x; i += kParts)
+        v += __ldcg(block_partials + (size_t)i * 28 + k);
+
+      s_part[part][k] = v;
+    }
+
+    __syncthreads();
+
+    if (threadIdx.x < 28)
+    {
+      double v = 0;
+      #pragma unroll
+      for(int part = 0; part < kParts; ++part)
+        v += s_part[part][threadIdx.x];
+
+      partial[threadIdx.x] = v;
+
+      // a cube shared by several GPUs: the slab's sums go straight into every peer's array
+      for(int k = 0; k < peers.count; ++k)
+        peers.slots[k][threadIdx.x] = v;
+    }
+
+    // ... and the peers' streams are told (they wait on their arrival counter, no kernel in between)
+    if (peers.count > 0 && peers.arrive[0])
+    {
+      __threadfence_system();
+      __syncthreads();
+
+      if ((int)threadIdx.x < peers.count)
+        asm volatile("red.release.sys.global.add.u32 [%0], 1;" :: "l"(peers.arrive[threadIdx.x]) : "memory");
+    }
+
+    if (threadIdx.x == 0)
+      *done_counter = 0;      // ready for the next launch on this stream
+  }
+
   // ---- irradiance cube from SH9: data/lighting.inc:351-366, 371 ---------------------
 
   __global__ void __launch_bounds__(256) sh9_irradiance_kernel(Sh9Coefficients sh, int w, int h, uint32_t *__restrict__ words, float *__restrict__ f32)
@@ -415,20 +683,48 @@ namespace ibl
 
   int sh9_partial_blocks(int w, int h, int sm_count)
   {
-    // upper bound for any slab of the cube: one CTA per (row, segment) item up to 4 resident CTAs per SM
-    long long items = (long long)6 * h * ((w + kSh9Segment - 1) / kSh9Segment);
+    // upper bound for any slab of the cube and either kernel: up to 4 resident CTAs per SM
+    long long items = (long long)6 * h * ((w + kSh9ColThreads - 1) / kSh9ColThreads);
     long long cap = (long long)sm_count * 4;
     return (int)(items < cap ? (items < 1 ? 1 : items) : cap);
   }
 
-  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, unsigned int *done_counter, double *partial, Sh9Peers const &peers, int sm_count, cudaStream_t stream)
+  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, unsigned int *done_counter, double *partial, Sh9Peers const &peers, int sm_count, cudaStream_t stream, int kernel, int rows_per_item)
   {
-    (void)sm_count;
+    if (kernel == 1)
+    {
+      // the row-segment kernel (A/B)
+      if (format == 0)
+        sh9_partial_kernel<0><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial, peers);
+      else
+        sh9_partial_kernel<1><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial, peers);
+
+      return cudaGetLastError();
+    }
+
+    // column strips: two CTAs per SM; runs short enough that the slab makes several items per resident CTA
+    // (the fold costs ~60 FMAs per run and thread: at least 8 rows per run keeps it under 8 per texel)
+    const int resident = sm_count * 2;
+    const int col_blocks = (w + kSh9ColThreads - 1) / kSh9ColThreads;
+    const int rows = row_end - row_begin;
+
+    if (rows_per_item <= 0)
+    {
+      long long want_items = 6ll * resident;
+      long long r = ((long long)rows * col_blocks + want_items - 1) / want_items;
+      rows_per_item = (int)(r < 8 ? 8 : (r > 64 ? 64 : r));
+      rows_per_item = (rows_per_item + kSh9ColUnroll - 1) / kSh9ColUnroll * kSh9ColUnroll;
+    }
+
+    long long items = (long long)((rows + rows_per_item - 1) / rows_per_item) * col_blocks;
+    int grid = (int)(items < resident ? (items < 1 ? 1 : items) : resident);
+    if (grid > blocks)
+      grid = blocks;      // the scratch holds `blocks` partial rows
 
     if (format == 0)
-      sh9_partial_kernel<0><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial, peers);
+      sh9_columns_kernel<0><<<grid, kSh9ColThreads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, rows_per_item, block_partials, done_counter, partial, peers);
     else
-      sh9_partial_kernel<1><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial, peers);
+      sh9_columns_kernel<1><<<grid, kSh9ColThreads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, rows_per_item, block_partials, done_counter, partial, peers);
 
     return cudaGetLastError();
   }

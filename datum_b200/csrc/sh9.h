@@ -24,7 +24,8 @@ namespace ibl
 
   // block_partials: blocks*28 doubles of scratch; done_counter: one zero-initialised word the kernel
   // leaves at zero; partial: 28 doubles (27 sums + weight sum).  One launch.
-  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, unsigned int *done_counter, double *partial, Sh9Peers const &peers, int sm_count, cudaStream_t stream);
+  // kernel: 0 = column strips (default), 1 = row segments (A/B); rows_per_item: 0 = automatic
+  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, unsigned int *done_counter, double *partial, Sh9Peers const &peers, int sm_count, cudaStream_t stream, int kernel = 0, int rows_per_item = 0);
 
   cudaError_t launch_sh9_irradiance(Sh9Coefficients const &sh, int w, int h, uint32_t *words, float *f32, int sm_count, cudaStream_t stream);
 }

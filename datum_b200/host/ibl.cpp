@@ -30,30 +30,69 @@ void image_pack_irradiance_cube(void const *sh9_bits, int width, int height, voi
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace
 {
   int g_samples = 1024; // tools/ibl.cpp:162
 
-  // One lazily created context per process, like the reference's stateless free
-  // functions: callers never see it.  DATUM_IBL_DEVICE selects the GPU.
-  datum_ibl_ctx *context()
+  // One lazily created device set per process, like the reference's stateless free functions: callers
+  // never see it.  DATUM_IBL_DEVICES="0,1,2,3" lists the GPUs this process may use (default: the one
+  // device DATUM_IBL_DEVICE names, else device 0).  With several devices a batch is spread probe by probe,
+  // and ONE probe of at least DATUM_IBL_SPLIT_MIN_FACE texels per face (default 1024 x 1024) is shared by
+  // all of them, rows of every level split (datum_ibl_multi_*); smaller probes run on the first device.
+  struct Devices
   {
-    static datum_ibl_ctx *ctx = nullptr;
+    datum_ibl_multi *multi = nullptr;
+    datum_ibl_ctx *first = nullptr;
+    int count = 0;
+    long long split_min_face = 1024LL * 1024LL;
+  };
+
+  Devices &devices()
+  {
+    static Devices set;
     static std::once_flag once;
     static std::string error;
 
     std::call_once(once, [] {
-      const char *env = std::getenv("DATUM_IBL_DEVICE");
-      if (datum_ibl_create(env ? std::atoi(env) : 0, &ctx))
+      std::vector<int> list;
+      if (const char *env = std::getenv("DATUM_IBL_DEVICES"))
+      {
+        for(const char *p = env; *p; )
+        {
+          char *end = nullptr;
+          long v = std::strtol(p, &end, 10);
+          if (end == p)
+            break;
+          list.push_back((int)v);
+          p = (*end == ',') ? end + 1 : end;
+        }
+      }
+      if (list.empty())
+      {
+        const char *env = std::getenv("DATUM_IBL_DEVICE");
+        list.push_back(env ? std::atoi(env) : 0);
+      }
+      if (const char *env = std::getenv("DATUM_IBL_SPLIT_MIN_FACE"))
+        set.split_min_face = std::atoll(env);
+
+      if (datum_ibl_multi_create((int)list.size(), list.data(), &set.multi))
         error = datum_ibl_last_error();
+      else
+      {
+        set.first = datum_ibl_multi_context(set.multi, 0);
+        set.count = (int)list.size();
+      }
     });
 
-    if (!ctx)
+    if (!set.multi)
       throw std::runtime_error("datum ibl: " + error);
 
-    return ctx;
+    return set;
   }
+
+  datum_ibl_ctx *context() { return devices().first; }
 
   void check(int status)
   {
@@ -65,7 +104,12 @@ namespace
 ///////////////////////// image_buildmips_cube_ibl //////////////////////////
 void image_buildmips_cube_ibl(int width, int height, int levels, void *bits)
 {
-  check(datum_ibl_buildmips_cube_ibl(context(), width, height, levels, g_samples, bits));
+  Devices &set = devices();
+
+  if (set.count > 1 && (long long)width * height >= set.split_min_face)
+    check(datum_ibl_multi_buildmips_cube_ibl(set.multi, width, height, levels, g_samples, bits));
+  else
+    check(datum_ibl_buildmips_cube_ibl(set.first, width, height, levels, g_samples, bits));
 }
 
 ///////////////////////// image_pack_cube_ibl ///////////////////////////////
@@ -95,7 +139,12 @@ void image_pack_watercolor(lml::Color3 const &deepcolor, lml::Color3 const &shal
 ///////////////////////// extensions ////////////////////////////////////////
 void image_project_sh9_cube(int width, int height, void const *level0_rgbe, float *sh)
 {
-  check(datum_ibl_project_sh9(context(), level0_rgbe, DATUM_IBL_FORMAT_RGBE, width, height, sh));
+  Devices &set = devices();
+
+  if (set.count > 1 && (long long)width * height >= set.split_min_face)
+    check(datum_ibl_multi_project_sh9(set.multi, level0_rgbe, DATUM_IBL_FORMAT_RGBE, width, height, sh));
+  else
+    check(datum_ibl_project_sh9(set.first, level0_rgbe, DATUM_IBL_FORMAT_RGBE, width, height, sh));
 }
 
 void image_pack_cube_faces_ibl(unsigned int const *argb, int width, int height, int levels, void *bits)
@@ -105,7 +154,7 @@ void image_pack_cube_faces_ibl(unsigned int const *argb, int width, int height, 
 
 void image_buildmips_cube_ibl_batch(int count, int width, int height, int levels, void *const *bits, float *sh)
 {
-  check(datum_ibl_bake_probes(context(), count, width, height, levels, g_samples, bits, sh));
+  check(datum_ibl_multi_bake_probes(devices().multi, count, width, height, levels, g_samples, bits, sh));
 }
 
 void image_pack_irradiance_sh9(int width, int height, void const *level0_rgbe, void *bits)

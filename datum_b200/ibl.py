@@ -162,6 +162,10 @@ class IblContext:
     def set_prefilter_variant(self, variant):
         self._check(self._lib.datum_ibl_set_prefilter_variant(self._handle, int(variant)))
 
+    def set_tuning(self, key, value):
+        """Development knobs of datum_ibl_set_tuning (A/B timing)."""
+        self._check(self._lib.datum_ibl_set_tuning(self._handle, key.encode(), int(value)))
+
     def last_prefilter_ms(self):
         ms = ctypes.c_float()
         self._check(self._lib.datum_ibl_last_prefilter_ms(self._handle, ctypes.byref(ms)))
@@ -382,6 +386,59 @@ class IblContext:
         height, width = faces.shape[1], faces.shape[2]
         ptr = _host_pointer(bits, image_datasize(width, height, 6, levels), "bits")
         self._check(self._lib.datum_ibl_ingest_cube_argb32_ibl(self._handle, width, height, levels, samples, faces.ctypes.data, ptr))
+
+
+class MultiContext:
+    """Several GPUs of one node driven from this process (wraps datum_ibl_multi): the single-process
+    counterpart of dist.py.  `devices` may list a device more than once."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        self.devices = [int(d) for d in devices]
+        handle = ctypes.c_void_p()
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        if self._lib.datum_ibl_multi_create(len(self.devices), arr, ctypes.byref(handle)):
+            raise IblError(self._lib.datum_ibl_last_error().decode("utf-8", "replace"))
+        self._handle = handle
+
+    def _check(self, status):
+        if status:
+            raise IblError(self._lib.datum_ibl_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.datum_ibl_multi_destroy(self._handle)
+            self._handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def image_buildmips_cube_ibl(self, width, height, levels, bits, samples=1024):
+        """tools/ibl.h:9 with ONE probe shared by the devices (rows of every big level split, NVLink peer stores)."""
+        ptr = _host_pointer(bits, image_datasize(width, height, 6, levels), "bits")
+        self._check(self._lib.datum_ibl_multi_buildmips_cube_ibl(self._handle, width, height, levels, samples, ptr))
+
+    def bake_probes(self, width, height, levels, payloads, samples=1024, sh9=False):
+        """IblContext.bake_probes with probe p on devices[p % ndev]."""
+        count = len(payloads)
+        need = image_datasize(width, height, 6, levels)
+        pointers = (ctypes.c_void_p * max(count, 1))()
+        for i, payload in enumerate(payloads):
+            pointers[i] = _host_pointer(payload, need, "payloads[%d]" % i)
+        sh = np.zeros((count, 9, 3), np.float32) if sh9 else None
+        self._check(self._lib.datum_ibl_multi_bake_probes(self._handle, count, width, height, levels, samples, pointers, sh.ctypes.data if sh9 and count else None))
+        return sh
+
+    def project_sh9(self, level0, fmt, width, height):
+        """IblContext.project_sh9 with the cube's rows split over the devices."""
+        texel_bytes = 4 if fmt == FORMAT_RGBE else 16
+        ptr = _host_pointer(level0, 6 * width * height * texel_bytes, "level0")
+        sh = np.zeros((9, 3), np.float32)
+        self._check(self._lib.datum_ibl_multi_project_sh9(self._handle, ptr, fmt, width, height, sh.ctypes.data))
+        return sh
 
 
 _default = {}

@@ -56,6 +56,12 @@ uint64_t datum_ibl_launch_count(datum_ibl_ctx *ctx);
 /* prefilter kernel variant: 0 = automatic (default); 51-54, 70-73, 80 pin one of the shipped kernels (tests); others exist in the tools build only */
 int datum_ibl_set_prefilter_variant(datum_ibl_ctx *ctx, int variant);
 
+/*
+ * Development knobs (A/B timing; defaults are what the library measured best): "prefilter_variant" (as above),
+ * "sh9_kernel" (0 = column strips, 1 = the row-segment kernel), "sh9_rows_per_item" (0 = automatic).
+ */
+int datum_ibl_set_tuning(datum_ibl_ctx *ctx, const char *key, int value);
+
 /* bytes of a `levels`-deep cube chain; tools/assetpacker.cpp:488-497 with layers = 6 */
 size_t datum_ibl_chain_bytes(int width, int height, int levels);
 
@@ -146,6 +152,41 @@ int datum_ibl_prefilter_level_peers(datum_ibl_ctx *ctx, uint32_t const *d_src, i
  */
 int datum_ibl_peer_barrier(datum_ibl_ctx *ctx, int rank, int world, uint32_t *const *d_flags, uint32_t epoch);
 int datum_ibl_set_peer_timeout_ms(datum_ibl_ctx *ctx, int milliseconds);
+
+/* ---- device list: several GPUs of a node driven from ONE process (SURVEY.md 8b last row) ------- */
+
+/*
+ * tools/assetbuilder.cpp is one process whose main thread calls image_buildmips_cube_ibl once per
+ * skybox (:465, :486; write_core :778).  A datum_ibl_multi owns one context per listed device and enables
+ * plain peer access between them (cudaDeviceEnablePeerAccess; no IPC handles, no second process).  At most
+ * 8 devices; a device may be listed more than once (two contexts on one GPU — how the exchange path is
+ * tested on a one-GPU box).  Every call is synchronous and must come from one thread at a time.
+ */
+typedef struct datum_ibl_multi datum_ibl_multi;
+
+int datum_ibl_multi_create(int ndev, int const *devices, datum_ibl_multi **out);
+void datum_ibl_multi_destroy(datum_ibl_multi *multi);
+int datum_ibl_multi_device_count(datum_ibl_multi *multi);
+datum_ibl_ctx *datum_ibl_multi_context(datum_ibl_multi *multi, int index);   /* the context of devices[index] (owned by multi) */
+
+/*
+ * datum_ibl_buildmips_cube_ibl with ONE probe shared by the devices (BASELINE config 3): the rows of every
+ * level above 6x16^2 texels are split evenly, each device's prefilter launch stores its slab into all
+ * payloads over NVLink and signals the peers, the streams wait on the arrival counters; smaller levels are
+ * computed by every device.  Level 0 is uploaded once and copied device to device; the result comes back
+ * from the first device.  Words equal the single-device bake's up to the re-cut tiles (>= 99.99 % identical).
+ */
+int datum_ibl_multi_buildmips_cube_ibl(datum_ibl_multi *multi, int width, int height, int levels, int samples, void *bits);
+
+/* datum_ibl_bake_probes with probe p on devices[p % ndev] (BASELINE config 4); results identical to one device's */
+int datum_ibl_multi_bake_probes(datum_ibl_multi *multi, int count, int width, int height, int levels, int samples, void *const *bits, float *sh);
+
+/* datum_ibl_project_sh9 with the cube's rows split over the devices (BASELINE config 5); slabs are added in device order on the host */
+int datum_ibl_multi_project_sh9(datum_ibl_multi *multi, void const *level0, int format, int width, int height, float *sh);
+
+/* the first two with the device list passed per call; the library keeps one datum_ibl_multi per distinct list */
+int datum_ibl_buildmips_cube_ibl_devices(int ndev, int const *devices, int width, int height, int levels, int samples, void *bits);
+int datum_ibl_bake_probes_devices(int ndev, int const *devices, int count, int width, int height, int levels, int samples, void *const *bits, float *sh);
 
 /* ---- equirectangular HDR image -> cube: tools/hdr.cpp:331-359, tools/ibl.cpp:283-288 ---- */
 

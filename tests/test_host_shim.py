@@ -29,8 +29,8 @@ def build_driver():
     return DRIVER
 
 
-def run_driver(*args):
-    return subprocess.run([build_driver()] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+def run_driver(*args, env=None):
+    return subprocess.run([build_driver()] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
 
 
 def write_hdr(path, image, exposure=None):

@@ -90,6 +90,56 @@ def test_baseline_config_3_level_1_against_the_oracle_on_spot_rows(ctx):
         parity.check_level(got, got_f32, src, ws, ws, 1, levels, samples, a, b, min_identical=0.98)
 
 
+def test_baseline_config_3_levels_2_to_11_against_the_oracle(ctx):
+    """BASELINE config 3 below its first level: the whole 2048^2 x 12-level x 4096-spp chain is baked on the
+    GPU, then every level is compared with the oracle run on the SAME source level — levels 2-4 (512^2,
+    256^2 and 128^2 faces: the pair kernel reading its 4096-entry table through L1) on rows at a face edge,
+    across a face seam, in a face centre and at the last edge; levels 5-11 (64^2 ... 1x1 faces, the tail
+    kernel at 4096 spp) completely."""
+    w, levels, samples = 2048, 12, 4096
+    offs = datum_b200.level_offsets(w, w, levels)
+    bits = synth.synthetic_chain(w, w, levels, probe=3, noise=True, sun=False)
+    d_bits = torch.from_numpy(bits.view(np.int32)).to(DEV)
+    d_f32 = torch.zeros((offs[-1] - offs[2]) * 3, dtype=torch.float32, device=DEV)      # levels >= 2 only (level 1 alone would be 75 MB)
+    # level 1 through the level entry point, the rest through the chain on the sub-pyramid that starts at level 1:
+    # roughness depends on (level, levels) only, so the sub-chain is run level by level
+    for level in range(1, levels):
+        ws = w >> (level - 1)
+        f32 = d_f32[(offs[level] - offs[2]) * 3:(offs[level + 1] - offs[2]) * 3] if level >= 2 else None
+        ctx.prefilter_level_device(d_bits[offs[level - 1]:offs[level]], ws, ws, level, levels, samples, 0, 6 * (ws >> 1), d_bits[offs[level]:offs[level + 1]], f32)
+    ctx.synchronize()
+    got = d_bits.cpu().numpy().view(np.uint32)
+    got_f32 = d_f32.cpu().numpy().reshape(-1, 3)
+    for level in range(2, levels):
+        ws = w >> (level - 1)
+        hd = ws >> 1
+        ranges = spot_ranges(hd, rows=2) if level <= 4 else [(0, 6 * hd)]
+        for a, b in ranges:
+            parity.check_level(got[offs[level]:offs[level + 1]], got_f32[offs[level] - offs[2]:offs[level + 1] - offs[2]],
+                               got[offs[level - 1]:offs[level]], ws, ws, level, levels, samples, a, b, min_identical=0.98 if level <= 3 else 0.99)
+
+
+def test_a_config_4_probe_through_the_batch_entry_against_the_oracle(ctx):
+    """BASELINE config 4's unit (256^2 faces, 8 levels, 1024 spp + SH9) through datum_ibl_bake_probes — the
+    probe-batched launches — against the ORACLE (not only against single calls): prefilter rows of the two big
+    levels, the small levels completely, and the SH9 coefficients."""
+    w, levels, samples = 256, 8, 1024
+    offs = datum_b200.level_offsets(w, w, levels)
+    payloads = [synth.synthetic_chain(w, w, levels, probe=p, sun=False) for p in (70, 71, 72)]
+    sources = [b.copy() for b in payloads]
+    sh = ctx.bake_probes(w, w, levels, payloads, samples, sh9=True)
+    for k in (0, 2):
+        got = payloads[k]
+        assert np.array_equal(got[: offs[1]], sources[k][: offs[1]])
+        for level in range(1, levels):
+            ws = w >> (level - 1)
+            hd = ws >> 1
+            for a, b in (spot_ranges(hd, rows=2) if level <= 2 else [(0, 6 * hd)]):
+                parity.check_level(got[offs[level]:offs[level + 1]], None, got[offs[level - 1]:offs[level]], ws, ws, level, levels, samples, a, b)
+        want = oracle_lib.project_sh9(sources[k][: offs[1]], datum_b200.FORMAT_RGBE, w, w)
+        assert np.abs(sh[k] - want).max() <= 1e-4 * np.abs(want).max()
+
+
 def test_hdr_sun_input_stays_within_tolerance(ctx):
     """A 2e4 sun disc next to 0.1-level sky: the ill-conditioned case."""
     w, levels = 128, 8

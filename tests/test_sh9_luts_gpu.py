@@ -83,6 +83,62 @@ def test_sh9_large_faces_keep_their_precision(ctx):
     assert np.abs(sh[1:]).max() <= 1e-4 * sh[0].max()
 
 
+def oracle_sh9_partial_threads(cube, w, row_begin, row_end, threads=8):
+    """fp64 oracle partial sums of rows [row_begin, row_end), row chunks on host threads."""
+    import threading
+    chunks = np.linspace(row_begin, row_end, threads + 1).astype(int)
+    parts = [None] * threads
+
+    def work(i):
+        parts[i] = oracle_lib.sh9_partial(cube, FORMAT_F32, w, w, int(chunks[i]), int(chunks[i + 1]))
+
+    pool = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in pool:
+        t.start()
+    for t in pool:
+        t.join()
+    return np.sum(parts, axis=0)
+
+
+def test_sh9_noise_cube_at_2048_and_its_eight_row_slabs_against_the_oracle(ctx):
+    """BASELINE config 5's shape (big RGBA32F faces, rows split over 8 GPUs) with per-texel noise over 6 stops
+    — the mirror-indexed solid-angle table and the row-segment addressing at a size where they matter —
+    against the fp64 oracle: the whole cube, and each of the eight slabs a GPU would own."""
+    w = 2048
+    rng = np.random.default_rng(55)
+    cube = np.ones((6, w, w, 4), np.float32)
+    cube[..., :3] = rng.random((6, w, w, 3), dtype=np.float32) * np.exp2(6 * rng.random((6, w, w, 1), dtype=np.float32) - 3)
+    cube[2, 100:140, 300:360, :3] += 3000.0                                # a bright patch off-centre on one face
+    d = torch.from_numpy(cube).to(DEV)
+    out = torch.zeros(9, 28, dtype=torch.float64, device=DEV)
+    ctx.sh9_partial_device(d, FORMAT_F32, w, w, 0, 6 * w, out[8])
+    rows = 6 * w // 8
+    for r in range(8):
+        ctx.sh9_partial_device(d, FORMAT_F32, w, w, r * rows, (r + 1) * rows, out[r])
+    ctx.synchronize()
+    p = out.cpu().numpy()
+    want_full = oracle_sh9_partial_threads(cube, w, 0, 6 * w)
+    scale = np.abs(want_full[:27]).max()
+    assert np.abs(p[8] - want_full).max() <= TOL_SH * scale
+    for r in (0, 3, 7):
+        want = oracle_sh9_partial_threads(cube, w, r * rows, (r + 1) * rows)
+        assert np.abs(p[r] - want).max() <= TOL_SH * np.abs(want[:27]).max(), r
+    assert np.abs(p[:8].sum(axis=0) - want_full).max() <= TOL_SH * scale
+    assert sh_error(ctx.sh9_finish(p[:8].sum(axis=0)), oracle_lib.sh9_finish(want_full)) <= TOL_SH
+
+
+def test_envbrdf_lut_at_the_shipped_size(ctx):
+    """tools/assetbuilder.cpp:496-503 bakes the env-BRDF LUT at 256 x 256 (ibl.cpp:292-308): that size, straight
+    through the C ABI, against the oracle's words and pre-quantisation values."""
+    want_words, want_f32 = oracle_lib.pack_envbrdf(256, 256, 1024)
+    got = np.zeros(256 * 256, np.uint32)
+    ctx.image_pack_envbrdf(256, 256, got)
+    dec = oracle_lib.rgbe_decode_array(got)[:, :3]
+    assert oracle_lib.relative_error(dec, want_f32).max() <= 4e-3          # one 9-bit mantissa code
+    stats = oracle_lib.word_stats(got, want_words)
+    assert oracle_lib.words_within_one_code(stats, 0.98), stats
+
+
 def test_irradiance_cube_matches_the_oracle(ctx):
     w = 32
     cube = synth.synthetic_cube(64, 64, probe=23, sun=False)
