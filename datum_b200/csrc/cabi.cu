@@ -285,6 +285,13 @@ namespace
     unsigned int *arrive[ibl::kMaxPeers] = {};   // null: no signal from the kernel
   };
 
+  // the same level of several chains in one launch (datum_ibl_bake_probes): chains `stride` words apart
+  struct Batch
+  {
+    int probes = 1;
+    size_t stride = 0;
+  };
+
   int fill_signal(datum_ibl_ctx *ctx, PeerTargets const &peers, ibl::PeerSignal &signal)
   {
     signal = ibl::PeerSignal();
@@ -308,18 +315,19 @@ namespace
   }
 
   // slabs of more than kTailTexels texels of a level at least a tile wide: denormal-mantissa kernels (prefilter_dn.cu)
-  int run_level_dn(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant, PeerTargets const &peers)
+  int run_level_dn(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant, PeerTargets const &peers, Batch const &batch)
   {
     int wd = ws >> 1, hd = hs >> 1;
 
-    cudaError_t err = ctx->records.reserve((size_t)6 * ws * hs);
+    cudaError_t err = ctx->records.reserve((size_t)6 * ws * hs * batch.probes);
     if (err == cudaSuccess)
       err = ctx->queue_heads.reserve((size_t)ctx->sm_count + 1);
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(quad records)", err);
 
     size_t partial_floats = 0, done_ints = 0;
-    ibl::prefilter_split_scratch(row_end - row_begin, wd, ctx->sm_count, &partial_floats, &done_ints);
+    if (ctx->prefilter_parts_all > 1 || ctx->prefilter_parts_pool > 1)       // sample-split tiles are an option (A/B), off by default
+      ibl::prefilter_split_scratch((row_end - row_begin) * batch.probes, wd, ctx->sm_count, &partial_floats, &done_ints);
     err = ctx->split_partials.reserve(partial_floats);
     if (err == cudaSuccess && done_ints > ctx->split_done.capacity)
     {
@@ -330,14 +338,17 @@ namespace
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(split scratch)", err);
 
-    err = ibl::launch_build_dn_records(d_src, ctx->records.ptr, ws, hs, ctx->queue_heads.ptr, ctx->sm_count + 1, ctx->sm_count, ctx->stream);
+    err = ibl::launch_build_dn_records(d_src, ctx->records.ptr, ws, hs, batch.probes, batch.stride, ctx->queue_heads.ptr, ctx->sm_count + 1, ctx->sm_count, ctx->stream);
     if (err != cudaSuccess)
       return fail_cuda("build_dn_records", err);
     ctx->launches += 1;
 
     ibl::PrefilterDnParams p = {};
-    p.partials = ctx->split_partials.ptr;
-    p.tile_done = ctx->split_done.ptr;
+    p.partials = partial_floats ? ctx->split_partials.ptr : nullptr;
+    p.tile_done = done_ints ? ctx->split_done.ptr : nullptr;
+    p.probes = batch.probes;
+    p.record_stride = (size_t)6 * ws * hs;
+    p.dst_stride = batch.stride;
     p.parts_all = ctx->prefilter_parts_all;
     p.parts_pool = ctx->prefilter_parts_pool;
     p.no_steal = ctx->prefilter_no_steal;
@@ -363,9 +374,10 @@ namespace
       p.quats[f] = ctx->quats[f];
     ibl::dn_channel_norms(table.total_weight, p.norm);
     p.exp_mul = 0x00800000u;
+    p.red_mul = 512u;
     p.counters = ctx->queue_heads.ptr;
 
-    int slot = record_dominant ? begin_dominant(ctx, (double)(row_end - row_begin) * wd * (double)table.samples) : -1;
+    int slot = record_dominant ? begin_dominant(ctx, (double)(row_end - row_begin) * wd * (double)table.samples * batch.probes) : -1;
 
     err = ibl::launch_prefilter_dn(p, ctx->prefilter_variant >= 50 ? ctx->prefilter_variant : 0, ctx->sm_count, ctx->stream, nullptr);
     if (err != cudaSuccess)
@@ -379,7 +391,7 @@ namespace
   }
 
   // one level on the context's stream: records of the source level, then the prefilter slab
-  int run_level(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant = false, PeerTargets const &peers = PeerTargets())
+  int run_level(datum_ibl_ctx *ctx, uint32_t const *d_src, int ws, int hs, DeviceTable const &table, int row_begin, int row_end, uint32_t *d_dst_words, float *d_dst_f32, bool record_dominant = false, PeerTargets const &peers = PeerTargets(), Batch const &batch = Batch())
   {
     int wd = ws >> 1, hd = hs >> 1;
 
@@ -418,8 +430,11 @@ namespace
         p.quats[f] = ctx->quats[f];
       ibl::dn_channel_norms(table.total_weight, p.norm);
       p.exp_mul = 0x00800000u;
+      p.probes = batch.probes;
+      p.src_stride = batch.stride;
+      p.dst_stride = batch.stride;
 
-      int slot = record_dominant ? begin_dominant(ctx, (double)(row_end - row_begin) * wd * (double)table.samples) : -1;
+      int slot = record_dominant ? begin_dominant(ctx, (double)(row_end - row_begin) * wd * (double)table.samples * batch.probes) : -1;
 
       cudaError_t err = ibl::launch_prefilter_tail(p, ctx->sm_count, ctx->stream);
       if (err != cudaSuccess)
@@ -433,12 +448,12 @@ namespace
     }
 
     if (ctx->prefilter_variant == 0 || ctx->prefilter_variant >= 50)
-      return run_level_dn(ctx, d_src, ws, hs, table, row_begin, row_end, d_dst_words, d_dst_f32, record_dominant, peers);
+      return run_level_dn(ctx, d_src, ws, hs, table, row_begin, row_end, d_dst_words, d_dst_f32, record_dominant, peers, batch);
 
 #ifdef DATUM_IBL_AB_VARIANTS
     // 10..27 pin a kernel of tools/ab/prefilter.cu (the tools build only, A/B timing)
-    if (peers.count > 0)
-      return fail("prefilter: the A/B kernels do not store to peers");
+    if (peers.count > 0 || batch.probes > 1)
+      return fail("prefilter: the A/B kernels do not store to peers or take batches");
 
     cudaError_t err = ctx->records.reserve((size_t)6 * ws * hs);
     if (err != cudaSuccess)
@@ -663,6 +678,67 @@ namespace
     ctx->timed = true;
 
     return 0;
+  }
+}
+
+namespace
+{
+  // tools/ibl.cpp:247-278 for `probes` chains `stride` words apart, level by level: one record pass and one
+  // prefilter launch per level for the whole group
+  int run_chain_batch(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, uint32_t *d_base, int probes, size_t stride)
+  {
+    std::vector<DeviceTable> *tables = nullptr;
+    if (get_tables(ctx, levels, samples, &tables))
+      return 1;
+
+    Batch batch;
+    batch.probes = probes;
+    batch.stride = stride;
+
+    cudaEventRecord(ctx->ev_begin, ctx->stream);
+
+    uint32_t *src = d_base;
+    uint32_t *dst = src + (size_t)width * height * 6;
+
+    for(int level = 1; level < levels; ++level)
+    {
+      int hd = height >> 1;
+
+      if (run_level(ctx, src, width, height, (*tables)[level], 0, 6 * hd, dst, nullptr, level == 1, PeerTargets(), batch))
+        return 1;
+
+      src += (size_t)width * height * 6;
+      dst += (size_t)(width >> 1) * hd * 6;
+      width /= 2;
+      height /= 2;
+    }
+
+    cudaEventRecord(ctx->ev_end, ctx->stream);
+    ctx->timed = true;
+
+    return 0;
+  }
+
+  // How many probes of a batch share a launch.  Probes of C2's size fill the machine by themselves (and
+  // their per-level downloads overlap the next level); smaller ones leave the level-1 grid a few waves
+  // deep and the last levels launch-bound, so they are baked 4 to 16 at a time.
+  int batch_group(int width, int height, int levels, int count)
+  {
+    long long level0 = 6ll * width * height;
+    long long group = (4ll * 6 * 512 * 512) / (level0 > 0 ? level0 : 1);
+    if (group > 16)
+      group = 16;
+    if (group > count)
+      group = count;
+    if (group < 2)
+      return 1;
+
+    // every level must be able to run on the kernels that take batches
+    for(int level = 1; level < levels; ++level)
+      if (!ibl::prefilter_batchable(width >> (level - 1), height >> (level - 1)))
+        return 1;
+
+    return (int)group;
   }
 }
 
@@ -933,9 +1009,11 @@ extern "C"
     size_t words = datum_ibl_chain_bytes(width, height, levels) / sizeof(uint32_t);
     size_t level0 = (size_t)width * height * 6;
 
-    cudaError_t err = ctx->chain.reserve(words);
-    if (err == cudaSuccess && count > 1)
-      err = ctx->chain2.reserve(words);
+    const int group = batch_group(width, height, levels, count);
+
+    cudaError_t err = ctx->chain.reserve(words * group);
+    if (err == cudaSuccess && count > group)
+      err = ctx->chain2.reserve(words * group);
     if (err == cudaSuccess && sh)
       err = ctx->batch_sh.reserve((size_t)count * 28);
     if (err != cudaSuccess)
@@ -960,16 +1038,17 @@ extern "C"
       return status;
     };
 
-    for(int i = 0; i < count; ++i)
+    for(int first = 0, g = 0; first < count; first += group, ++g)
     {
-      int k = i & 1;
-      uint32_t *d_bits = slots[k];
+      int k = g & 1;
+      int n = std::min(group, count - first);
+      uint32_t *d_base = slots[k];
 
-      // upload i waits until download i-2 has drained this payload
-      if (i >= 2)
+      // the uploads of group g wait until the downloads of group g-2 have drained these payloads
+      if (g >= 2)
         err = cudaStreamWaitEvent(ctx->copy_in, ctx->ev_downloaded[k], 0);
-      if (err == cudaSuccess)
-        err = cudaMemcpyAsync(d_bits, bits[i], level0 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_in);
+      for(int j = 0; j < n && err == cudaSuccess; ++j)
+        err = cudaMemcpyAsync(d_base + (size_t)j * words, bits[first + j], level0 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_in);
       if (err == cudaSuccess)
         err = cudaEventRecord(ctx->ev_uploaded[k], ctx->copy_in);
       if (err == cudaSuccess)
@@ -978,16 +1057,34 @@ extern "C"
         return drain(fail_cuda("datum_ibl_bake_probes: upload", err));
 
       // the projection reads level 0 only: it runs behind the upload on the upload stream, under the
-      // prefilter kernels of the previous probe; the next upload into this payload queues behind it
-      if (sh && sh9_partial_on(ctx, ctx->copy_in, d_bits, DATUM_IBL_FORMAT_RGBE, width, height, 0, 6 * height, ctx->batch_sh.ptr + (size_t)i * 28))
-        return drain(1);
+      // prefilter kernels of the previous group; the next upload into these payloads queues behind it
+      for(int j = 0; sh && j < n; ++j)
+        if (sh9_partial_on(ctx, ctx->copy_in, d_base + (size_t)j * words, DATUM_IBL_FORMAT_RGBE, width, height, 0, 6 * height, ctx->batch_sh.ptr + (size_t)(first + j) * 28))
+          return drain(1);
 
-      if (run_chain(ctx, width, height, levels, samples, d_bits, nullptr, (uint32_t*)bits[i]))
-        return drain(1);
+      if (group == 1)
+      {
+        // one probe per launch: every level goes home as soon as it is complete, under the next level's kernels
+        if (run_chain(ctx, width, height, levels, samples, d_base, nullptr, (uint32_t*)bits[first]))
+          return drain(1);
+      }
+      else
+      {
+        // level L of the whole group in one launch; the group's levels go home behind its last level,
+        // under the kernels of the next group
+        if (run_chain_batch(ctx, width, height, levels, samples, d_base, n, words))
+          return drain(1);
 
-      err = cudaEventRecord(ctx->ev_computed[k], ctx->stream);
-      if (err == cudaSuccess)
-        err = cudaEventRecord(ctx->ev_downloaded[k], ctx->copy_out);
+        err = cudaEventRecord(ctx->ev_computed[k], ctx->stream);
+        if (err == cudaSuccess)
+          err = cudaStreamWaitEvent(ctx->copy_out, ctx->ev_computed[k], 0);
+        for(int j = 0; j < n && err == cudaSuccess && words > level0; ++j)
+          err = cudaMemcpyAsync((uint32_t*)bits[first + j] + level0, d_base + (size_t)j * words + level0, (words - level0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_out);
+        if (err != cudaSuccess)
+          return drain(fail_cuda("datum_ibl_bake_probes: download", err));
+      }
+
+      err = cudaEventRecord(ctx->ev_downloaded[k], ctx->copy_out);
       if (err != cudaSuccess)
         return drain(fail_cuda("datum_ibl_bake_probes: download", err));
     }

@@ -60,6 +60,7 @@ namespace ibl
     Quatf quats[6];           // face rotations, tools/ibl.cpp:253-261
     float norm[3];            // per channel: sum -> radiance / total weight (dn_channel_norms)
     uint32_t exp_mul;         // 2^23 (a parameter on purpose, see scale_by_exponent)
+    uint32_t red_mul;         // 2^9 (A/B: r mantissa as the high half of word * 2^9)
     int *counters;            // queues+1 tile queue heads, zeroed by launch_build_dn_records
     int blocks_x, tiles;      // filled by the launcher: 4x4-blocked tile numbering
     int queues, chunk, queued;
@@ -70,6 +71,11 @@ namespace ibl
     // ticket (`tile_done`, zero between launches) adds them in unit order and writes the texels.
     // Quarter tiles at the end of a launch, or for a slab that would not fill the machine, cut the idle
     // tail of the last wave to a quarter.  Filled by the launcher from parts_all / parts_pool (0 = automatic).
+    // the same level of `probes` chains in one launch (datum_ibl_bake_probes): records of the probes back
+    // to back (record_stride each), destination levels dst_stride words apart
+    int probes, tiles_per_probe;
+    size_t record_stride, dst_stride;
+
     int parts, units;
     int parts_all, parts_pool;
     int no_steal;             // A/B: a group whose chunk and pool are empty leaves instead of helping other SMs
@@ -100,6 +106,8 @@ namespace ibl
     Quatf quats[6];
     float norm[3];
     uint32_t exp_mul;
+    int probes, texels_per_probe;     // the same level of several chains in one launch
+    size_t src_stride, dst_stride;    // words between the probes' source / destination levels
   };
 
   // slabs up to this many texels go to the tail kernel
@@ -115,7 +123,10 @@ namespace ibl
   cudaError_t launch_peer_signal(PeerSignal const &s, cudaStream_t stream);
 
   // also zeroes the `ncounters` tile queue heads for the prefilter launch that follows
-  cudaError_t launch_build_dn_records(uint32_t const *src, uint4 *rec, int ws, int hs, int *counters, int ncounters, int sm_count, cudaStream_t stream);
+  cudaError_t launch_build_dn_records(uint32_t const *src, uint4 *rec, int ws, int hs, int probes, size_t src_stride, int *counters, int ncounters, int sm_count, cudaStream_t stream);
+
+  // can the same level of several probes go into one launch (pair kernel usable for a ws x hs source)?
+  bool prefilter_batchable(int ws, int hs);
 
 #ifdef DATUM_IBL_AB_VARIANTS
   // variant 0 = pick by slab size; 1..15 = fixed <tile width, texels per lane, warps per tile>

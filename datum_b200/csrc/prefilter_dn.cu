@@ -69,6 +69,18 @@ namespace ibl
     return u2f(r + f2u(w));
   }
 
+  // r mantissa = word >> 23: a shift on the ALU pipe, or (A/B) the high half of word * 2^9 on the FMA pipe
+  template<bool HI>
+  __device__ __forceinline__ float red_field(uint32_t word, uint32_t rmul)
+  {
+    if (!HI)
+      return u2f(word >> 23);
+
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(word), "r"(rmul));
+    return u2f(r);
+  }
+
   template<bool ALU>
   __device__ __forceinline__ float scale_tap(float w, uint32_t word, uint32_t emul)
   {
@@ -77,26 +89,30 @@ namespace ibl
 
   // ---- quad records ----------------------------------------------------------------
 
-  __global__ void __launch_bounds__(256) build_dn_records_kernel(uint32_t const *__restrict__ src, uint4 *__restrict__ rec, int ws, int hs, int *__restrict__ counters, int ncounters)
+  __global__ void __launch_bounds__(256) build_dn_records_kernel(uint32_t const *__restrict__ src, uint4 *__restrict__ rec, int ws, int hs, int probes, size_t src_stride, int *__restrict__ counters, int ncounters)
   {
     // the prefilter launch that follows on the stream takes its tiles from these queues
     if (blockIdx.x == 0)
       for(int i = threadIdx.x; i < ncounters; i += blockDim.x)
         counters[i] = 0;
 
-    size_t total = (size_t)6 * ws * hs;
+    // `probes` source levels `src_stride` words apart (a batch of chains), their records back to back
+    size_t level = (size_t)6 * ws * hs, total = level * probes;
     for(size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
     {
-      int i = (int)(idx % ws);
-      int j = (int)((idx / ws) % hs);
+      size_t probe = idx / level, local = idx - probe * level;
+      int i = (int)(local % ws);
+      int j = (int)((local / ws) % hs);
       size_t right = (i + 1 < ws) ? 1 : 0;      // neighbours clamped inside the face; the clamped
       size_t down = (j + 1 < hs) ? (size_t)ws : 0; // ones are never addressed (i <= ws-2, j <= hs-2)
 
+      uint32_t const *t = src + probe * src_stride + local;
+
       uint4 r;
-      r.x = pack_dn_word(__ldg(src + idx));
-      r.y = pack_dn_word(__ldg(src + idx + right));
-      r.z = pack_dn_word(__ldg(src + idx + down));
-      r.w = pack_dn_word(__ldg(src + idx + down + right));
+      r.x = pack_dn_word(__ldg(t));
+      r.y = pack_dn_word(__ldg(t + right));
+      r.z = pack_dn_word(__ldg(t + down));
+      r.w = pack_dn_word(__ldg(t + down + right));
       rec[idx] = r;
     }
   }
@@ -563,7 +579,7 @@ namespace ibl
   }
 
   // (fu, fv) of both samples -> records, weights, taps.  EXP_ALU of the four taps of a sample take their exponent on the ALU pipe.  `base` holds the bias (and the face on the same-face path).
-  template<int EXP_ALU>
+  template<int EXP_ALU, bool RHI>
   __device__ __forceinline__ void gather_pair(PrefilterDnParams const &p, uint4 const *base, uint32_t off_a, uint32_t off_b, f32x2 fu, f32x2 fv, PairEntry const &e, Sums &acc)
   {
     f32x2 mu = add2(fu, bcast2(kMagic));
@@ -602,14 +618,14 @@ namespace ibl
     w01b = scale_tap<(EXP_ALU > 1)>(w01b, rb.z, emul);
     w11b = scale_tap<(EXP_ALU > 3)>(w11b, rb.w, emul);
 
-    acc.rg = fma2(pack2(u2f(ra.x >> 23), u2f(ra.x & kDnMaskG)), bcast2(w00a), acc.rg);
-    acc.rg = fma2(pack2(u2f(ra.y >> 23), u2f(ra.y & kDnMaskG)), bcast2(w10a), acc.rg);
-    acc.rg = fma2(pack2(u2f(ra.z >> 23), u2f(ra.z & kDnMaskG)), bcast2(w01a), acc.rg);
-    acc.rg = fma2(pack2(u2f(ra.w >> 23), u2f(ra.w & kDnMaskG)), bcast2(w11a), acc.rg);
-    acc.rg = fma2(pack2(u2f(rb.x >> 23), u2f(rb.x & kDnMaskG)), bcast2(w00b), acc.rg);
-    acc.rg = fma2(pack2(u2f(rb.y >> 23), u2f(rb.y & kDnMaskG)), bcast2(w10b), acc.rg);
-    acc.rg = fma2(pack2(u2f(rb.z >> 23), u2f(rb.z & kDnMaskG)), bcast2(w01b), acc.rg);
-    acc.rg = fma2(pack2(u2f(rb.w >> 23), u2f(rb.w & kDnMaskG)), bcast2(w11b), acc.rg);
+    acc.rg = fma2(pack2(red_field<RHI>(ra.x, p.red_mul), u2f(ra.x & kDnMaskG)), bcast2(w00a), acc.rg);
+    acc.rg = fma2(pack2(red_field<RHI>(ra.y, p.red_mul), u2f(ra.y & kDnMaskG)), bcast2(w10a), acc.rg);
+    acc.rg = fma2(pack2(red_field<RHI>(ra.z, p.red_mul), u2f(ra.z & kDnMaskG)), bcast2(w01a), acc.rg);
+    acc.rg = fma2(pack2(red_field<RHI>(ra.w, p.red_mul), u2f(ra.w & kDnMaskG)), bcast2(w11a), acc.rg);
+    acc.rg = fma2(pack2(red_field<RHI>(rb.x, p.red_mul), u2f(rb.x & kDnMaskG)), bcast2(w00b), acc.rg);
+    acc.rg = fma2(pack2(red_field<RHI>(rb.y, p.red_mul), u2f(rb.y & kDnMaskG)), bcast2(w10b), acc.rg);
+    acc.rg = fma2(pack2(red_field<RHI>(rb.z, p.red_mul), u2f(rb.z & kDnMaskG)), bcast2(w01b), acc.rg);
+    acc.rg = fma2(pack2(red_field<RHI>(rb.w, p.red_mul), u2f(rb.w & kDnMaskG)), bcast2(w11b), acc.rg);
 
     acc.bb = fma2(pack2(u2f(ra.x & kDnMaskB), u2f(rb.x & kDnMaskB)), pack2(w00a, w00b), acc.bb);
     acc.bb = fma2(pack2(u2f(ra.y & kDnMaskB), u2f(rb.y & kDnMaskB)), pack2(w10a, w10b), acc.bb);
@@ -618,7 +634,7 @@ namespace ibl
   }
 
   // frame rows in face-local (a, b, m) coordinates, a and b pre-scaled to source texels
-  template<int EXP_ALU>
+  template<int EXP_ALU, bool RHI>
   __device__ __forceinline__ void pair_same_face(PrefilterDnParams const &p, Frame const &t, uint4 const *base, PairEntry const &e, Sums &acc)
   {
     f32x2 la, lb, lm;
@@ -628,11 +644,11 @@ namespace ibl
     unpack2(lm, ma, mb);
     f32x2 r = pack2(rcp_fast(ma), rcp_fast(mb));
 
-    gather_pair<EXP_ALU>(p, base, 0u, 0u, fma2(la, r, bcast2(p.geom.hwm)), fma2(lb, r, bcast2(p.geom.hhm)), e, acc);
+    gather_pair<EXP_ALU, RHI>(p, base, 0u, 0u, fma2(la, r, bcast2(p.geom.hwm)), fma2(lb, r, bcast2(p.geom.hhm)), e, acc);
   }
 
   // frame rows in world coordinates: cube face selection of tools/ibl.cpp:43-88 per sample
-  template<int EXP_ALU>
+  template<int EXP_ALU, bool RHI>
   __device__ __forceinline__ void pair_general(PrefilterDnParams const &p, Frame const &t, uint4 const *base, PairEntry const &e, Sums &acc)
   {
     f32x2 x, y, z;
@@ -652,10 +668,10 @@ namespace ibl
     f32x2 fv = fma2(pack2(qva, qvb), bcast2(p.geom.hh), bcast2(p.geom.hhm));
 
     // the face offset goes into the 32-bit index (bias + 6 faces cannot wrap, see the launcher)
-    gather_pair<EXP_ALU>(p, base, fa * p.geom.face_size, fb * p.geom.face_size, fu, fv, e, acc);
+    gather_pair<EXP_ALU, RHI>(p, base, fa * p.geom.face_size, fb * p.geom.face_size, fu, fv, e, acc);
   }
 
-  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU, int DEPTH = 1>
+  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU, int DEPTH = 1, bool RHI = false>
   __global__ void __launch_bounds__(32 * NW, MINB) prefilter_dp_kernel(PrefilterDnParams p)
   {
     extern __shared__ float4 smem[];
@@ -722,8 +738,17 @@ namespace ibl
         parts = p.parts;
       }
 
+      // a launch may carry the same level of several probes (datum_ibl_bake_probes): tiles are numbered
+      // probe by probe, records and destination levels sit at fixed strides
+      int probe = 0, ltile = tile;
+      if (p.probes > 1)
+      {
+        probe = tile / p.tiles_per_probe;
+        ltile = tile - probe * p.tiles_per_probe;
+      }
+
       int x, row;
-      bool valid = tile_texel(p, tile, lane, x, row);
+      bool valid = tile_texel(p, ltile, lane, x, row);
 
       if (__ballot_sync(0xffffffffu, valid) == 0u)
       {
@@ -736,6 +761,8 @@ namespace ibl
 
       int face = row / p.hd;
       int y = row - face * p.hd;
+
+      uint4 const *biased_probe = opaque(biased + (size_t)probe * p.record_stride);
 
       Frame st;
       int n_same;
@@ -773,14 +800,14 @@ namespace ibl
       int band = part;
 
       {
-        uint4 const *base = opaque(biased + (size_t)face * p.geom.face_size);
+        uint4 const *base = opaque(biased_probe + (size_t)face * p.geom.face_size);
 
         #pragma unroll BAND_UNROLL
         for(; band < n_same; band += parts)
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
-            pair_same_face<EXP_ALU>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+            pair_same_face<EXP_ALU, RHI>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
         }
       }
 
@@ -796,7 +823,7 @@ namespace ibl
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
-            pair_general<EXP_ALU>(p, st, biased, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+            pair_general<EXP_ALU, RHI>(p, st, biased_probe, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
         }
       }
 
@@ -863,7 +890,7 @@ namespace ibl
         {
           // sum/totalweight of ibl.cpp:186, then rgbe() of ibl.cpp:269
           float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
-          size_t o = (size_t)row * p.wd + x;
+          size_t o = (size_t)row * p.wd + x + (size_t)probe * p.dst_stride;
 
           if (p.dst_words || p.peers > 0)
           {
@@ -910,7 +937,13 @@ namespace ibl
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    const int texel = blockIdx.x;
+    // a launch may carry the same level of several probes: texels are numbered probe by probe
+    int texel = blockIdx.x, probe = 0;
+    if (p.probes > 1)
+    {
+      probe = texel / p.texels_per_probe;
+      texel -= probe * p.texels_per_probe;
+    }
     const int row = p.row_begin + texel / p.wd;
     const int x = texel - (texel / p.wd) * p.wd;
     const int face = row / p.hd;
@@ -949,7 +982,7 @@ namespace ibl
       float w[4];
       footprint_weights(du, dv, e.w, e.z, w);
 
-      uint32_t const *t = p.src + idx;
+      uint32_t const *t = p.src + (size_t)probe * p.src_stride + idx;
       dn_accumulate_tap(pack_dn_word(__ldg(t)), w[0], acc);
       dn_accumulate_tap(pack_dn_word(__ldg(t + 1)), w[1], acc);
       dn_accumulate_tap(pack_dn_word(__ldg(t + p.geom.ws)), w[2], acc);
@@ -982,7 +1015,7 @@ namespace ibl
 
       // sum/totalweight of ibl.cpp:186, then rgbe() of ibl.cpp:269
       float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
-      size_t o = (size_t)row * p.wd + x;
+      size_t o = (size_t)row * p.wd + x + (size_t)probe * p.dst_stride;
 
       if (p.dst_words || p.peers > 0)
       {
@@ -1006,22 +1039,31 @@ namespace ibl
     signal_peers_when_last(p.signal);
   }
 
-  cudaError_t launch_prefilter_tail(PrefilterTailParams const &p, int sm_count, cudaStream_t stream)
+  cudaError_t launch_prefilter_tail(PrefilterTailParams const &params, int sm_count, cudaStream_t stream)
   {
+    PrefilterTailParams p = params;
+
     int texels = (p.row_end - p.row_begin) * p.wd;
     if (texels <= 0)
       return cudaSuccess;
 
-    // warps per texel: enough CTAs to cover the machine first, then depth; never more lanes than samples
+    if (p.probes < 1)
+      p.probes = 1;
+    p.texels_per_probe = texels;
+
+    // warps per texel: enough CTAs to cover the machine first, then depth; never more lanes than samples.
+    // Chosen from ONE probe's texels also when a launch carries several: the shape decides the order of
+    // the sums, and a batch must give the words of single calls.
     (void)sm_count;
+    int grid = texels * p.probes;
     if (texels >= 4096 || p.table_count <= 128)
-      prefilter_tail_kernel<4><<<texels, 128, 0, stream>>>(p);
+      prefilter_tail_kernel<4><<<grid, 128, 0, stream>>>(p);
     else if (texels >= 1024 || p.table_count <= 256)
-      prefilter_tail_kernel<8><<<texels, 256, 0, stream>>>(p);
+      prefilter_tail_kernel<8><<<grid, 256, 0, stream>>>(p);
     else if (texels >= 256 || p.table_count <= 512)
-      prefilter_tail_kernel<16><<<texels, 512, 0, stream>>>(p);
+      prefilter_tail_kernel<16><<<grid, 512, 0, stream>>>(p);
     else
-      prefilter_tail_kernel<32><<<texels, 1024, 0, stream>>>(p);
+      prefilter_tail_kernel<32><<<grid, 1024, 0, stream>>>(p);
 
     return cudaGetLastError();
   }
@@ -1042,16 +1084,16 @@ namespace ibl
 
   // ---- host-side launchers ---------------------------------------------------------------
 
-  cudaError_t launch_build_dn_records(uint32_t const *src, uint4 *rec, int ws, int hs, int *counters, int ncounters, int sm_count, cudaStream_t stream)
+  cudaError_t launch_build_dn_records(uint32_t const *src, uint4 *rec, int ws, int hs, int probes, size_t src_stride, int *counters, int ncounters, int sm_count, cudaStream_t stream)
   {
-    size_t total = (size_t)6 * ws * hs;
+    size_t total = (size_t)6 * ws * hs * (probes > 0 ? probes : 1);
     size_t blocks = (total + 255) / 256;
     size_t cap = (size_t)sm_count * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
     if (grid < 1)
       grid = 1;
 
-    build_dn_records_kernel<<<grid, 256, 0, stream>>>(src, rec, ws, hs, counters, ncounters);
+    build_dn_records_kernel<<<grid, 256, 0, stream>>>(src, rec, ws, hs, probes > 0 ? probes : 1, src_stride, counters, ncounters);
 
     return cudaGetLastError();
   }
@@ -1142,15 +1184,18 @@ namespace ibl
 
   namespace
   {
-    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0, int DEPTH = 1>
+    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0, int DEPTH = 1, bool RHI = false>
     cudaError_t launch_dp(PrefilterDnParams p, int sm_count, cudaStream_t stream, int *launched_grid)
     {
-      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU, DEPTH>;
+      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU, DEPTH, RHI>;
 
       int rows = p.row_end - p.row_begin;
       int tiles_x = (p.wd + 7) / 8, tiles_y = (rows + 3) / 4;
       p.blocks_x = (tiles_x + 3) / 4;
-      p.tiles = p.blocks_x * ((tiles_y + 3) / 4) * 16;
+      p.tiles_per_probe = p.blocks_x * ((tiles_y + 3) / 4) * 16;
+      if (p.probes < 1)
+        p.probes = 1;
+      p.tiles = p.tiles_per_probe * p.probes;
 
       size_t smem = (SMEM_TABLE ? (size_t)p.bands * kSampleBand * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
 
@@ -1224,6 +1269,14 @@ namespace ibl
     *done_ints = split;
   }
 
+  bool prefilter_batchable(int ws, int hs)
+  {
+    PrefilterDnParams p = {};
+    p.geom = make_level_geom(ws, hs);
+    p.table_pairs = reinterpret_cast<float4 const*>(&p);     // any non-null value: only the geometry decides
+    return pair_kernel_usable(p);
+  }
+
   cudaError_t launch_prefilter_dn(PrefilterDnParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid)
   {
     int rows = p.row_end - p.row_begin;
@@ -1240,11 +1293,18 @@ namespace ibl
       // the two biggest classes work on two samples at a time (prefilter_dp_kernel; measured on C2:
       // level 1 885 -> 862 us, level 2 277 -> 262, level 3 96 -> 88); launch_prefilter_dn falls back to
       // the one-sample kernel when the biased record index could wrap
+      // Warps per tile follow ONE probe's slab (they decide the order of the sums: a batch must give the
+      // words of single calls), the tile queues follow the whole launch.
       if (texels >= kQueuedTexels)
         variant = big_table ? 71 : 70;
+      else if (texels * (size_t)(p.probes > 1 ? p.probes : 1) >= kQueuedTexels)
+        variant = big_table ? 91 : 90;
       else
         variant = big_table ? 73 : 72;      // slabs of at most kTailTexels never get here (prefilter_tail_kernel)
     }
+
+    if (p.probes > 1 && !(variant >= 70 && variant <= 99 && pair_kernel_usable(p)))
+      return cudaErrorNotSupported;         // batches run on the pair kernel only (the caller checks prefilter_batchable)
 
     // two samples at a time; when the biased index could wrap, the same shape one sample at a time
     if (variant >= 81 && variant <= 86 && !pair_kernel_usable(p))
@@ -1264,6 +1324,8 @@ namespace ibl
       case 71: return launch_dp<4, 8, false, true>(p, sm_count, stream, launched_grid);
       case 72: return launch_dp<8, 4, true, false>(p, sm_count, stream, launched_grid);
       case 73: return launch_dp<8, 4, false, false>(p, sm_count, stream, launched_grid);
+      case 90: return launch_dp<8, 4, true, true>(p, sm_count, stream, launched_grid);     // several probes' small slabs in one launch
+      case 91: return launch_dp<8, 4, false, true>(p, sm_count, stream, launched_grid);
       //                        NW UNR MINB SMEM  QUEUES
       case 51: return launch_dn<4, 4, 8, true, true>(p, sm_count, stream, launched_grid);
       case 52: return launch_dn<4, 4, 8, false, true>(p, sm_count, stream, launched_grid);
@@ -1273,6 +1335,8 @@ namespace ibl
 #ifdef DATUM_IBL_AB_VARIANTS
       // A/B shapes of the tuning history (profiles/): only in the tools build (datum_b200.build --ab)
       case 74: return launch_dp<4, 8, true, false>(p, sm_count, stream, launched_grid);
+      case 87: return launch_dp<4, 8, true, true, 0, 1, true>(p, sm_count, stream, launched_grid);    // r mantissa through IMAD.HI
+      case 88: return launch_dp<8, 4, true, false, 0, 1, true>(p, sm_count, stream, launched_grid);
       case 75: return launch_dp<4, 8, true, true, 1>(p, sm_count, stream, launched_grid);
       case 76: return launch_dp<4, 8, true, true, 2>(p, sm_count, stream, launched_grid);
       case 77: return launch_dp<4, 8, true, true, 3>(p, sm_count, stream, launched_grid);
