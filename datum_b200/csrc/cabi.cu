@@ -124,9 +124,6 @@ struct datum_ibl_ctx
   cudaEvent_t ev_level[16] = {};  // level L of the current chain is complete (its download starts behind it)
   DeviceBuffer<uint4> records;    // quad records of the current source level
   DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
-  DeviceBuffer<float> split_partials; // partial sums of sample-split tiles (prefilter_dn.cu)
-  DeviceBuffer<int> split_done;       // their per-tile tickets, zero between launches
-  int prefilter_parts_all = 0, prefilter_parts_pool = 0;   // 0 = automatic
   int prefilter_no_steal = 0;
   int sh9_kernel = 0, sh9_rows_per_item = 0;   // A/B: 0 = column strips / automatic run length
   DeviceBuffer<unsigned int> peer_ticket; // "CTAs done" counter of launches that signal peers, zero between launches
@@ -325,32 +322,15 @@ namespace
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(quad records)", err);
 
-    size_t partial_floats = 0, done_ints = 0;
-    if (ctx->prefilter_parts_all > 1 || ctx->prefilter_parts_pool > 1)       // sample-split tiles are an option (A/B), off by default
-      ibl::prefilter_split_scratch((row_end - row_begin) * batch.probes, wd, ctx->sm_count, &partial_floats, &done_ints);
-    err = ctx->split_partials.reserve(partial_floats);
-    if (err == cudaSuccess && done_ints > ctx->split_done.capacity)
-    {
-      err = ctx->split_done.reserve(done_ints);
-      if (err == cudaSuccess)
-        err = cudaMemsetAsync(ctx->split_done.ptr, 0, ctx->split_done.capacity * sizeof(int), ctx->stream);   // the kernel leaves them at zero
-    }
-    if (err != cudaSuccess)
-      return fail_cuda("cudaMalloc(split scratch)", err);
-
     err = ibl::launch_build_dn_records(d_src, ctx->records.ptr, ws, hs, batch.probes, batch.stride, ctx->queue_heads.ptr, ctx->sm_count + 1, ctx->sm_count, ctx->stream);
     if (err != cudaSuccess)
       return fail_cuda("build_dn_records", err);
     ctx->launches += 1;
 
     ibl::PrefilterDnParams p = {};
-    p.partials = partial_floats ? ctx->split_partials.ptr : nullptr;
-    p.tile_done = done_ints ? ctx->split_done.ptr : nullptr;
     p.probes = batch.probes;
     p.record_stride = (size_t)6 * ws * hs;
     p.dst_stride = batch.stride;
-    p.parts_all = ctx->prefilter_parts_all;
-    p.parts_pool = ctx->prefilter_parts_pool;
     p.no_steal = ctx->prefilter_no_steal;
     p.records = ctx->records.ptr;
     p.table = table.d_banded;
@@ -832,8 +812,6 @@ extern "C"
       if (ctx->ev_level[k]) cudaEventDestroy(ctx->ev_level[k]);
     ctx->records.release();
     ctx->queue_heads.release();
-    ctx->split_partials.release();
-    ctx->split_done.release();
     ctx->peer_ticket.release();
     ctx->sh_weights.release();
     ctx->sh_partials.release();
@@ -905,14 +883,11 @@ extern "C"
 
   int datum_ibl_set_prefilter_variant(datum_ibl_ctx *ctx, int variant)
   {
-    // kernel shape + 100 * (shares per tile of a slab too small for the tile queues) + 1000 * (shares per tile
-    // of the pool behind the queues) + 10000 * (no tile stealing, A/B); 0 in a field = automatic
-    if (!ctx || variant < 0 || variant > 19999)
+    // kernel shape + 10000 * (no tile stealing, A/B); 0 = automatic
+    if (!ctx || variant < 0 || variant > 19999 || (variant % 10000) > 99)
       return fail("datum_ibl_set_prefilter_variant: bad argument");
 
     ctx->prefilter_variant = variant % 100;
-    ctx->prefilter_parts_all = (variant / 100) % 10;
-    ctx->prefilter_parts_pool = (variant / 1000) % 10;
     ctx->prefilter_no_steal = variant / 10000;
     return 0;
   }

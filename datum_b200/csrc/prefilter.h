@@ -65,26 +65,13 @@ namespace ibl
     int blocks_x, tiles;      // filled by the launcher: 4x4-blocked tile numbering
     int queues, chunk, queued;
 
-    // Sample-split tiles (pair kernel).  A work unit below `queued` is a whole tile; from there on
-    // `parts` consecutive units share one tile, unit k taking bands k, k + parts, ... of the table.  Their
-    // partial sums meet in `partials` (96 floats per unit), the unit that arrives last at the tile's
-    // ticket (`tile_done`, zero between launches) adds them in unit order and writes the texels.
-    // Quarter tiles at the end of a launch, or for a slab that would not fill the machine, cut the idle
-    // tail of the last wave to a quarter.  Filled by the launcher from parts_all / parts_pool (0 = automatic).
     // the same level of `probes` chains in one launch (datum_ibl_bake_probes): records of the probes back
     // to back (record_stride each), destination levels dst_stride words apart
     int probes, tiles_per_probe;
     size_t record_stride, dst_stride;
 
-    int parts, units;
-    int parts_all, parts_pool;
     int no_steal;             // A/B: a group whose chunk and pool are empty leaves instead of helping other SMs
-    float *partials;
-    int *tile_done;
   };
-
-  // scratch the sample-split needs for a slab: floats of `partials`, ints of `tile_done`
-  void prefilter_split_scratch(int rows, int wd, int sm_count, size_t *partial_floats, size_t *done_ints);
 
   // ---- tail levels (prefilter_dn.cu, prefilter_tail_kernel): a few hundred texels ----
   //

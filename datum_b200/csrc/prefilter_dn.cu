@@ -248,7 +248,7 @@ namespace ibl
       else
       {
         int u = p.queued + atomicAdd(p.counters + p.queues, 1);
-        if (u < p.units)
+        if (u < p.tiles)
           unit = u;
       }
     }
@@ -706,7 +706,7 @@ namespace ibl
 
     for(int it = 0; ; ++it)
     {
-      int unit;
+      int tile;
       if (QUEUES)
       {
         if (warp == 0)
@@ -716,27 +716,17 @@ namespace ibl
             *s_tile = next;
         }
         __syncthreads();
-        unit = *s_tile;
+        tile = *s_tile;
       }
       else
       {
-        unit = (int)blockIdx.x + it * (int)gridDim.x;
-        if (unit >= p.units)
-          unit = -1;
+        tile = (int)blockIdx.x + it * (int)gridDim.x;
+        if (tile >= p.tiles)
+          tile = -1;
       }
 
-      if (unit < 0)
+      if (tile < 0)
         break;
-
-      // whole tile, or one of `parts` interleaved shares of a tile's bands
-      int tile = unit, part = 0, parts = 1;
-      if (unit >= p.queued)
-      {
-        int u = unit - p.queued;
-        tile = p.queued + u / p.parts;
-        part = u - (tile - p.queued) * p.parts;
-        parts = p.parts;
-      }
 
       // a launch may carry the same level of several probes (datum_ibl_bake_probes): tiles are numbered
       // probe by probe, records and destination levels sit at fixed strides
@@ -797,13 +787,13 @@ namespace ibl
       acc.bb = 0ull;
 
       float4 const *tw = table + warp * PER;   // entry index == float4 index in the pair-interleaved table
-      int band = part;
+      int band = 0;
 
       {
         uint4 const *base = opaque(biased_probe + (size_t)face * p.geom.face_size);
 
         #pragma unroll BAND_UNROLL
-        for(; band < n_same; band += parts)
+        for(; band < n_same; ++band)
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
@@ -819,7 +809,7 @@ namespace ibl
         st.N = from_face_local(face, Vec3f{ st.N.x * p.geom.inv_hw, st.N.y * p.geom.inv_hh, st.N.z });
 
         #pragma unroll BAND_UNROLL
-        for(; band < p.bands; band += parts)
+        for(; band < p.bands; ++band)
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
@@ -850,43 +840,7 @@ namespace ibl
             sum[c] += s_red[(w * 3 + c) * 32 + lane];
         }
 
-        // a share of a tile: the sums of all shares meet in global memory, the share that arrives last
-        // adds them in share order (deterministic whatever the arrival order) and finishes the texels
-        bool finish = true;
-        if (parts > 1)
-        {
-          float *mine = p.partials + (size_t)(unit - p.queued) * 96;
-          #pragma unroll
-          for(int c = 0; c < 3; ++c)
-            __stcg(mine + c * 32 + lane, sum[c]);
-
-          __threadfence();
-
-          int ticket = 0;
-          if (lane == 0)
-            ticket = atomicAdd(p.tile_done + (tile - p.queued), 1);
-          ticket = __shfl_sync(0xffffffffu, ticket, 0);
-
-          finish = ticket == parts - 1;
-          if (finish)
-          {
-            __threadfence();
-
-            float const *all = p.partials + (size_t)(tile - p.queued) * p.parts * 96;
-            sum[0] = sum[1] = sum[2] = 0.0f;
-            for(int k = 0; k < parts; ++k)
-            {
-              #pragma unroll
-              for(int c = 0; c < 3; ++c)
-                sum[c] += __ldcg(all + (k * 3 + c) * 32 + lane);
-            }
-
-            if (lane == 0)
-              p.tile_done[tile - p.queued] = 0;      // ready for the next launch on this stream
-          }
-        }
-
-        if (valid && finish)
+        if (valid)
         {
           // sum/totalweight of ibl.cpp:186, then rgbe() of ibl.cpp:269
           float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
@@ -1170,8 +1124,6 @@ namespace ibl
       p.queues = sm_count;
       p.chunk = (p.tiles - p.tiles / 8) / sm_count;
       p.queued = p.chunk * sm_count;
-      p.units = p.tiles;      // the one-sample kernel only knows whole tiles
-      p.parts = 1;
 
       kernel<<<grid, 32 * NW, smem, stream>>>(p);
 
@@ -1206,38 +1158,16 @@ namespace ibl
 
       const int slots = sm_count * resident;
 
-      p.queues = sm_count;
-
-      if (QUEUES)
-      {
-        // 7/8 of the tiles as whole tiles in per-SM chunks, then the pool that evens out the end of the
-        // launch.  Pool tiles in 2, 4 or 8 shares were measured (profiles/r2_summary.md): no gain on the
-        // 512^2 -> 256^2 level, 2 % on the next one; whole tiles stay the default.
-        p.chunk = (p.tiles - p.tiles / 8) / sm_count;
-        p.queued = p.chunk * sm_count;
-        p.parts = p.parts_pool > 0 ? p.parts_pool : 1;
-      }
-      else
-      {
-        // A slab that does not fill the machine several times over could run every tile in shares so
-        // that the last wave is short.  Measured on 768 tiles for 592 resident CTAs: 2 shares -5 %,
-        // 4 shares +11 %, 8 shares +38 % (every share repeats the tile set-up, and a half-empty SM runs
-        // its CTAs faster than a full one anyway): whole tiles unless asked otherwise.
-        p.chunk = 0;
-        p.queued = 0;
-        p.parts = p.parts_all > 0 ? p.parts_all : 1;
-      }
-
-      if (p.parts > p.bands)
-        p.parts = p.bands > 0 ? p.bands : 1;
-      if (!p.partials || !p.tile_done)
-        p.parts = 1;
-
-      p.units = p.queued + (p.tiles - p.queued) * p.parts;
-
-      int grid = p.units < slots ? p.units : slots;
+      int grid = p.tiles < slots ? p.tiles : slots;
       if (grid < 1)
         grid = 1;
+
+      // queues: 7/8 of the tiles in per-SM chunks, the rest in the common pool that evens out the end of
+      // the launch.  (Cutting the pool's tiles, or every tile of a slab too small to fill the machine,
+      // into 2-8 shares of their bands was measured and dropped: profiles/r2_summary.md.)
+      p.queues = sm_count;
+      p.chunk = (p.tiles - p.tiles / 8) / sm_count;
+      p.queued = p.chunk * sm_count;
 
       kernel<<<grid, 32 * NW, smem, stream>>>(p);
 
@@ -1254,20 +1184,8 @@ namespace ibl
     }
   }
 
-  // slabs of at least this many texels take their tiles from per-SM queues (and only split the pool)
+  // slabs of at least this many texels take their tiles from per-SM queues
   constexpr size_t kQueuedTexels = 32u * 148u * 8u;
-
-  void prefilter_split_scratch(int rows, int wd, int sm_count, size_t *partial_floats, size_t *done_ints)
-  {
-    // upper bound for any split the launchers choose: 8 shares of every tile that can be split
-    int tiles_x = (wd + 7) / 8, tiles_y = (rows + 3) / 4;
-    size_t tiles = (size_t)((tiles_x + 3) / 4) * ((tiles_y + 3) / 4) * 16;
-    size_t split = tiles;
-    if ((size_t)rows * wd >= kQueuedTexels)
-      split = tiles - ((tiles - tiles / 8) / sm_count) * sm_count;     // the pool behind the per-SM chunks
-    *partial_floats = split * 8 * 96;
-    *done_ints = split;
-  }
 
   bool prefilter_batchable(int ws, int hs)
   {
