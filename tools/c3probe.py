@@ -5,7 +5,7 @@ import numpy as np, torch, datum_b200
 from datum_b200 import synth
 ctx = datum_b200.IblContext(0)
 cases = [tuple(int(x) for x in c.split(",")) for c in os.environ.get("IBL_CASES", "256,8,1024;2048,12,4096").split(";")]
-variants = [int(v) for v in os.environ.get("IBL_VARIANTS", "0,19").split(",")]
+variants = [int(v) for v in os.environ.get("IBL_VARIANTS", "0").split(",")]
 for (w, levels, samples) in cases:
     n = sum(6 * (w >> i) ** 2 for i in range(levels))
     bits = synth.synthetic_chain(w, w, 1)
