@@ -586,7 +586,10 @@ def run_ours(args):
     job.barrier()
     t0 = time.perf_counter()
     ctx.bake_probes(w, w, levels, batch, samples)
-    e2e_batch_s = job.max_over_ranks(time.perf_counter() - t0)
+    e2e_batch_local = time.perf_counter() - t0
+    e2e_batch_s = job.max_over_ranks(e2e_batch_local)
+    if world > 1:
+        print("bench.py: rank %d e2e_batched %.3f ms per step" % (rank, e2e_batch_local * 1e3 / args.steps), file=sys.stderr, flush=True)
     job.barrier()
 
     clocks = sampler.stop()
@@ -706,7 +709,8 @@ def run_ours(args):
         try:
             configs[name] = fn()
         except Exception as exc:                      # noqa: BLE001 - reported in the JSON line
-            configs[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            configs[name] = {"error": "rank %d: %s: %s" % (rank, type(exc).__name__, exc)}
+            print("bench.py: config %s failed on rank %d: %s: %s" % (name, rank, type(exc).__name__, exc), file=sys.stderr, flush=True)
             try:
                 torch.cuda.synchronize()
             except Exception:

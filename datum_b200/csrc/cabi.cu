@@ -359,9 +359,10 @@ namespace
 
     int slot = record_dominant ? begin_dominant(ctx, (double)(row_end - row_begin) * wd * (double)table.samples * batch.probes) : -1;
 
-    err = ibl::launch_prefilter_dn(p, ctx->prefilter_variant >= 50 ? ctx->prefilter_variant : 0, ctx->sm_count, ctx->stream, nullptr);
+    int grid = 0;
+    err = ibl::launch_prefilter_dn(p, ctx->prefilter_variant >= 50 ? ctx->prefilter_variant : 0, ctx->sm_count, ctx->stream, &grid);
     if (err != cudaSuccess)
-      return fail_cuda("prefilter_dn", err);
+      return fail_cuda(("prefilter_dn (source " + std::to_string(ws) + "x" + std::to_string(hs) + ", rows " + std::to_string(row_begin) + ".." + std::to_string(row_end) + ", " + std::to_string(batch.probes) + " probe(s), table " + std::to_string(table.count) + ", grid " + std::to_string(grid) + ")").c_str(), err);
     ctx->launches += 1;
 
     if (slot >= 0)

@@ -34,6 +34,8 @@
 
 #include <cuda_runtime.h>
 
+#include <vector>
+
 namespace ibl
 {
   typedef unsigned long long f32x2;
@@ -1054,35 +1056,48 @@ namespace ibl
 
   namespace
   {
-    // dynamic shared memory opt-in + resident CTAs per SM of one kernel instantiation, remembered per
-    // (device, shared-memory size): the two runtime calls cost more host time than the launch itself
-    template<typename Kernel>
-    cudaError_t resident_ctas(Kernel kernel, int threads, size_t smem, int *resident)
+    // Resident CTAs per SM of one kernel for one dynamic shared-memory size, remembered per (kernel,
+    // device, size): the occupancy query costs more host time than the launch itself.  Every kernel
+    // instantiation here has the same function-pointer type, so the kernel's ADDRESS is part of the key
+    // (round 1 keyed by size only: a hit recorded by one kernel skipped the opt-in of another).  The
+    // dynamic shared-memory opt-in is only ever raised, and only above the 48 KB every kernel may use
+    // without it: setting the attribute to a smaller value would LOWER the kernel's limit.
+    cudaError_t resident_ctas(void (*kernel)(PrefilterDnParams), int threads, size_t smem, int *resident)
     {
-      struct Entry { int device; size_t smem; int resident; };
-      thread_local static Entry cache[8] = {};
-      thread_local static int used = 0;
-      thread_local static size_t opted_in[16] = {};      // per device: the opt-in only ever grows
+      struct Entry { void (*kernel)(PrefilterDnParams); int device; size_t smem; int resident; };
+      thread_local static std::vector<Entry> cache;
+      struct OptIn { void (*kernel)(PrefilterDnParams); int device; size_t smem; };
+      thread_local static std::vector<OptIn> opted;
 
       int device = 0;
       cudaError_t err = cudaGetDevice(&device);
       if (err != cudaSuccess)
         return err;
 
-      for(int i = 0; i < used; ++i)
-        if (cache[i].device == device && cache[i].smem == smem)
+      for(auto const &e : cache)
+        if (e.kernel == kernel && e.device == device && e.smem == smem)
         {
-          *resident = cache[i].resident;
+          *resident = e.resident;
           return cudaSuccess;
         }
 
-      if (device < 0 || device >= 16 || smem > opted_in[device])
+      if (smem > 48 * 1024)
       {
-        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess)
-          return err;
-        if (device >= 0 && device < 16)
-          opted_in[device] = smem;
+        OptIn *mine = nullptr;
+        for(auto &o : opted)
+          if (o.kernel == kernel && o.device == device)
+            mine = &o;
+
+        if (!mine || mine->smem < smem)
+        {
+          err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (err != cudaSuccess)
+            return err;
+          if (mine)
+            mine->smem = smem;
+          else
+            opted.push_back(OptIn{ kernel, device, smem });
+        }
       }
 
       err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(resident, kernel, threads, smem);
@@ -1091,10 +1106,9 @@ namespace ibl
       if (*resident < 1)
         return cudaErrorLaunchOutOfResources;
 
-      // when the table is full overwrite round-robin
-      cache[used < 8 ? used : (int)(smem % 8)] = Entry{ device, smem, *resident };
-      if (used < 8)
-        used += 1;
+      if (cache.size() >= 256)
+        cache.clear();
+      cache.push_back(Entry{ kernel, device, smem, *resident });
 
       return cudaSuccess;
     }

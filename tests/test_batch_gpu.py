@@ -55,6 +55,24 @@ def test_batch_at_the_c4_probe_size(ctx):
     assert ctx.bake_probes(w, w, levels, payloads, samples) is None
     for got, ref in zip(payloads, want):
         assert np.array_equal(got, ref)
+    # ... and a single call AFTER the batch (regression: the batch's launch shapes and a single call's
+    # share shared-memory sizes; a per-size cache once skipped the second kernel's set-up)
+    again = single_calls(ctx, w, levels, samples, probes[:1])
+    assert np.array_equal(again[0], want[0])
+
+
+def test_a_group_of_sixteen_small_probes_equals_single_calls(ctx):
+    """Probes well below C2's size are baked up to 16 per launch (level L of the whole group in one grid):
+    same words as single calls, SH9 included, also when the last group is short."""
+    w, levels, samples = 64, 7, 128
+    probes = list(range(200, 219))            # 19 probes: one group of 16 and a group of 3
+    want = single_calls(ctx, w, levels, samples, probes)
+    payloads = [torch.from_numpy(synth.synthetic_chain(w, w, levels, probe=p).view(np.int32).copy()).pin_memory() for p in probes]
+    sh = ctx.bake_probes(w, w, levels, payloads, samples, sh9=True)
+    for i in range(len(probes)):
+        assert np.array_equal(payloads[i].numpy().view(np.uint32), want[i]), i
+        level0 = np.ascontiguousarray(want[i][: 6 * w * w])
+        assert np.array_equal(sh[i], ctx.project_sh9(level0, datum_b200.FORMAT_RGBE, w, w).reshape(9, 3))
 
 
 def test_empty_batch_and_bad_arguments(ctx):
