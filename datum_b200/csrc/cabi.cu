@@ -480,7 +480,7 @@ namespace
   // data/project.comp:23-106 for a slab of rows, on `stream` (the context's own, or the upload stream of a
   // batch so that the projection of probe i+1 runs under the prefilter kernels of probe i).  The scratch
   // (block partials, ticket) is shared: callers keep their projections on ONE stream at a time.
-  int sh9_partial_on(datum_ibl_ctx *ctx, cudaStream_t stream, void const *d_level0, int format, int width, int height, int row_begin, int row_end, double *d_partial, ibl::Sh9Peers const &peers = ibl::Sh9Peers())
+  int sh9_partial_on(datum_ibl_ctx *ctx, cudaStream_t stream, void const *d_level0, int format, int width, int height, int row_begin, int row_end, double *d_partial, ibl::Sh9Peers const &peers = ibl::Sh9Peers(), int probes = 1, size_t probe_stride = 0)
   {
     if (ctx->sh_weights_w != width || ctx->sh_weights_h != height)
     {
@@ -501,17 +501,20 @@ namespace
 
     int blocks = ibl::sh9_partial_blocks(width, height, ctx->sm_count);
 
-    cudaError_t err = ctx->sh_partials.reserve((size_t)blocks * 28 + 28);
-    if (err == cudaSuccess && !ctx->sh_counter.ptr)
+    // one ticket per cube of a batch (zeroed once, the kernel leaves them at zero), block partials per cube
+    cudaError_t err = ctx->sh_partials.reserve((size_t)blocks * 28 * probes + 28);
+    if (err == cudaSuccess && ctx->sh_counter.capacity < (size_t)(probes > 16 ? probes : 16))
     {
-      err = ctx->sh_counter.reserve(1);
+      err = cudaStreamSynchronize(stream);             // a projection in flight still owns the old tickets
       if (err == cudaSuccess)
-        err = cudaMemsetAsync(ctx->sh_counter.ptr, 0, sizeof(unsigned int), stream);
+        err = ctx->sh_counter.reserve(probes > 16 ? probes : 16);
+      if (err == cudaSuccess)
+        err = cudaMemsetAsync(ctx->sh_counter.ptr, 0, ctx->sh_counter.capacity * sizeof(unsigned int), stream);
     }
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(sh9 partials)", err);
 
-    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, ctx->sh_counter.ptr, d_partial, peers, ctx->sm_count, stream, ctx->sh9_kernel, ctx->sh9_rows_per_item);
+    err = ibl::launch_sh9_partial(d_level0, format, ctx->sh_weights.ptr, width, height, row_begin, row_end, ctx->sh_partials.ptr, blocks, ctx->sh_counter.ptr, d_partial, peers, ctx->sm_count, stream, ctx->sh9_kernel, ctx->sh9_rows_per_item, probes, probe_stride);
     if (err != cudaSuccess)
       return fail_cuda("sh9_partial", err);
     ctx->launches += 1;
@@ -1034,7 +1037,9 @@ extern "C"
 
       // the projection reads level 0 only: it runs behind the upload on the upload stream, under the
       // prefilter kernels of the previous group; the next upload into these payloads queues behind it
-      for(int j = 0; sh && j < n; ++j)
+      if (sh && sh9_partial_on(ctx, ctx->copy_in, d_base, DATUM_IBL_FORMAT_RGBE, width, height, 0, 6 * height, ctx->batch_sh.ptr + (size_t)first * 28, ibl::Sh9Peers(), ctx->sh9_kernel == 0 ? n : 1, words * sizeof(uint32_t)))
+        return drain(1);
+      for(int j = 1; sh && ctx->sh9_kernel != 0 && j < n; ++j)        // the A/B kernel takes one cube per launch
         if (sh9_partial_on(ctx, ctx->copy_in, d_base + (size_t)j * words, DATUM_IBL_FORMAT_RGBE, width, height, 0, 6 * height, ctx->batch_sh.ptr + (size_t)(first + j) * 28))
           return drain(1);
 

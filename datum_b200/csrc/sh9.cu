@@ -415,8 +415,15 @@ namespace ibl
   }
 
   template<int FORMAT>
-  __global__ void __launch_bounds__(kSh9ColThreads, 2) sh9_columns_kernel(void const *__restrict__ level0, float const *__restrict__ weights, int w, int h, int row_begin, int row_end, int rows_per_item, double *__restrict__ block_partials, unsigned int *__restrict__ done_counter, double *__restrict__ partial, Sh9Peers peers)
+  __global__ void __launch_bounds__(kSh9ColThreads, 2) sh9_columns_kernel(void const *__restrict__ level0, float const *__restrict__ weights, int w, int h, int row_begin, int row_end, int rows_per_item, double *__restrict__ block_partials, unsigned int *__restrict__ done_counter, double *__restrict__ partial, Sh9Peers peers, size_t probe_stride)
   {
+    // blockIdx.y = which cube of a batch (datum_ibl_bake_probes): cubes probe_stride bytes apart, their
+    // block partials, tickets and results back to back
+    level0 = static_cast<unsigned char const*>(level0) + (size_t)blockIdx.y * probe_stride;
+    block_partials += (size_t)blockIdx.y * gridDim.x * 28;
+    done_counter += blockIdx.y;
+    partial += (size_t)blockIdx.y * 28;
+
     float acc[28];
     #pragma unroll
     for(int k = 0; k < 28; ++k)
@@ -689,11 +696,17 @@ namespace ibl
     return (int)(items < cap ? (items < 1 ? 1 : items) : cap);
   }
 
-  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, unsigned int *done_counter, double *partial, Sh9Peers const &peers, int sm_count, cudaStream_t stream, int kernel, int rows_per_item)
+  cudaError_t launch_sh9_partial(void const *level0, int format, float const *weights, int w, int h, int row_begin, int row_end, double *block_partials, int blocks, unsigned int *done_counter, double *partial, Sh9Peers const &peers, int sm_count, cudaStream_t stream, int kernel, int rows_per_item, int probes, size_t probe_stride)
   {
+    if (probes < 1)
+      probes = 1;
+
     if (kernel == 1)
     {
-      // the row-segment kernel (A/B)
+      // the row-segment kernel (A/B; one cube at a time)
+      if (probes != 1)
+        return cudaErrorNotSupported;
+
       if (format == 0)
         sh9_partial_kernel<0><<<blocks, kSh9Threads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, block_partials, done_counter, partial, peers);
       else
@@ -711,20 +724,22 @@ namespace ibl
     if (rows_per_item <= 0)
     {
       long long want_items = 6ll * resident;
-      long long r = ((long long)rows * col_blocks + want_items - 1) / want_items;
+      long long r = ((long long)rows * col_blocks + want_items - 1) / want_items;      // from ONE cube: a batch gives the bits of single calls
       rows_per_item = (int)(r < 8 ? 8 : (r > 64 ? 64 : r));
       rows_per_item = (rows_per_item + kSh9ColUnroll - 1) / kSh9ColUnroll * kSh9ColUnroll;
     }
 
     long long items = (long long)((rows + rows_per_item - 1) / rows_per_item) * col_blocks;
-    int grid = (int)(items < resident ? (items < 1 ? 1 : items) : resident);
+    int grid = (int)(items < resident ? (items < 1 ? 1 : items) : resident);     // per cube, whatever the batch
     if (grid > blocks)
-      grid = blocks;      // the scratch holds `blocks` partial rows
+      grid = blocks;      // the scratch holds `blocks` partial rows per cube
+
+    dim3 cubes(grid, probes);
 
     if (format == 0)
-      sh9_columns_kernel<0><<<grid, kSh9ColThreads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, rows_per_item, block_partials, done_counter, partial, peers);
+      sh9_columns_kernel<0><<<cubes, kSh9ColThreads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, rows_per_item, block_partials, done_counter, partial, peers, probe_stride);
     else
-      sh9_columns_kernel<1><<<grid, kSh9ColThreads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, rows_per_item, block_partials, done_counter, partial, peers);
+      sh9_columns_kernel<1><<<cubes, kSh9ColThreads, 0, stream>>>(level0, weights, w, h, row_begin, row_end, rows_per_item, block_partials, done_counter, partial, peers, probe_stride);
 
     return cudaGetLastError();
   }
