@@ -409,7 +409,7 @@ namespace
       p.geom = ibl::make_level_geom(ws, hs);
       for(int f = 0; f < 6; ++f)
         p.quats[f] = ctx->quats[f];
-      ibl::dn_channel_norms(table.total_weight, p.norm);
+      ibl::raw_channel_norms(table.total_weight, p.norm);
       p.exp_mul = 0x00800000u;
       p.probes = batch.probes;
       p.src_stride = batch.stride;

@@ -360,6 +360,20 @@ namespace ibl
     acc[2] = fmaf(u2f(word & kDnMaskB), ws, acc[2]);
   }
 
+  // The same on a word in the reference's own layout (E 27..31, b 18..26, g 9..17, r 0..8), for the
+  // kernel that reads the source level directly: r and g are subnormals in place, b is brought below
+  // the exponent field with one shift (bits 14..22), E comes down with one shift.  5 logic ops + 1
+  // integer multiply-add per tap; re-laying the word first (pack_dn_word) cost 12.  Every product is
+  // exact and the sums differ from dn_accumulate_tap's by exact powers of two per channel
+  // (raw_channel_norms), so the results are bit-identical.
+  IBL_HD void raw_accumulate_tap(uint32_t word, float w, uint32_t emul, float acc[3])
+  {
+    float ws = u2f(f2u(w) + (word >> 27) * emul);
+    acc[0] = fmaf(u2f(word & 0x000001FFu), ws, acc[0]);
+    acc[1] = fmaf(u2f(word & 0x0003FE00u), ws, acc[1]);
+    acc[2] = fmaf(u2f((word >> 4) & 0x007FC000u), ws, acc[2]);
+  }
+
   // sums -> radiance: radiance = (m/511) * 2^(E-15), sums hold m * 2^-149 * 2^(field position) * 2^64 * 2^E * weight
   IBL_HD void dn_channel_norms(double total_weight, float norm[3])
   {
@@ -367,5 +381,13 @@ namespace ibl
     norm[0] = (float)base;
     norm[1] = (float)ldexp(base, -14);
     norm[2] = (float)ldexp(base, -5);
+  }
+
+  IBL_HD void raw_channel_norms(double total_weight, float norm[3])
+  {
+    double base = ldexp(1.0, 149 - 64 - 15) / 511.0 / total_weight;
+    norm[0] = (float)base;
+    norm[1] = (float)ldexp(base, -9);
+    norm[2] = (float)ldexp(base, -14);
   }
 }

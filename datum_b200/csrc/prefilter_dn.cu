@@ -883,8 +883,8 @@ namespace ibl
   // consecutive table entries: NW*32 samples per step, warp-shuffle + shared-memory reduction at the
   // end.  Every sample goes through the cube-face selection (at these roughnesses almost all leave
   // the face anyway); the four words of a footprint are read from the source level itself (it fits in
-  // L1/L2) and re-laid in registers, so the level needs no record pass: one launch instead of two.
-  // Arithmetic per sample is the one-sample kernel's general path.
+  // L1/L2) in the reference's own bit layout (raw_accumulate_tap), so the level needs no record pass: one
+  // launch instead of two.  Arithmetic per sample is the one-sample kernel's general path.
   template<int NW>
   __global__ void __launch_bounds__(32 * NW) prefilter_tail_kernel(PrefilterTailParams p)
   {
@@ -939,10 +939,10 @@ namespace ibl
       footprint_weights(du, dv, e.w, e.z, w);
 
       uint32_t const *t = p.src + (size_t)probe * p.src_stride + idx;
-      dn_accumulate_tap(pack_dn_word(__ldg(t)), w[0], acc);
-      dn_accumulate_tap(pack_dn_word(__ldg(t + 1)), w[1], acc);
-      dn_accumulate_tap(pack_dn_word(__ldg(t + p.geom.ws)), w[2], acc);
-      dn_accumulate_tap(pack_dn_word(__ldg(t + p.geom.ws + 1)), w[3], acc);
+      raw_accumulate_tap(__ldg(t), w[0], p.exp_mul, acc);
+      raw_accumulate_tap(__ldg(t + 1), w[1], p.exp_mul, acc);
+      raw_accumulate_tap(__ldg(t + p.geom.ws), w[2], p.exp_mul, acc);
+      raw_accumulate_tap(__ldg(t + p.geom.ws + 1), w[3], p.exp_mul, acc);
     }
 
     #pragma unroll

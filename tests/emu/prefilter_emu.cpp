@@ -341,6 +341,16 @@ extern "C" void emu_dn_tap(uint32_t rgbe_word, float w, float *rgb)
   rgb[0] = acc[0] * norm[0]; rgb[1] = acc[1] * norm[1]; rgb[2] = acc[2] * norm[2];
 }
 
+// the same tap through raw_accumulate_tap (the tail kernel: the word in the reference's own bit layout)
+extern "C" void emu_raw_tap(uint32_t rgbe_word, float w, float *rgb)
+{
+  float acc[3] = { 0, 0, 0 }, norm[3];
+  raw_accumulate_tap(rgbe_word, w * kDnTableScale, 0x00800000u, acc);
+  raw_channel_norms(1.0, norm);
+  for(int c = 0; c < 3; ++c)
+    rgb[c] = acc[c] * norm[c];
+}
+
 extern "C" double emu_last_fast_fraction() { return g_fast_fraction; }
 
 extern "C" uint32_t emu_rgbe_encode(float r, float g, float b) { return rgbe_encode(r, g, b); }

@@ -31,6 +31,7 @@ def load():
         lib.emu_pack_dn_word.argtypes = [ctypes.c_uint32]
         lib.emu_pack_dn_word.restype = ctypes.c_uint32
         lib.emu_dn_tap.argtypes = [ctypes.c_uint32, ctypes.c_float, ctypes.c_void_p]
+        lib.emu_raw_tap.argtypes = [ctypes.c_uint32, ctypes.c_float, ctypes.c_void_p]
         lib.emu_last_fast_fraction.restype = ctypes.c_double
         lib.emu_rgbe_encode.restype = ctypes.c_uint32
         lib.emu_rgbe_encode.argtypes = [ctypes.c_float] * 3

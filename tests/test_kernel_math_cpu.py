@@ -161,6 +161,9 @@ def test_dn_tap_decodes_every_field_exactly():
             emu.emu_dn_tap(word, w, got.ctypes.data)
             emu.emu_rgbe_decode(word, want.ctypes.data)
             assert np.allclose(got, want * np.float32(w), rtol=3e-7, atol=0.0), (hex(word), w, got, want)
+            raw = np.zeros(3, np.float32)
+            emu.emu_raw_tap(word, w, raw.ctypes.data)          # the tail kernel's form, straight from the rgbe word
+            assert np.array_equal(raw, got), (hex(word), w, raw, got)
     m = emu.emu_pack_dn_word(5 << 27 | 3 << 18 | 2 << 9 | 1)
     assert m == (1 << 23 | 2 << 14 | 3 << 5 | 5)
 
