@@ -582,7 +582,7 @@ def run_ours(args):
 
     # ---- the same K bakes as ONE batched call (datum_ibl_bake_probes): copies of probe i+1 / i-1 under the kernels of probe i
     batch = [pinned[i % len(pinned)] for i in range(args.steps)]
-    ctx.bake_probes(w, w, levels, batch[: min(4, len(batch))], samples)
+    ctx.bake_probes(w, w, levels, batch[: min(12, len(batch))], samples)      # enough payloads for both device buffers of the pipeline to exist
     job.barrier()
     t0 = time.perf_counter()
     ctx.bake_probes(w, w, levels, batch, samples)

@@ -1,0 +1,116 @@
+// datum_b200 — per-level GGX sample tables (host side); see ibl_tables.h.
+
+#include "ibl_tables.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace ibl
+{
+  float radicalinverse_VdC(uint32_t bits)
+  {
+    uint32_t r = 0;
+    for(int k = 0; k < 32; ++k, bits >>= 1)
+      r = (r << 1) | (bits & 1u);
+
+    return float(r) * 2.3283064365386963e-10f; // 2^-32, rounded to fp32 like ibl.cpp:103
+  }
+
+  LevelSamples build_level_samples(int level, int levels, int samples)
+  {
+    LevelSamples out;
+
+    // ibl.cpp:251, 173: roughness = level/(levels-1), alpha = roughness^2 — in fp32 like the reference
+    float roughness = (float)level / (float)(levels - 1);
+    float alpha = roughness * roughness;
+    float a2m1 = alpha * alpha - 1;
+
+    out.roughness = roughness;
+    out.entries.reserve(samples);
+
+    for(int i = 0; i < samples; ++i)
+    {
+      // ibl.cpp:106-109, 119-121 in fp32 so that (phi, theta) are the reference's values
+      float ux = float(i) / float(samples);
+      float uy = radicalinverse_VdC((uint32_t)i);
+      float phi = 2 * 3.14159265358979323846f * ux;
+      float costheta = std::sqrt((1 - uy) / (1 + a2m1 * uy));
+      float sintheta = std::sqrt(1 - costheta * costheta);
+
+      double hx = (double)sintheta * std::cos((double)phi);
+      double hy = (double)sintheta * std::sin((double)phi);
+      double hz = (double)costheta;
+
+      double lz = 2 * hz * hz - 1;
+
+      if (!(lz > 0))
+        continue; // ibl.cpp:178
+
+      SampleEntry e;
+      e.lx = (float)(2 * hz * hx);
+      e.ly = (float)(2 * hz * hy);
+      e.lz = (float)std::min(lz, 1.0);
+      e.wh = 0.5f * e.lz;
+
+      out.total_weight += (double)e.lz;
+      out.entries.push_back(e);
+    }
+
+    out.accepted = (int)out.entries.size();
+
+    std::stable_sort(out.entries.begin(), out.entries.end(), [](SampleEntry const &a, SampleEntry const &b) { return a.lz > b.lz; });
+
+    return out;
+  }
+
+  BandedSamples build_banded_samples(int level, int levels, int samples, int band)
+  {
+    BandedSamples out;
+    out.level = build_level_samples(level, levels, samples);
+    out.band = band;
+
+    auto &e = out.level.entries;
+    for(size_t begin = 0; begin < e.size(); begin += (size_t)band)
+    {
+      size_t end = std::min(e.size(), begin + (size_t)band);
+
+      out.band_min_lz.push_back(e[end - 1].lz);
+
+      std::stable_sort(e.begin() + begin, e.begin() + end, [](SampleEntry const &a, SampleEntry const &b) {
+        return std::atan2((double)a.ly, (double)a.lx) < std::atan2((double)b.ly, (double)b.lx);
+      });
+    }
+
+    return out;
+  }
+
+  std::vector<float> build_paired_entries(BandedSamples const &banded, float scale)
+  {
+    std::vector<SampleEntry> e = banded.level.entries;
+    for(auto &s : e)
+    {
+      s.lx *= scale; s.ly *= scale; s.lz *= scale; s.wh *= scale;
+    }
+
+    // fill the last band: direction (0, 0, 1) in the tangent frame, i.e. the normal itself (always on
+    // the texel's own face), at 2^-60 of the scale of a real entry
+    size_t band = (size_t)(banded.band > 0 ? banded.band : 1);
+    size_t padded = (e.size() + band - 1) / band * band;
+    float tiny = std::ldexp(scale, -60);
+    padded += padded & 1;   // pairs: an even count whatever the band size
+    while (e.size() < padded)
+      e.push_back(SampleEntry{ 0.0f, 0.0f, tiny, 0.5f * tiny });
+
+    std::vector<float> out(4 * padded);
+    for(size_t i = 0; i < padded; i += 2)
+    {
+      SampleEntry const &a = e[i];
+      SampleEntry const &b = e[i + 1];
+      float *o = out.data() + 4 * i;
+      o[0] = a.lx; o[1] = b.lx; o[2] = a.ly; o[3] = b.ly;
+      o[4] = a.lz; o[5] = b.lz; o[6] = a.wh; o[7] = b.wh;
+    }
+
+    return out;
+  }
+}

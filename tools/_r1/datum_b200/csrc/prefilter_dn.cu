@@ -2,8 +2,7 @@
 //
 // Replaces the triple loop of tools/ibl.cpp:263-272 and the per-texel sample loop of
 // tools/ibl.cpp:160-187 (reference paths relative to /root/reference).  This is the kernel the
-// library uses for every slab of more than kTailTexels texels; smaller slabs and levels narrower
-// than a tile go to prefilter_tail_kernel below.
+// library uses for every level at least 8 texels wide; narrower levels go to prefilter.cu.
 //
 // What one bilinear tap costs decides the speed of this loop (profiles/): the first kernel
 // (prefilter.cu) turned each 9-bit mantissa into a float with shift + mask logic, six ALU-pipe ops
@@ -33,8 +32,6 @@
 #include "ibl_math.cuh"
 
 #include <cuda_runtime.h>
-
-#include <vector>
 
 namespace ibl
 {
@@ -71,18 +68,6 @@ namespace ibl
     return u2f(r + f2u(w));
   }
 
-  // r mantissa = word >> 23: a shift on the ALU pipe, or (A/B) the high half of word * 2^9 on the FMA pipe
-  template<bool HI>
-  __device__ __forceinline__ float red_field(uint32_t word, uint32_t rmul)
-  {
-    if (!HI)
-      return u2f(word >> 23);
-
-    uint32_t r;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(word), "r"(rmul));
-    return u2f(r);
-  }
-
   template<bool ALU>
   __device__ __forceinline__ float scale_tap(float w, uint32_t word, uint32_t emul)
   {
@@ -91,62 +76,27 @@ namespace ibl
 
   // ---- quad records ----------------------------------------------------------------
 
-  __global__ void __launch_bounds__(256) build_dn_records_kernel(uint32_t const *__restrict__ src, uint4 *__restrict__ rec, int ws, int hs, size_t src_stride, int *__restrict__ counters, int ncounters)
+  __global__ void __launch_bounds__(256) build_dn_records_kernel(uint32_t const *__restrict__ src, uint4 *__restrict__ rec, int ws, int hs, int *__restrict__ counters, int ncounters)
   {
     // the prefilter launch that follows on the stream takes its tiles from these queues
-    if (blockIdx.x == 0 && blockIdx.y == 0)
+    if (blockIdx.x == 0)
       for(int i = threadIdx.x; i < ncounters; i += blockDim.x)
         counters[i] = 0;
 
-    // blockIdx.y = probe of a batch: source levels `src_stride` words apart, their records back to back
-    const uint32_t level = 6u * (uint32_t)ws * (uint32_t)hs;
-    src += (size_t)blockIdx.y * src_stride;
-    rec += (size_t)blockIdx.y * level;
-
-    for(uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < level; idx += gridDim.x * blockDim.x)
+    size_t total = (size_t)6 * ws * hs;
+    for(size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
     {
-      uint32_t i = idx % (uint32_t)ws;
-      uint32_t j = (idx / (uint32_t)ws) % (uint32_t)hs;
-      uint32_t right = (i + 1 < (uint32_t)ws) ? 1u : 0u;           // neighbours clamped inside the face; the clamped
-      uint32_t down = (j + 1 < (uint32_t)hs) ? (uint32_t)ws : 0u;  // ones are never addressed (i <= ws-2, j <= hs-2)
-
-      uint32_t const *t = src + idx;
+      int i = (int)(idx % ws);
+      int j = (int)((idx / ws) % hs);
+      size_t right = (i + 1 < ws) ? 1 : 0;      // neighbours clamped inside the face; the clamped
+      size_t down = (j + 1 < hs) ? (size_t)ws : 0; // ones are never addressed (i <= ws-2, j <= hs-2)
 
       uint4 r;
-      r.x = pack_dn_word(__ldg(t));
-      r.y = pack_dn_word(__ldg(t + right));
-      r.z = pack_dn_word(__ldg(t + down));
-      r.w = pack_dn_word(__ldg(t + down + right));
+      r.x = pack_dn_word(__ldg(src + idx));
+      r.y = pack_dn_word(__ldg(src + idx + right));
+      r.z = pack_dn_word(__ldg(src + idx + down));
+      r.w = pack_dn_word(__ldg(src + idx + down + right));
       rec[idx] = r;
-    }
-  }
-
-
-  // ---- "this launch has stored everything" -----------------------------------------------------
-  //
-  // One probe shared by several GPUs: the epilogues above store every word into the peers' chains.
-  // The CTA that finishes LAST (ticket counter) bumps an arrival counter in every peer's flag block
-  // with a system-scope release; the peers' streams wait on their own counter (a stream memory
-  // operation, no kernel) before the next level reads the words.  Every thread fences its own
-  // stores before the ticket, the last CTA fences again behind it (cumulativity).
-  __device__ __forceinline__ void signal_peers_when_last(PeerSignal const &s)
-  {
-    if (s.count <= 0)
-      return;
-
-    __threadfence_system();
-    __syncthreads();
-
-    if (threadIdx.x == 0)
-    {
-      unsigned int ticket = atomicAdd(s.ticket, 1u);
-      if (ticket == gridDim.x - 1)
-      {
-        __threadfence_system();
-        for(int k = 0; k < s.count; ++k)
-          asm volatile("red.release.sys.global.add.u32 [%0], 1;" :: "l"(s.arrive[k]) : "memory");
-        *s.ticket = 0;        // ready for the next launch on this stream
-      }
     }
   }
 
@@ -231,48 +181,7 @@ namespace ibl
   // Tiles of 8x4 texels are numbered in 4x4-blocked order over the slab.  With QUEUES the first
   // `queued` tiles are cut into one contiguous chunk per SM (queue index = %smid) and the rest form
   // a common pool that evens out the tail: a group takes tiles from its SM's chunk, then from the pool.
-  //
-  // %smid values are not guaranteed to be contiguous, and under MPS limits, green contexts or a
-  // concurrent kernel an SM may host no CTA of this launch at all: once its own chunk and the pool are
-  // empty (next_tile_plain returns -1) a group therefore looks through every other chunk before it
-  // gives up, so every tile is computed whatever the placement of the CTAs.  The look is made by the 32
-  // lanes of the group's first warp side by side (148 dependent L2 reads by one thread cost ~20 us per
-  // call, measured as +5 % on a whole level; 5 rounds of 32 cost under 1 us), and only then: the common
-  // hand-out stays one thread and one or two atomics.  Called by all lanes of warp 0; every lane gets the tile.
-  // NOT inlined on purpose: with this code inside the kernel body ptxas schedules the sample loops ~1 % (512^2
-  // level) to ~3 % (256^2 level) slower although it only ever runs at the very end of a launch (measured A/B).
-  __device__ __noinline__ int steal_tile(int *counters, int queues, int chunk, uint32_t smid, int lane)
-  {
-    const int own = (int)(smid % (uint32_t)queues);
-
-    for(int base = 1; base < queues; base += 32)
-    {
-      int i = base + lane;
-      int q = own + i;
-      if (q >= queues)
-        q -= queues;
-
-      // a drained chunk costs one read; only chunks that still hold tiles are bumped
-      bool holds = i < queues && *(volatile int const *)(counters + q) < chunk;
-
-      for(unsigned candidates = __ballot_sync(0xffffffffu, holds); candidates != 0u; candidates &= candidates - 1u)
-      {
-        int src = __ffs(candidates) - 1;
-        int k = -1;
-        if (lane == src)
-          k = atomicAdd(counters + q, 1);
-        k = __shfl_sync(0xffffffffu, k, src);
-
-        if (k < chunk)
-          return __shfl_sync(0xffffffffu, q, src) * chunk + k;
-      }
-    }
-
-    return -1;
-  }
-
-  // the common hand-out, one thread: the SM's own chunk, then the pool; -1 when both are empty
-  __device__ __forceinline__ int next_tile_plain(PrefilterDnParams const &p, uint32_t smid)
+  __device__ __forceinline__ int next_tile(PrefilterDnParams const &p, uint32_t smid)
   {
     if ((int)smid < p.queues)
     {
@@ -340,22 +249,9 @@ namespace ibl
       if (QUEUES)
       {
         if (tid == 0)
-          *s_tile = next_tile_plain(p, smid);
+          *s_tile = next_tile(p, smid);
         __syncthreads();
         tile = *s_tile;
-
-        if (tile < 0 && !p.no_steal)
-        {
-          __syncthreads();                 // everybody has read the empty hand-out
-          if (warp == 0)
-          {
-            int stolen = steal_tile(p.counters, p.queues, p.chunk, smid, lane);
-            if (lane == 0)
-              *s_tile = stolen;
-          }
-          __syncthreads();
-          tile = *s_tile;
-        }
       }
       else
       {
@@ -520,8 +416,6 @@ namespace ibl
 
       __syncthreads();   // s_red and s_tile are reused by the next tile
     }
-
-    signal_peers_when_last(p.signal);
   }
 
   // ---- two samples at a time --------------------------------------------------------------
@@ -589,7 +483,7 @@ namespace ibl
   }
 
   // (fu, fv) of both samples -> records, weights, taps.  EXP_ALU of the four taps of a sample take their exponent on the ALU pipe.  `base` holds the bias (and the face on the same-face path).
-  template<int EXP_ALU, bool RHI>
+  template<int EXP_ALU>
   __device__ __forceinline__ void gather_pair(PrefilterDnParams const &p, uint4 const *base, uint32_t off_a, uint32_t off_b, f32x2 fu, f32x2 fv, PairEntry const &e, Sums &acc)
   {
     f32x2 mu = add2(fu, bcast2(kMagic));
@@ -628,14 +522,14 @@ namespace ibl
     w01b = scale_tap<(EXP_ALU > 1)>(w01b, rb.z, emul);
     w11b = scale_tap<(EXP_ALU > 3)>(w11b, rb.w, emul);
 
-    acc.rg = fma2(pack2(red_field<RHI>(ra.x, p.red_mul), u2f(ra.x & kDnMaskG)), bcast2(w00a), acc.rg);
-    acc.rg = fma2(pack2(red_field<RHI>(ra.y, p.red_mul), u2f(ra.y & kDnMaskG)), bcast2(w10a), acc.rg);
-    acc.rg = fma2(pack2(red_field<RHI>(ra.z, p.red_mul), u2f(ra.z & kDnMaskG)), bcast2(w01a), acc.rg);
-    acc.rg = fma2(pack2(red_field<RHI>(ra.w, p.red_mul), u2f(ra.w & kDnMaskG)), bcast2(w11a), acc.rg);
-    acc.rg = fma2(pack2(red_field<RHI>(rb.x, p.red_mul), u2f(rb.x & kDnMaskG)), bcast2(w00b), acc.rg);
-    acc.rg = fma2(pack2(red_field<RHI>(rb.y, p.red_mul), u2f(rb.y & kDnMaskG)), bcast2(w10b), acc.rg);
-    acc.rg = fma2(pack2(red_field<RHI>(rb.z, p.red_mul), u2f(rb.z & kDnMaskG)), bcast2(w01b), acc.rg);
-    acc.rg = fma2(pack2(red_field<RHI>(rb.w, p.red_mul), u2f(rb.w & kDnMaskG)), bcast2(w11b), acc.rg);
+    acc.rg = fma2(pack2(u2f(ra.x >> 23), u2f(ra.x & kDnMaskG)), bcast2(w00a), acc.rg);
+    acc.rg = fma2(pack2(u2f(ra.y >> 23), u2f(ra.y & kDnMaskG)), bcast2(w10a), acc.rg);
+    acc.rg = fma2(pack2(u2f(ra.z >> 23), u2f(ra.z & kDnMaskG)), bcast2(w01a), acc.rg);
+    acc.rg = fma2(pack2(u2f(ra.w >> 23), u2f(ra.w & kDnMaskG)), bcast2(w11a), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.x >> 23), u2f(rb.x & kDnMaskG)), bcast2(w00b), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.y >> 23), u2f(rb.y & kDnMaskG)), bcast2(w10b), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.z >> 23), u2f(rb.z & kDnMaskG)), bcast2(w01b), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.w >> 23), u2f(rb.w & kDnMaskG)), bcast2(w11b), acc.rg);
 
     acc.bb = fma2(pack2(u2f(ra.x & kDnMaskB), u2f(rb.x & kDnMaskB)), pack2(w00a, w00b), acc.bb);
     acc.bb = fma2(pack2(u2f(ra.y & kDnMaskB), u2f(rb.y & kDnMaskB)), pack2(w10a, w10b), acc.bb);
@@ -644,7 +538,7 @@ namespace ibl
   }
 
   // frame rows in face-local (a, b, m) coordinates, a and b pre-scaled to source texels
-  template<int EXP_ALU, bool RHI>
+  template<int EXP_ALU>
   __device__ __forceinline__ void pair_same_face(PrefilterDnParams const &p, Frame const &t, uint4 const *base, PairEntry const &e, Sums &acc)
   {
     f32x2 la, lb, lm;
@@ -654,11 +548,11 @@ namespace ibl
     unpack2(lm, ma, mb);
     f32x2 r = pack2(rcp_fast(ma), rcp_fast(mb));
 
-    gather_pair<EXP_ALU, RHI>(p, base, 0u, 0u, fma2(la, r, bcast2(p.geom.hwm)), fma2(lb, r, bcast2(p.geom.hhm)), e, acc);
+    gather_pair<EXP_ALU>(p, base, 0u, 0u, fma2(la, r, bcast2(p.geom.hwm)), fma2(lb, r, bcast2(p.geom.hhm)), e, acc);
   }
 
   // frame rows in world coordinates: cube face selection of tools/ibl.cpp:43-88 per sample
-  template<int EXP_ALU, bool RHI>
+  template<int EXP_ALU>
   __device__ __forceinline__ void pair_general(PrefilterDnParams const &p, Frame const &t, uint4 const *base, PairEntry const &e, Sums &acc)
   {
     f32x2 x, y, z;
@@ -678,10 +572,10 @@ namespace ibl
     f32x2 fv = fma2(pack2(qva, qvb), bcast2(p.geom.hh), bcast2(p.geom.hhm));
 
     // the face offset goes into the 32-bit index (bias + 6 faces cannot wrap, see the launcher)
-    gather_pair<EXP_ALU, RHI>(p, base, fa * p.geom.face_size, fb * p.geom.face_size, fu, fv, e, acc);
+    gather_pair<EXP_ALU>(p, base, fa * p.geom.face_size, fb * p.geom.face_size, fu, fv, e, acc);
   }
 
-  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false>
+  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU, int DEPTH = 1>
   __global__ void __launch_bounds__(32 * NW, MINB) prefilter_dp_kernel(PrefilterDnParams p)
   {
     extern __shared__ float4 smem[];
@@ -720,22 +614,9 @@ namespace ibl
       if (QUEUES)
       {
         if (tid == 0)
-          *s_tile = next_tile_plain(p, smid);
+          *s_tile = next_tile(p, smid);
         __syncthreads();
         tile = *s_tile;
-
-        if (!PLAIN_QUEUE && tile < 0 && !p.no_steal)
-        {
-          __syncthreads();                 // everybody has read the empty hand-out
-          if (warp == 0)
-          {
-            int stolen = steal_tile(p.counters, p.queues, p.chunk, smid, lane);
-            if (lane == 0)
-              *s_tile = stolen;
-          }
-          __syncthreads();
-          tile = *s_tile;
-        }
       }
       else
       {
@@ -747,17 +628,8 @@ namespace ibl
       if (tile < 0)
         break;
 
-      // a launch may carry the same level of several probes (datum_ibl_bake_probes): tiles are numbered
-      // probe by probe, records and destination levels sit at fixed strides
-      int probe = 0, ltile = tile;
-      if (!LEAN && p.probes > 1)
-      {
-        probe = tile / p.tiles_per_probe;
-        ltile = tile - probe * p.tiles_per_probe;
-      }
-
       int x, row;
-      bool valid = tile_texel(p, ltile, lane, x, row);
+      bool valid = tile_texel(p, tile, lane, x, row);
 
       if (__ballot_sync(0xffffffffu, valid) == 0u)
       {
@@ -770,9 +642,6 @@ namespace ibl
 
       int face = row / p.hd;
       int y = row - face * p.hd;
-
-      // this probe's records (a batch: records of the probes back to back)
-      uint4 const *biased_probe = LEAN ? biased : opaque(biased + (size_t)probe * p.record_stride);
 
       Frame st;
       int n_same;
@@ -810,14 +679,14 @@ namespace ibl
       int band = 0;
 
       {
-        uint4 const *base = opaque(biased_probe + (size_t)face * p.geom.face_size);
+        uint4 const *base = opaque(biased + (size_t)face * p.geom.face_size);
 
         #pragma unroll BAND_UNROLL
         for(; band < n_same; ++band)
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
-            pair_same_face<EXP_ALU, RHI>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+            pair_same_face<EXP_ALU>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
         }
       }
 
@@ -833,7 +702,7 @@ namespace ibl
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
-            pair_general<EXP_ALU, RHI>(p, st, biased_probe, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+            pair_general<EXP_ALU>(p, st, biased, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
         }
       }
 
@@ -864,7 +733,7 @@ namespace ibl
         {
           // sum/totalweight of ibl.cpp:186, then rgbe() of ibl.cpp:269
           float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
-          size_t o = (size_t)row * p.wd + x + (LEAN ? (size_t)0 : (size_t)probe * p.dst_stride);
+          size_t o = (size_t)row * p.wd + x;
 
           if (p.dst_words || p.peers > 0)
           {
@@ -889,9 +758,6 @@ namespace ibl
 
       __syncthreads();
     }
-
-    if (!LEAN)
-      signal_peers_when_last(p.signal);
   }
 
   // ---- tail levels: lanes are samples ----------------------------------------------------------
@@ -902,8 +768,8 @@ namespace ibl
   // consecutive table entries: NW*32 samples per step, warp-shuffle + shared-memory reduction at the
   // end.  Every sample goes through the cube-face selection (at these roughnesses almost all leave
   // the face anyway); the four words of a footprint are read from the source level itself (it fits in
-  // L1/L2) in the reference's own bit layout (raw_accumulate_tap), so the level needs no record pass: one
-  // launch instead of two.  Arithmetic per sample is the one-sample kernel's general path.
+  // L1/L2) and re-laid in registers, so the level needs no record pass: one launch instead of two.
+  // Arithmetic per sample is the one-sample kernel's general path.
   template<int NW>
   __global__ void __launch_bounds__(32 * NW) prefilter_tail_kernel(PrefilterTailParams p)
   {
@@ -912,13 +778,7 @@ namespace ibl
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // a launch may carry the same level of several probes: texels are numbered probe by probe
-    int texel = blockIdx.x, probe = 0;
-    if (p.probes > 1)
-    {
-      probe = texel / p.texels_per_probe;
-      texel -= probe * p.texels_per_probe;
-    }
+    const int texel = blockIdx.x;
     const int row = p.row_begin + texel / p.wd;
     const int x = texel - (texel / p.wd) * p.wd;
     const int face = row / p.hd;
@@ -957,11 +817,11 @@ namespace ibl
       float w[4];
       footprint_weights(du, dv, e.w, e.z, w);
 
-      uint32_t const *t = p.src + (size_t)probe * p.src_stride + idx;
-      raw_accumulate_tap(__ldg(t), w[0], p.exp_mul, acc);
-      raw_accumulate_tap(__ldg(t + 1), w[1], p.exp_mul, acc);
-      raw_accumulate_tap(__ldg(t + p.geom.ws), w[2], p.exp_mul, acc);
-      raw_accumulate_tap(__ldg(t + p.geom.ws + 1), w[3], p.exp_mul, acc);
+      uint32_t const *t = p.src + idx;
+      dn_accumulate_tap(pack_dn_word(__ldg(t)), w[0], acc);
+      dn_accumulate_tap(pack_dn_word(__ldg(t + 1)), w[1], acc);
+      dn_accumulate_tap(pack_dn_word(__ldg(t + p.geom.ws)), w[2], acc);
+      dn_accumulate_tap(pack_dn_word(__ldg(t + p.geom.ws + 1)), w[3], acc);
     }
 
     #pragma unroll
@@ -990,7 +850,7 @@ namespace ibl
 
       // sum/totalweight of ibl.cpp:186, then rgbe() of ibl.cpp:269
       float r = sum[0] * p.norm[0], g = sum[1] * p.norm[1], b = sum[2] * p.norm[2];
-      size_t o = (size_t)row * p.wd + x + (size_t)probe * p.dst_stride;
+      size_t o = (size_t)row * p.wd + x;
 
       if (p.dst_words || p.peers > 0)
       {
@@ -1010,116 +870,112 @@ namespace ibl
         p.dst_f32[3*o + 2] = b;
       }
     }
-
-    signal_peers_when_last(p.signal);
   }
 
-  cudaError_t launch_prefilter_tail(PrefilterTailParams const &params, int sm_count, cudaStream_t stream)
+  cudaError_t launch_prefilter_tail(PrefilterTailParams const &p, int sm_count, cudaStream_t stream)
   {
-    PrefilterTailParams p = params;
-
     int texels = (p.row_end - p.row_begin) * p.wd;
     if (texels <= 0)
       return cudaSuccess;
 
-    if (p.probes < 1)
-      p.probes = 1;
-    p.texels_per_probe = texels;
-
-    // warps per texel: enough CTAs to cover the machine first, then depth; never more lanes than samples.
-    // Chosen from ONE probe's texels also when a launch carries several: the shape decides the order of
-    // the sums, and a batch must give the words of single calls.
+    // warps per texel: enough CTAs to cover the machine first, then depth; never more lanes than samples
     (void)sm_count;
-    int grid = texels * p.probes;
     if (texels >= 4096 || p.table_count <= 128)
-      prefilter_tail_kernel<4><<<grid, 128, 0, stream>>>(p);
+      prefilter_tail_kernel<4><<<texels, 128, 0, stream>>>(p);
     else if (texels >= 1024 || p.table_count <= 256)
-      prefilter_tail_kernel<8><<<grid, 256, 0, stream>>>(p);
+      prefilter_tail_kernel<8><<<texels, 256, 0, stream>>>(p);
     else if (texels >= 256 || p.table_count <= 512)
-      prefilter_tail_kernel<16><<<grid, 512, 0, stream>>>(p);
+      prefilter_tail_kernel<16><<<texels, 512, 0, stream>>>(p);
     else
-      prefilter_tail_kernel<32><<<grid, 1024, 0, stream>>>(p);
+      prefilter_tail_kernel<32><<<texels, 1024, 0, stream>>>(p);
 
     return cudaGetLastError();
   }
 
-  // ---- arrival signal without a producing launch (the barrier at the start of a shared bake) ------
-  __global__ void peer_signal_kernel(PeerSignal s)
+  // ---- barrier between the GPUs sharing a probe ------------------------------------------------
+  //
+  // Runs on the bake's stream right behind a prefilter launch whose epilogue stored the slab into
+  // the peers' chains.  Stream order puts those stores before this kernel; the system-scope fence
+  // and release store publish them, the acquire loads of the waiting side order its next level
+  // behind them.
+  __global__ void peer_barrier_kernel(PeerFlags flags, int rank, int world, uint32_t epoch)
   {
+    int r = threadIdx.x;
+    if (r >= world)
+      return;
+
     __threadfence_system();
-    if ((int)threadIdx.x < s.count)
-      asm volatile("red.release.sys.global.add.u32 [%0], 1;" :: "l"(s.arrive[threadIdx.x]) : "memory");
+
+    uint32_t *theirs = flags.ptr[r] + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(theirs), "r"(epoch) : "memory");
+
+    uint32_t const *mine = flags.ptr[rank] + r;
+    long long start = clock64();
+    for(;;)
+    {
+      uint32_t seen;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+      if ((int)(seen - epoch) >= 0)
+        break;
+      if (clock64() - start > 20000000000ll)   // ~10 s: a peer is gone; fail the context instead of hanging the GPU
+        __trap();
+      __nanosleep(200);
+    }
   }
 
-  cudaError_t launch_peer_signal(PeerSignal const &s, cudaStream_t stream)
+  cudaError_t launch_peer_barrier(PeerFlags const &flags, int rank, int world, uint32_t epoch, cudaStream_t stream)
   {
-    peer_signal_kernel<<<1, 32, 0, stream>>>(s);
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(flags, rank, world, epoch);
     return cudaGetLastError();
   }
 
   // ---- host-side launchers ---------------------------------------------------------------
 
-  cudaError_t launch_build_dn_records(uint32_t const *src, uint4 *rec, int ws, int hs, int probes, size_t src_stride, int *counters, int ncounters, int sm_count, cudaStream_t stream)
+  cudaError_t launch_build_dn_records(uint32_t const *src, uint4 *rec, int ws, int hs, int *counters, int ncounters, int sm_count, cudaStream_t stream)
   {
-    if (probes < 1)
-      probes = 1;
-
-    size_t level = (size_t)6 * ws * hs;          // < 2^32 for every face size a chain can have (6 * 16384^2 would not fit HBM as records)
-    size_t blocks = (level + 255) / 256;
-    size_t cap = ((size_t)sm_count * 8 + probes - 1) / probes;
+    size_t total = (size_t)6 * ws * hs;
+    size_t blocks = (total + 255) / 256;
+    size_t cap = (size_t)sm_count * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
     if (grid < 1)
       grid = 1;
 
-    build_dn_records_kernel<<<dim3(grid, probes), 256, 0, stream>>>(src, rec, ws, hs, src_stride, counters, ncounters);
+    build_dn_records_kernel<<<grid, 256, 0, stream>>>(src, rec, ws, hs, counters, ncounters);
 
     return cudaGetLastError();
   }
 
   namespace
   {
-    // Resident CTAs per SM of one kernel for one dynamic shared-memory size, remembered per (kernel,
-    // device, size): the occupancy query costs more host time than the launch itself.  Every kernel
-    // instantiation here has the same function-pointer type, so the kernel's ADDRESS is part of the key
-    // (round 1 keyed by size only: a hit recorded by one kernel skipped the opt-in of another).  The
-    // dynamic shared-memory opt-in is only ever raised, and only above the 48 KB every kernel may use
-    // without it: setting the attribute to a smaller value would LOWER the kernel's limit.
-    cudaError_t resident_ctas(void (*kernel)(PrefilterDnParams), int threads, size_t smem, int *resident)
+    // dynamic shared memory opt-in + resident CTAs per SM of one kernel instantiation, remembered per
+    // (device, shared-memory size): the two runtime calls cost more host time than the launch itself
+    template<typename Kernel>
+    cudaError_t resident_ctas(Kernel kernel, int threads, size_t smem, int *resident)
     {
-      struct Entry { void (*kernel)(PrefilterDnParams); int device; size_t smem; int resident; };
-      thread_local static std::vector<Entry> cache;
-      struct OptIn { void (*kernel)(PrefilterDnParams); int device; size_t smem; };
-      thread_local static std::vector<OptIn> opted;
+      struct Entry { int device; size_t smem; int resident; };
+      thread_local static Entry cache[8] = {};
+      thread_local static int used = 0;
+      thread_local static size_t opted_in[16] = {};      // per device: the opt-in only ever grows
 
       int device = 0;
       cudaError_t err = cudaGetDevice(&device);
       if (err != cudaSuccess)
         return err;
 
-      for(auto const &e : cache)
-        if (e.kernel == kernel && e.device == device && e.smem == smem)
+      for(int i = 0; i < used; ++i)
+        if (cache[i].device == device && cache[i].smem == smem)
         {
-          *resident = e.resident;
+          *resident = cache[i].resident;
           return cudaSuccess;
         }
 
-      if (smem > 48 * 1024)
+      if (device < 0 || device >= 16 || smem > opted_in[device])
       {
-        OptIn *mine = nullptr;
-        for(auto &o : opted)
-          if (o.kernel == kernel && o.device == device)
-            mine = &o;
-
-        if (!mine || mine->smem < smem)
-        {
-          err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          if (err != cudaSuccess)
-            return err;
-          if (mine)
-            mine->smem = smem;
-          else
-            opted.push_back(OptIn{ kernel, device, smem });
-        }
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess)
+          return err;
+        if (device >= 0 && device < 16)
+          opted_in[device] = smem;
       }
 
       err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(resident, kernel, threads, smem);
@@ -1128,9 +984,10 @@ namespace ibl
       if (*resident < 1)
         return cudaErrorLaunchOutOfResources;
 
-      if (cache.size() >= 256)
-        cache.clear();
-      cache.push_back(Entry{ kernel, device, smem, *resident });
+      // when the table is full overwrite round-robin
+      cache[used < 8 ? used : (int)(smem % 8)] = Entry{ device, smem, *resident };
+      if (used < 8)
+        used += 1;
 
       return cudaSuccess;
     }
@@ -1172,18 +1029,15 @@ namespace ibl
 
   namespace
   {
-    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false>
+    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0, int DEPTH = 1>
     cudaError_t launch_dp(PrefilterDnParams p, int sm_count, cudaStream_t stream, int *launched_grid)
     {
-      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU, DEPTH, RHI, PLAIN_QUEUE, LEAN>;
+      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU, DEPTH>;
 
       int rows = p.row_end - p.row_begin;
       int tiles_x = (p.wd + 7) / 8, tiles_y = (rows + 3) / 4;
       p.blocks_x = (tiles_x + 3) / 4;
-      p.tiles_per_probe = p.blocks_x * ((tiles_y + 3) / 4) * 16;
-      if (p.probes < 1)
-        p.probes = 1;
-      p.tiles = p.tiles_per_probe * p.probes;
+      p.tiles = p.blocks_x * ((tiles_y + 3) / 4) * 16;
 
       size_t smem = (SMEM_TABLE ? (size_t)p.bands * kSampleBand * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
 
@@ -1192,15 +1046,10 @@ namespace ibl
       if (err != cudaSuccess)
         return err;
 
-      const int slots = sm_count * resident;
-
-      int grid = p.tiles < slots ? p.tiles : slots;
+      int grid = p.tiles < sm_count * resident ? p.tiles : sm_count * resident;
       if (grid < 1)
         grid = 1;
 
-      // queues: 7/8 of the tiles in per-SM chunks, the rest in the common pool that evens out the end of
-      // the launch.  (Cutting the pool's tiles, or every tile of a slab too small to fill the machine,
-      // into 2-8 shares of their bands was measured and dropped: profiles/r2_summary.md.)
       p.queues = sm_count;
       p.chunk = (p.tiles - p.tiles / 8) / sm_count;
       p.queued = p.chunk * sm_count;
@@ -1220,17 +1069,6 @@ namespace ibl
     }
   }
 
-  // slabs of at least this many texels take their tiles from per-SM queues
-  constexpr size_t kQueuedTexels = 32u * 148u * 8u;
-
-  bool prefilter_batchable(int ws, int hs)
-  {
-    PrefilterDnParams p = {};
-    p.geom = make_level_geom(ws, hs);
-    p.table_pairs = reinterpret_cast<float4 const*>(&p);     // any non-null value: only the geometry decides
-    return pair_kernel_usable(p);
-  }
-
   cudaError_t launch_prefilter_dn(PrefilterDnParams const &p, int variant, int sm_count, cudaStream_t stream, int *launched_grid)
   {
     int rows = p.row_end - p.row_begin;
@@ -1247,18 +1085,11 @@ namespace ibl
       // the two biggest classes work on two samples at a time (prefilter_dp_kernel; measured on C2:
       // level 1 885 -> 862 us, level 2 277 -> 262, level 3 96 -> 88); launch_prefilter_dn falls back to
       // the one-sample kernel when the biased record index could wrap
-      // Warps per tile follow ONE probe's slab (they decide the order of the sums: a batch must give the
-      // words of single calls), the tile queues follow the whole launch.
-      if (texels >= kQueuedTexels)
+      if (texels >= 32u * 148u * 8u)
         variant = big_table ? 71 : 70;
-      else if (texels * (size_t)(p.probes > 1 ? p.probes : 1) >= kQueuedTexels)
-        variant = big_table ? 91 : 90;
       else
         variant = big_table ? 73 : 72;      // slabs of at most kTailTexels never get here (prefilter_tail_kernel)
     }
-
-    if (p.probes > 1 && !(variant >= 70 && variant <= 99 && pair_kernel_usable(p)))
-      return cudaErrorNotSupported;         // batches run on the pair kernel only (the caller checks prefilter_batchable)
 
     // two samples at a time; when the biased index could wrap, the same shape one sample at a time
     if (variant >= 81 && variant <= 86 && !pair_kernel_usable(p))
@@ -1266,38 +1097,18 @@ namespace ibl
 
     if (variant >= 70 && variant <= 79 && !pair_kernel_usable(p))
     {
-      static const int fallback[10] = { 51, 52, 53, 54, 51, 51, 51, 51, 51, 53 };
+      static const int fallback[10] = { 51, 52, 53, 54, 50, 51, 51, 51, 51, 53 };
       variant = fallback[variant - 70];
     }
 
-    const bool lean = p.probes <= 1 && p.signal.count == 0;
-
     switch (variant)
     {
-      // the shapes the library picks by itself (and the one-sample forms they hand over to)
       //                        NW MINB SMEM  QUEUES
-      // LEAN = no batch / peer-signal code in the kernel (single probe on one GPU: the common case; the
-      // feature code costs ~1 % of a level through register allocation alone, profiles/r2_summary.md)
-      case 70: return lean ? launch_dp<4, 8, true, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid) : launch_dp<4, 8, true, true>(p, sm_count, stream, launched_grid);
-      case 71: return lean ? launch_dp<4, 8, false, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid) : launch_dp<4, 8, false, true>(p, sm_count, stream, launched_grid);
-      case 72: return lean ? launch_dp<8, 4, true, false, 0, 1, false, false, true>(p, sm_count, stream, launched_grid) : launch_dp<8, 4, true, false>(p, sm_count, stream, launched_grid);
-      case 73: return lean ? launch_dp<8, 4, false, false, 0, 1, false, false, true>(p, sm_count, stream, launched_grid) : launch_dp<8, 4, false, false>(p, sm_count, stream, launched_grid);
-      case 90: return launch_dp<8, 4, true, true>(p, sm_count, stream, launched_grid);     // several probes' small slabs in one launch
-      case 91: return launch_dp<8, 4, false, true>(p, sm_count, stream, launched_grid);
-      //                        NW UNR MINB SMEM  QUEUES
-      case 51: return launch_dn<4, 4, 8, true, true>(p, sm_count, stream, launched_grid);
-      case 52: return launch_dn<4, 4, 8, false, true>(p, sm_count, stream, launched_grid);
-      case 53: return launch_dn<8, 2, 4, true, false>(p, sm_count, stream, launched_grid);
-      case 54: return launch_dn<8, 2, 4, false, false>(p, sm_count, stream, launched_grid);
-
-#ifdef DATUM_IBL_AB_VARIANTS
-      // A/B shapes of the tuning history (profiles/): only in the tools build (datum_b200.build --ab)
+      case 70: return launch_dp<4, 8, true, true>(p, sm_count, stream, launched_grid);
+      case 71: return launch_dp<4, 8, false, true>(p, sm_count, stream, launched_grid);
+      case 72: return launch_dp<8, 4, true, false>(p, sm_count, stream, launched_grid);
+      case 73: return launch_dp<8, 4, false, false>(p, sm_count, stream, launched_grid);
       case 74: return launch_dp<4, 8, true, false>(p, sm_count, stream, launched_grid);
-      case 87: return launch_dp<4, 8, true, true, 0, 1, true>(p, sm_count, stream, launched_grid);    // r mantissa through IMAD.HI
-      case 88: return launch_dp<8, 4, true, false, 0, 1, true>(p, sm_count, stream, launched_grid);
-      case 92: return launch_dp<4, 8, true, true, 0, 1, false, true>(p, sm_count, stream, launched_grid);   // round 1's tile hand-out (one thread, no stealing)
-      case 93: return launch_dp<4, 8, true, true, 0, 1, false, true, true>(p, sm_count, stream, launched_grid);   // ... and no batch / peer-signal code
-      case 94: return launch_dp<4, 8, true, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid);  // stealing hand-out, no batch / peer-signal code
       case 75: return launch_dp<4, 8, true, true, 1>(p, sm_count, stream, launched_grid);
       case 76: return launch_dp<4, 8, true, true, 2>(p, sm_count, stream, launched_grid);
       case 77: return launch_dp<4, 8, true, true, 3>(p, sm_count, stream, launched_grid);
@@ -1309,7 +1120,12 @@ namespace ibl
       case 84: return launch_dp<4, 6, true, true, 0, 2>(p, sm_count, stream, launched_grid);
       case 85: return launch_dp<4, 8, true, true, 0, 2>(p, sm_count, stream, launched_grid);
       case 86: return launch_dp<4, 5, true, true, 0, 2>(p, sm_count, stream, launched_grid);
+      //                        NW UNR MINB SMEM  QUEUES
       case 50: return launch_dn<4, 4, 8, true, false>(p, sm_count, stream, launched_grid);
+      case 51: return launch_dn<4, 4, 8, true, true>(p, sm_count, stream, launched_grid);
+      case 52: return launch_dn<4, 4, 8, false, true>(p, sm_count, stream, launched_grid);
+      case 53: return launch_dn<8, 2, 4, true, false>(p, sm_count, stream, launched_grid);
+      case 54: return launch_dn<8, 2, 4, false, false>(p, sm_count, stream, launched_grid);
       case 55: return launch_dn<16, 1, 2, true, false>(p, sm_count, stream, launched_grid);
       case 56: return launch_dn<16, 1, 2, false, false>(p, sm_count, stream, launched_grid);
       case 57: return launch_dn<32, 1, 1, true, false>(p, sm_count, stream, launched_grid);
@@ -1320,7 +1136,6 @@ namespace ibl
       case 63: return launch_dn<4, 2, 8, true, true>(p, sm_count, stream, launched_grid);
       case 64: return launch_dn<8, 2, 5, true, true>(p, sm_count, stream, launched_grid);
       case 65: return launch_dn<4, 4, 10, true, true>(p, sm_count, stream, launched_grid);
-#endif
       default: return cudaErrorInvalidValue;
     }
   }
