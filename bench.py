@@ -493,6 +493,22 @@ def config_c5(job, ctx, engine, stream):
 
     peer_sh = ibl_dist.PeerSh9(ctx)
     ms_peers = job.timed(stream, lambda: peer_sh.enqueue(cube, datum_b200.FORMAT_F32, w, w), reps=10)
+
+    # A single projection timed from a host barrier also carries the launch skew between the ranks (tens of
+    # microseconds, as much as the kernel itself at 8 GPUs): K projections queued back to back — the
+    # arrival counters keep the ranks in step, the two result arrays alternate — give the per-projection time
+    K = 20
+
+    def burst_peers():
+        for _ in range(K):
+            peer_sh.enqueue(cube, datum_b200.FORMAT_F32, w, w)
+
+    def burst_nccl():
+        for _ in range(K):
+            project()
+
+    ms_peers_burst = job.timed(stream, burst_peers, reps=3) / K
+    ms_nccl_burst = job.timed(stream, burst_nccl, reps=3) / K if world > 1 else ms_peers_burst
     sh_peers = peer_sh.project(cube, datum_b200.FORMAT_F32, w, w)
     peer_sh.close()
 
@@ -510,6 +526,8 @@ def config_c5(job, ctx, engine, stream):
         "workload": "C5: SH9 projection (data/project.comp) of one 4096^2-face RGBA32F cube (1.007e8 texels, 1.61 GB), %d rows per GPU on %d GPU(s)" % (rows, world),
         "texels": 6 * w * w, "ms": ms, "texels_per_s": 6 * w * w / ms * 1e3,
         "ms_peer_stores": ms_peers, "ms_nccl_all_reduce": ms_nccl, "ms_kernel_only": ms_kernel,
+        "ms_per_projection_back_to_back": min(ms_peers_burst, ms_nccl_burst), "ms_per_projection_back_to_back_peer_stores": ms_peers_burst, "ms_per_projection_back_to_back_nccl": ms_nccl_burst,
+        "timing": "ms / ms_peer_stores / ms_nccl_all_reduce: ONE projection from a host barrier (includes the ranks' launch skew); ms_per_projection_back_to_back: %d projections queued back to back, per projection" % K,
         "exchange": "28 doubles per rank: peer stores from the projection kernel's last block + arrival counters, or one NCCL all-reduce",
         "hbm_gb_per_s_per_gpu_kernel": gbs, "hbm_frac_of_measured_kernel": gbs / hbm, "hbm_peak": hbm, "hbm_peak_source": hbm_source,
         "max_rel_vs_oracle": err_peers, "max_rel_vs_oracle_nccl": err_nccl,
