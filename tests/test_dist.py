@@ -168,3 +168,59 @@ def test_two_gpus_split_one_probe_over_nccl(tmp_path, ctx):
         peer = np.load(tmp_path / ("sh_peer_%d.npy" % rank))
         assert np.abs(peer - want_sh).max() <= 1e-4 * np.abs(want_sh).max()
     assert np.array_equal(np.load(tmp_path / "sh_peer_0.npy"), np.load(tmp_path / "sh_peer_1.npy"))   # rows added in rank order on every rank
+
+
+# ---- two PROCESSES sharing one GPU: the IPC path of PeerChain / PeerSh9 on a one-GPU box ----------
+
+def _ipc_worker(rank, world, port, w, levels, samples, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # plumbing only: the 64-byte IPC handles
+    try:
+        import datum_b200
+        torch.cuda.set_device(0)
+        ctx = datum_b200.IblContext(0)
+        ctx.set_peer_timeout_ms(30000)
+        shared = ibl_dist.PeerChain(ctx, w, w, levels)
+        for probe in (45, 43):
+            with torch.cuda.stream(ctx.torch_stream()):
+                shared.chain.copy_(torch.from_numpy(synth.synthetic_chain(w, w, levels, probe=probe).view(np.int32)), non_blocking=False)
+                shared.bake(samples)
+                fused = shared.chain.clone()
+            ctx.synchronize()
+        np.save(os.path.join(out_dir, "ipc_chain_%d.npy" % rank), fused.cpu().numpy().view(np.uint32))
+        shared.close()
+
+        cube = torch.from_numpy(synth.synthetic_cube(128, 128, probe=44)).to("cuda:0")
+        peer_sh = ibl_dist.PeerSh9(ctx)
+        peer_sh.project(torch.from_numpy(synth.synthetic_cube(128, 128, probe=46)).to("cuda:0"), FORMAT_F32, 128, 128)
+        np.save(os.path.join(out_dir, "ipc_sh_%d.npy" % rank), peer_sh.project(cube, FORMAT_F32, 128, 128))
+        peer_sh.close()
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_processes_on_one_gpu_share_a_probe_through_ipc(tmp_path, ctx):
+    """The multi-process shared-probe path (payloads mapped through CUDA IPC handles, slabs stored into the
+    peer's payload by the prefilter kernel, arrival counters + stream waits) with BOTH ranks on cuda:0: what a
+    one-GPU box can run of `bench.py --gpus N`'s config 3 / 5 machinery.  Two GPUs run the same through NCCL
+    and NVLink in test_two_gpus_split_one_probe_over_nccl."""
+    w, levels, samples = 192, 7, 256
+    mp.spawn(_ipc_worker, args=(2, free_port(), w, levels, samples, str(tmp_path)), nprocs=2, join=True)
+
+    want = synth.synthetic_chain(w, w, levels, probe=43)
+    ctx.image_buildmips_cube_ibl(w, w, levels, want, samples)
+    a, b = np.load(tmp_path / "ipc_chain_0.npy"), np.load(tmp_path / "ipc_chain_1.npy")
+    assert np.array_equal(a, b)                                    # both ranks hold the same complete chain
+    offs = level_offsets(w, w, levels)
+    assert np.array_equal(a[: offs[1]], want[: offs[1]])
+    stats = oracle_lib.word_stats(a[offs[1]:], want[offs[1]:])
+    assert oracle_lib.words_within_one_code(stats, 0.995), stats
+
+    cube = synth.synthetic_cube(128, 128, probe=44)
+    want_sh = oracle_lib.project_sh9(cube, FORMAT_F32, 128, 128)
+    sh0, sh1 = np.load(tmp_path / "ipc_sh_0.npy"), np.load(tmp_path / "ipc_sh_1.npy")
+    assert np.array_equal(sh0, sh1)
+    assert np.abs(sh0 - want_sh).max() <= 1e-4 * np.abs(want_sh).max()
