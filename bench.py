@@ -27,6 +27,8 @@ HBM copy bandwidth; `cpu_baseline` is the unmodified reference tools/ibl.cpp
   C4  256 probes of 256^2 x 8 levels x 1024 spp + SH9, probe p on rank p % N, no collective;
   C5  SH9 of one 4096^2 RGBA32F cube, rows split, 28 partial sums exchanged (NCCL all-reduce
       and peer stores).
+  C3_one_process (N > 1)  config 3 again through the device-list entry point: rank 0 alone, after the
+      other ranks have left, drives all N GPUs from one process (datum_ibl_multi_*), host buffers in and out.
 """
 
 import argparse
@@ -405,6 +407,42 @@ def config_c3(job, ctx, engine, stream):
     return out
 
 
+def config_c3_one_process(job, ctx):
+    """Config 3 through the device-list entry point: ONE process (this rank, after the others have left)
+    drives all the GPUs of the job — what DATUM_IBL_DEVICES gives a single-process assetbuilder.  End to end
+    from a pinned host payload: level 0 up once and copied GPU to GPU, the chain back from the first GPU."""
+    import datum_b200
+    from datum_b200 import synth
+
+    torch, world = job.torch, job.world
+    w, levels, samples = 2048, 12, 4096
+    offs = datum_b200.level_offsets(w, w, levels)
+    source = synth.synthetic_chain(w, w, levels, probe=3)
+
+    alone = torch.from_numpy(source.view(np.int32).copy()).pin_memory()
+    ctx.image_buildmips_cube_ibl(w, w, levels, alone, samples)
+    t0 = time.perf_counter()
+    ctx.image_buildmips_cube_ibl(w, w, levels, alone, samples)
+    ms_alone = (time.perf_counter() - t0) * 1e3
+
+    shared = torch.from_numpy(source.view(np.int32).copy()).pin_memory()
+    with datum_b200.MultiContext(list(range(world))) as multi:
+        multi.image_buildmips_cube_ibl(w, w, levels, shared, samples)         # allocations, tables and peer mappings on every device
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            multi.image_buildmips_cube_ibl(w, w, levels, shared, samples)
+            best = min(best, (time.perf_counter() - t0) * 1e3)
+
+    same = float((shared.numpy() == alone.numpy()).mean())
+    return {
+        "workload": "C3 from ONE process: datum_ibl_multi_buildmips_cube_ibl over devices 0..%d, pinned host payload in and out (100.7 MB up, 33.5 MB down)" % (world - 1),
+        "ms_e2e": best, "ms_e2e_one_gpu": ms_alone, "speedup_e2e_vs_one_gpu": ms_alone / best,
+        "texel_samples_per_s_e2e": texel_samples(w, levels, samples) / best * 1e3,
+        "words_identical_to_one_gpu": same, "parity_ok": bool(same >= 0.999),
+    }
+
+
 def config_c4(job, ctx):
     import datum_b200
     import oracle_lib
@@ -743,12 +781,22 @@ def run_ours(args):
         attempt("C3", lambda: config_c3(job, ctx, engine, stream))
         if world == 1 and args.steps >= 5:
             attempt("C1", lambda: config_c1(job, ctx))
+
+        # the device-list path on the same GPUs: the other ranks leave first, then this process alone drives all of them
+        if world > 1:
+            job.barrier()
+            job.dist.destroy_process_group()      # every rank together; nothing below is collective
+            if rank != 0:
+                watchdog.cancel()
+                return 0
+            time.sleep(1.0)                       # the other processes release their contexts
+            attempt("C3_one_process", lambda: config_c3_one_process(job, ctx))
         watchdog.cancel()
 
     if rank == 0:
         emit()
 
-    if world > 1:
+    if world > 1 and job.dist.is_initialized():
         job.dist.destroy_process_group()
     return 0
 
