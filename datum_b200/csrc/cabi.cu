@@ -24,6 +24,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -855,6 +856,8 @@ extern "C"
       cudaError_t state;
       while ((state = cudaStreamQuery(ctx->stream)) == cudaErrorNotReady)
       {
+        std::this_thread::yield();
+
         if (std::chrono::steady_clock::now() > deadline)
         {
           const unsigned int release[2] = { 0x40000000u, 0x40000000u };

@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -228,7 +229,12 @@ extern "C"
       if (err == cudaSuccess)
         err = cudaEventRecord(uploaded, streams[0]);
       if (err != cudaSuccess)
+      {
+        if (uploaded)
+          cudaEventDestroy(uploaded);
+        cudaStreamSynchronize(streams[0]);           // nothing may keep reading the caller's payload
         return fail_cuda("datum_ibl_multi_buildmips_cube_ibl: upload", err);
+      }
     }
 
     int failed = 0;
@@ -454,6 +460,8 @@ extern "C"
     datum_ibl_multi *cached_multi(int ndev, int const *devices)
     {
       static std::vector<datum_ibl_multi*> cache;
+      static std::mutex guard;                       // the cache may be reached from several threads; a handle still serves one caller at a time
+      std::lock_guard<std::mutex> lock(guard);
 
       if (ndev < 1 || !devices)
       {

@@ -410,6 +410,13 @@ class MultiContext:
             self._lib.datum_ibl_multi_destroy(self._handle)
             self._handle = None
 
+    def __del__(self):
+        try:
+            if not sys.is_finalizing():
+                self.close()
+        except Exception:
+            pass
+
     def __enter__(self):
         return self
 
