@@ -123,6 +123,9 @@ struct datum_ibl_ctx
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // created on first use by datum_ibl_bake_probes
   cudaEvent_t ev_uploaded[2] = { nullptr, nullptr }, ev_computed[2] = { nullptr, nullptr }, ev_downloaded[2] = { nullptr, nullptr };
   cudaEvent_t ev_level[16] = {};  // level L of the current chain is complete (its download starts behind it)
+  cudaEvent_t ev_copied[16] = {}; // level L has arrived in host memory (pageable callers: in the pinned staging)
+  void *host_stage = nullptr;     // pinned staging between the device and a caller's PAGEABLE payload
+  size_t host_stage_bytes = 0;
   DeviceBuffer<uint4> records;    // quad records of the current source level
   DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
   int prefilter_no_steal = 0;
@@ -604,12 +607,161 @@ namespace
         err = cudaEventCreateWithFlags(&ctx->ev_downloaded[k], cudaEventDisableTiming);
     }
     for(int k = 0; k < 16 && err == cudaSuccess; ++k)
+    {
       err = cudaEventCreateWithFlags(&ctx->ev_level[k], cudaEventDisableTiming);
+      if (err == cudaSuccess)
+        err = cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming);
+    }
 
     if (err != cudaSuccess)
       return fail_cuda("copy streams", err);
 
     return 0;
+  }
+
+  // ---- pageable caller buffers -------------------------------------------------------------------
+  //
+  // tools/assetbuilder.cpp hands over a plain std::vector<char> (:439, :484).  cudaMemcpyAsync from or to
+  // pageable memory is staged by the driver on the calling thread and blocks it: the upload runs at one
+  // core's memcpy speed and every level's download stalls the launches behind it (2.17 ms instead of
+  // 1.45 ms per 512^2 x 8 bake).  Here pageable payloads go through a pinned staging buffer of the
+  // context: the upload in four chunks, each copied by a few host threads and sent while the next one
+  // is being copied; the downloads asynchronously like a pinned caller's, each level moved on to the
+  // caller's memory as soon as it has arrived, while the later levels are still being computed.
+
+  bool host_is_pinned(void const *ptr)
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return false;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+  }
+
+  int reserve_host_stage(datum_ibl_ctx *ctx, size_t bytes)
+  {
+    if (bytes <= ctx->host_stage_bytes)
+      return 0;
+
+    if (ctx->host_stage)
+    {
+      cudaStreamSynchronize(ctx->stream);
+      if (ctx->copy_out)
+        cudaStreamSynchronize(ctx->copy_out);
+      cudaFreeHost(ctx->host_stage);
+      ctx->host_stage = nullptr;
+      ctx->host_stage_bytes = 0;
+    }
+
+    cudaError_t err = cudaHostAlloc(&ctx->host_stage, bytes, cudaHostAllocDefault);
+    if (err != cudaSuccess)
+      return fail_cuda("cudaHostAlloc(staging)", err);
+
+    ctx->host_stage_bytes = bytes;
+    return 0;
+  }
+
+  // memcpy on up to four host threads (one core moves ~10 GB/s, a payload level is megabytes)
+  void copy_parallel(void *dst, void const *src, size_t bytes)
+  {
+    size_t parts = bytes >= ((size_t)2 << 20) ? 4 : (bytes >= ((size_t)512 << 10) ? 2 : 1);
+    if (parts == 1)
+    {
+      std::memcpy(dst, src, bytes);
+      return;
+    }
+
+    size_t each = (bytes / parts + 63) & ~(size_t)63;
+    std::vector<std::thread> helpers;
+    for(size_t k = 1; k < parts; ++k)
+    {
+      size_t begin = k * each, end = std::min(bytes, begin + each);
+      if (begin < end)
+        helpers.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + begin, static_cast<char const*>(src) + begin, end - begin); });
+    }
+    std::memcpy(dst, src, std::min(bytes, each));
+    for(auto &t : helpers)
+      t.join();
+  }
+
+  // host -> device on the context's stream; a pageable source goes through `stage` (pinned, at least `bytes`):
+  // up to four host threads each own a contiguous share, copy it into the staging in two pieces and queue every
+  // piece's DMA behind its copy, so that the copies of one piece run under the DMA of another
+  cudaError_t upload_host(datum_ibl_ctx *ctx, void *d_dst, void const *src, size_t bytes, bool pinned, void *stage)
+  {
+    if (pinned)
+      return cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+
+    const size_t workers = bytes >= ((size_t)2 << 20) ? 4 : 1;
+    const size_t share = ((bytes + workers - 1) / workers + 255) & ~(size_t)255;
+    std::vector<cudaError_t> status(workers, cudaSuccess);
+
+    auto work = [&](size_t k)
+    {
+      cudaSetDevice(ctx->device);
+      size_t begin = k * share, end = std::min(bytes, begin + share);
+      size_t piece = ((end - begin) / 2 + 255) & ~(size_t)255;
+      for(size_t at = begin; at < end && piece > 0; at += piece)
+      {
+        size_t n = std::min(piece, end - at);
+        std::memcpy(static_cast<char*>(stage) + at, static_cast<char const*>(src) + at, n);
+        cudaError_t err = cudaMemcpyAsync(static_cast<char*>(d_dst) + at, static_cast<char*>(stage) + at, n, cudaMemcpyHostToDevice, ctx->stream);
+        if (err != cudaSuccess)
+        {
+          status[k] = err;
+          return;
+        }
+      }
+    };
+
+    std::vector<std::thread> helpers;
+    for(size_t k = 1; k < workers; ++k)
+      if (k * share < bytes)
+        helpers.emplace_back(work, k);
+    work(0);
+    for(auto &t : helpers)
+      t.join();
+
+    for(auto err : status)
+      if (err != cudaSuccess)
+        return err;
+
+    return cudaSuccess;
+  }
+
+  // levels [first, levels) of a chain have been sent to the staging by run_chain / send_level: move each on
+  // to the caller's pageable payload as soon as it has arrived
+  int drain_staged_levels(datum_ibl_ctx *ctx, int width, int height, int levels, int first, uint32_t *bits)
+  {
+    size_t offset = 0;
+    for(int level = 0; level < levels; ++level)
+    {
+      size_t count = (size_t)(width >> level) * (height >> level) * 6;
+      if (level >= first)
+      {
+        cudaError_t err = cudaEventSynchronize(ctx->ev_copied[level]);
+        if (err != cudaSuccess)
+          return fail_cuda("cudaEventSynchronize(level copied)", err);
+        copy_parallel(bits + offset, static_cast<uint32_t*>(ctx->host_stage) + offset, count * sizeof(uint32_t));
+      }
+      offset += count;
+    }
+    return 0;
+  }
+
+  // one finished level -> host (the caller's pinned payload or the staging), behind the compute stream
+  cudaError_t send_level(datum_ibl_ctx *ctx, int level, uint32_t *host_dst, uint32_t const *d_src, size_t count)
+  {
+    cudaError_t err = cudaEventRecord(ctx->ev_level[level], ctx->stream);
+    if (err == cudaSuccess)
+      err = cudaStreamWaitEvent(ctx->copy_out, ctx->ev_level[level], 0);
+    if (err == cudaSuccess)
+      err = cudaMemcpyAsync(host_dst, d_src, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_out);
+    if (err == cudaSuccess)
+      err = cudaEventRecord(ctx->ev_copied[level], ctx->copy_out);
+    return err;
   }
 
   // `host_bits` (optional): the caller's payload; every computed level is copied into it on the
@@ -641,11 +793,7 @@ namespace
 
       if (host_bits)
       {
-        cudaError_t err = cudaEventRecord(ctx->ev_level[level], ctx->stream);
-        if (err == cudaSuccess)
-          err = cudaStreamWaitEvent(ctx->copy_out, ctx->ev_level[level], 0);
-        if (err == cudaSuccess)
-          err = cudaMemcpyAsync(host_bits + (dst - d_bits), dst, outcount * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_out);
+        cudaError_t err = send_level(ctx, level, host_bits + (dst - d_bits), dst, outcount);
         if (err != cudaSuccess)
           return fail_cuda("cudaMemcpyAsync(level)", err);
       }
@@ -661,6 +809,48 @@ namespace
 
     cudaEventRecord(ctx->ev_end, ctx->stream);
     ctx->timed = true;
+
+    return 0;
+  }
+}
+
+namespace
+{
+  // Level 0 is already in ctx->chain (six-image ingest, equirect pack): send it home at once — it travels
+  // under the level-1 kernels — then the chain with every level following as soon as it is complete.
+  // `bits` receives the whole payload; pageable payloads go through the pinned staging.
+  int finish_chain_to_host(datum_ibl_ctx *ctx, int width, int height, int levels, int samples, void *bits, const char *who)
+  {
+    size_t words = datum_ibl_chain_bytes(width, height, levels) / sizeof(uint32_t);
+    size_t level0 = (size_t)width * height * 6;
+
+    if (ensure_pipeline(ctx))
+      return 1;
+
+    const bool pinned = host_is_pinned(bits);
+    if (!pinned && reserve_host_stage(ctx, words * sizeof(uint32_t)))
+      return 1;
+
+    uint32_t *host = pinned ? static_cast<uint32_t*>(bits) : static_cast<uint32_t*>(ctx->host_stage);
+
+    int failed = 0;
+    cudaError_t err = send_level(ctx, 0, host, ctx->chain.ptr, level0);
+    if (err != cudaSuccess)
+      failed = fail_cuda("cudaMemcpyAsync(level 0)", err);
+
+    if (!failed)
+      failed = run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr, host);
+
+    if (!failed && !pinned)
+      failed = drain_staged_levels(ctx, width, height, levels, 0, static_cast<uint32_t*>(bits));
+
+    // also after a failure: nothing may stay in flight that writes the caller's payload
+    err = cudaStreamSynchronize(ctx->stream);
+    cudaError_t err2 = cudaStreamSynchronize(ctx->copy_out);
+    if (failed)
+      return 1;
+    if (err != cudaSuccess || err2 != cudaSuccess)
+      return fail_cuda(who, err != cudaSuccess ? err : err2);
 
     return 0;
   }
@@ -814,7 +1004,12 @@ extern "C"
       if (ctx->ev_downloaded[k]) cudaEventDestroy(ctx->ev_downloaded[k]);
     }
     for(int k = 0; k < 16; ++k)
+    {
       if (ctx->ev_level[k]) cudaEventDestroy(ctx->ev_level[k]);
+      if (ctx->ev_copied[k]) cudaEventDestroy(ctx->ev_copied[k]);
+    }
+    if (ctx->host_stage)
+      cudaFreeHost(ctx->host_stage);
     ctx->records.release();
     ctx->queue_heads.release();
     ctx->peer_ticket.release();
@@ -952,11 +1147,27 @@ extern "C"
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(chain)", err);
 
-    err = cudaMemcpyAsync(ctx->chain.ptr, bits, level0 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (err != cudaSuccess)
-      return fail_cuda("cudaMemcpyAsync(level 0)", err);
+    if (ensure_pipeline(ctx))
+      return 1;
 
-    int failed = run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr, (uint32_t*)bits);
+    // a pageable payload (assetbuilder's std::vector<char>) goes through the context's pinned staging
+    const bool pinned = host_is_pinned(bits);
+    if (!pinned && reserve_host_stage(ctx, words * sizeof(uint32_t)))
+      return 1;
+
+    uint32_t *host = pinned ? static_cast<uint32_t*>(bits) : static_cast<uint32_t*>(ctx->host_stage);
+
+    err = upload_host(ctx, ctx->chain.ptr, bits, level0 * sizeof(uint32_t), pinned, ctx->host_stage);
+    if (err != cudaSuccess)
+    {
+      cudaStreamSynchronize(ctx->stream);
+      return fail_cuda("cudaMemcpyAsync(level 0)", err);
+    }
+
+    int failed = run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr, host);
+
+    if (!failed && !pinned)
+      failed = drain_staged_levels(ctx, width, height, levels, 1, static_cast<uint32_t*>(bits));
 
     // also after a failure: nothing may stay in flight that reads or writes the caller's payload
     err = cudaStreamSynchronize(ctx->stream);
@@ -1459,9 +1670,17 @@ extern "C"
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(staging)", err);
 
-    err = cudaMemcpyAsync(ctx->staging.ptr, pixels, image_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    // HDRImage::bits is a std::vector: pageable, through the pinned staging in chunks (see upload_host)
+    const bool pinned = host_is_pinned(pixels);
+    if (!pinned && reserve_host_stage(ctx, image_bytes))
+      return 1;
+
+    err = upload_host(ctx, ctx->staging.ptr, pixels, image_bytes, pinned, ctx->host_stage);
     if (err != cudaSuccess)
+    {
+      cudaStreamSynchronize(ctx->stream);
       return fail_cuda("cudaMemcpyAsync(image)", err);
+    }
 
     ibl::ResampleParams p = {};
     p.image = reinterpret_cast<float4 const *>(ctx->staging.ptr);
@@ -1531,18 +1750,14 @@ extern "C"
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(chain)", err);
 
+    if (!host_is_pinned(bits) && reserve_host_stage(ctx, std::max(words * sizeof(uint32_t), (size_t)imgwidth * imgheight * sizeof(float4))))     // before the upload uses it
+      return 1;
+
     // tools/ibl.cpp:285, 287
     if (pack_cube_to_device(ctx, imgwidth, imgheight, pixels, width, height, ctx->chain.ptr))
       return 1;
 
-    if (run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr))
-      return 1;
-
-    err = cudaMemcpyAsync(bits, ctx->chain.ptr, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
-    if (err == cudaSuccess)
-      err = cudaStreamSynchronize(ctx->stream);
-
-    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_pack_cube_ibl", err);
+    return finish_chain_to_host(ctx, width, height, levels, samples, bits, "datum_ibl_pack_cube_ibl");
   }
 
   // ---- six ARGB32 face images -> level 0 (+ chain) -------------------------------------
@@ -1575,9 +1790,17 @@ extern "C"
       if (err != cudaSuccess)
         return fail_cuda("cudaMalloc(staging)", err);
 
-      err = cudaMemcpyAsync(ctx->staging.ptr, argb, level0 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+      // QImage::bits() is pageable memory: through the pinned staging in chunks (see upload_host)
+      const bool pinned = host_is_pinned(argb);
+      if (!pinned && reserve_host_stage(ctx, level0 * sizeof(uint32_t)))
+        return 1;
+
+      err = upload_host(ctx, ctx->staging.ptr, argb, level0 * sizeof(uint32_t), pinned, ctx->host_stage);
       if (err != cudaSuccess)
+      {
+        cudaStreamSynchronize(ctx->stream);
         return fail_cuda("cudaMemcpyAsync(argb)", err);
+      }
 
       err = ibl::launch_ingest_argb32((uint32_t const*)ctx->staging.ptr, ctx->srgb_lut.ptr, width, height, d_level0, ctx->sm_count, ctx->stream);
       if (err != cudaSuccess)
@@ -1628,18 +1851,14 @@ extern "C"
     if (err != cudaSuccess)
       return fail_cuda("cudaMalloc(chain)", err);
 
+    if (!host_is_pinned(bits) && reserve_host_stage(ctx, words * sizeof(uint32_t)))     // before the upload uses it
+      return 1;
+
     // tools/assetbuilder.cpp:443-462, then :465
     if (ingest_to_device(ctx, width, height, argb, ctx->chain.ptr))
       return 1;
 
-    if (run_chain(ctx, width, height, levels, samples, ctx->chain.ptr, nullptr))
-      return 1;
-
-    err = cudaMemcpyAsync(bits, ctx->chain.ptr, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
-    if (err == cudaSuccess)
-      err = cudaStreamSynchronize(ctx->stream);
-
-    return err == cudaSuccess ? 0 : fail_cuda("datum_ibl_ingest_cube_argb32_ibl", err);
+    return finish_chain_to_host(ctx, width, height, levels, samples, bits, "datum_ibl_ingest_cube_argb32_ibl");
   }
 
   // ---- LUTs -----------------------------------------------------------------------
