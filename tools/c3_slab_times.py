@@ -7,6 +7,7 @@ import numpy as np, torch, datum_b200
 from datum_b200 import synth, dist as ibl_dist
 
 ctx = datum_b200.IblContext(0)
+variant = int(os.environ.get("IBL_VARIANT", "0"))
 w, levels, samples = int(os.environ.get("IBL_W", "2048")), int(os.environ.get("IBL_LEVELS", "12")), int(os.environ.get("IBL_SAMPLES", "4096"))
 world = int(os.environ.get("IBL_WORLD", "8"))
 offs = datum_b200.level_offsets(w, w, levels)
@@ -26,6 +27,8 @@ def timed(fn, reps=3):
     return best
 
 
+ctx.set_prefilter_variant(variant)
+print("variant", variant)
 total_full, total_slab = 0.0, 0.0
 for step in plan:
     level, ws = step["level"], step["ws"]
