@@ -130,6 +130,7 @@ struct datum_ibl_ctx
   DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
   int prefilter_no_steal = 0;
   int sh9_kernel = 0, sh9_rows_per_item = 0;   // A/B: 0 = column strips / automatic run length
+  int table_order = 0;            // A/B: 0 = bands are rings of the lobe, 1 = compact patches
   DeviceBuffer<unsigned int> peer_ticket; // "CTAs done" counter of launches that signal peers, zero between launches
   bool peer_wait_pending = false; // a stream wait on a peer's arrival is queued: synchronize() watches the clock
   unsigned int *peer_wait_word = nullptr; // the local arrival counters ([2]) those waits look at
@@ -219,7 +220,7 @@ namespace
         static_assert(sizeof(ibl::SampleEntry) == sizeof(float4), "table entry layout");
 
         err = cudaMemcpyAsync(t.d_entries, host.entries.data(), sizeof(float4) * (size_t)t.count, cudaMemcpyHostToDevice, ctx->stream);
-        ibl::BandedSamples banded = ibl::build_banded_samples(level, levels, samples, ibl::kSampleBand);
+        ibl::BandedSamples banded = ibl::build_banded_samples(level, levels, samples, ibl::kSampleBand, ctx->table_order);
         t.bands = (int)banded.band_min_lz.size();
 
         std::vector<float> paired = ibl::build_paired_entries(banded, ibl::kDnTableScale);
@@ -1102,7 +1103,20 @@ extern "C"
     std::string k = key;
     if (k == "prefilter_variant")
       return datum_ibl_set_prefilter_variant(ctx, value);
-    if (k == "sh9_kernel" && value <= 1)
+    if (k == "table_order" && value <= 1)
+    {
+      if (value != ctx->table_order)
+      {
+        // cached tables were built in the other order
+        cudaStreamSynchronize(ctx->stream);
+        for(auto &entry : ctx->tables)
+          for(auto &t : entry.second)
+            free_table(t);
+        ctx->tables.clear();
+      }
+      ctx->table_order = value;
+    }
+    else if (k == "sh9_kernel" && value <= 1)
       ctx->sh9_kernel = value;
     else if (k == "sh9_rows_per_item" && value <= 4096)
       ctx->sh9_rows_per_item = value;

@@ -63,23 +63,94 @@ namespace ibl
     return out;
   }
 
-  BandedSamples build_banded_samples(int level, int levels, int samples, int band)
+  BandedSamples build_banded_samples(int level, int levels, int samples, int band, int order)
   {
     BandedSamples out;
     out.level = build_level_samples(level, levels, samples);
     out.band = band;
 
     auto &e = out.level.entries;
-    for(size_t begin = 0; begin < e.size(); begin += (size_t)band)
+
+    auto by_angle = [](SampleEntry const &a, SampleEntry const &b) {
+      return std::atan2((double)a.ly, (double)a.lx) < std::atan2((double)b.ly, (double)b.lx);
+    };
+
+    if (order == 0)
     {
-      size_t end = std::min(e.size(), begin + (size_t)band);
+      // rings: every band is one ring of the lobe-angle order, walked by angle
+      for(size_t begin = 0; begin < e.size(); begin += (size_t)band)
+      {
+        size_t end = std::min(e.size(), begin + (size_t)band);
 
-      out.band_min_lz.push_back(e[end - 1].lz);
+        out.band_min_lz.push_back(e[end - 1].lz);
 
-      std::stable_sort(e.begin() + begin, e.begin() + end, [](SampleEntry const &a, SampleEntry const &b) {
-        return std::atan2((double)a.ly, (double)a.lx) < std::atan2((double)b.ly, (double)b.lx);
-      });
+        std::stable_sort(e.begin() + begin, e.begin() + end, by_angle);
+      }
+
+      return out;
     }
+
+    // patches: a ring of s*band consecutive entries of the lobe-angle order is cut into s sectors of
+    // `band` entries, s chosen so that a sector is about as wide as it is deep.  The warps of a tile
+    // (they share a band) then fetch from ONE compact patch of the lobe instead of from four quarters
+    // of a ring: on the wider lobes of the higher levels that is the difference between sharing the
+    // footprint in L1 and not.
+    auto radius = [](SampleEntry const &a) { return std::sqrt((double)a.lx * a.lx + (double)a.ly * a.ly); };
+
+    struct Band { size_t begin; float min_lz; };
+    std::vector<Band> bands;
+
+    for(size_t begin = 0; begin < e.size(); )
+    {
+      size_t left = e.size() - begin;
+      size_t sectors = 1;
+
+      double best = 1e300;
+      for(size_t s = 1; s <= 8 && s * (size_t)band <= left; ++s)
+      {
+        double r0 = radius(e[begin]), r1 = radius(e[begin + s * band - 1]);
+        double depth = std::max(r1 - r0, 1e-12);
+        double width = std::max(2 * 3.14159265358979323846 * 0.5 * (r0 + r1) / (double)s, 1e-12);
+        double skew = std::fabs(std::log(depth / width));
+        if (skew < best)
+        {
+          best = skew;
+          sectors = s;
+        }
+      }
+
+      size_t end = std::min(e.size(), begin + sectors * (size_t)band);
+
+      std::stable_sort(e.begin() + begin, e.begin() + end, by_angle);
+
+      for(size_t b = begin; b < end; b += (size_t)band)
+      {
+        size_t bend = std::min(end, b + (size_t)band);
+        float min_lz = e[b].lz;
+        for(size_t i = b; i < bend; ++i)
+          min_lz = std::min(min_lz, e[i].lz);
+        bands.push_back(Band{ b, min_lz });
+      }
+
+      begin = end;
+    }
+
+    // the kernel's same-face search needs the bands' smallest lz in decreasing order; the short band (if
+    // any) stays last
+    size_t full = e.size() / (size_t)band;
+    std::stable_sort(bands.begin(), bands.begin() + std::min(full, bands.size()), [](Band const &a, Band const &b) { return a.min_lz > b.min_lz; });
+
+    std::vector<SampleEntry> ordered;
+    ordered.reserve(e.size());
+    float floor_lz = 1e30f;
+    for(auto const &b : bands)
+    {
+      size_t bend = std::min(e.size(), b.begin + (size_t)band);
+      ordered.insert(ordered.end(), e.begin() + b.begin, e.begin() + bend);
+      floor_lz = std::min(floor_lz, b.min_lz);     // monotone whatever the short band holds
+      out.band_min_lz.push_back(floor_lz);
+    }
+    e.swap(ordered);
 
     return out;
   }

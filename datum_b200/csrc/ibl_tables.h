@@ -47,7 +47,9 @@ namespace ibl
     std::vector<float> band_min_lz;
   };
 
-  BandedSamples build_banded_samples(int level, int levels, int samples, int band);
+  // order 0 = rings (every band one ring, walked by angle); 1 = patches (rings of s*band entries cut into s
+  // sectors of `band` entries each, roughly as wide as deep, bands ordered by their smallest lz)
+  BandedSamples build_banded_samples(int level, int levels, int samples, int band, int order = 0);
 
   // The banded entries for the kernel that works on two samples at a time (prefilter_dn.cu,
   // prefilter_dp_kernel): every entry multiplied by `scale`, the last band filled up with

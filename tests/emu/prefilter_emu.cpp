@@ -330,6 +330,21 @@ extern "C" int emu_banded_table(int level, int levels, int samples, int band, fl
   return (int)banded.level.entries.size();
 }
 
+// the same in patch order (ibl_tables.h: order 1)
+extern "C" int emu_patch_table(int level, int levels, int samples, int band, float *entries, float *band_min, int *bands)
+{
+  BandedSamples banded = build_banded_samples(level, levels, samples, band, 1);
+  for(size_t i = 0; i < banded.level.entries.size(); ++i)
+  {
+    entries[4*i + 0] = banded.level.entries[i].lx; entries[4*i + 1] = banded.level.entries[i].ly;
+    entries[4*i + 2] = banded.level.entries[i].lz; entries[4*i + 3] = banded.level.entries[i].wh;
+  }
+  for(size_t k = 0; k < banded.band_min_lz.size(); ++k)
+    band_min[k] = banded.band_min_lz[k];
+  *bands = (int)banded.band_min_lz.size();
+  return (int)banded.level.entries.size();
+}
+
 extern "C" uint32_t emu_pack_dn_word(uint32_t w) { return pack_dn_word(w); }
 
 // one tap through dn_accumulate_tap and the channel norms with total weight 1 and weight w: returns w * texel value

@@ -28,6 +28,8 @@ def load():
         lib.emu_paired_table.restype = ctypes.c_int
         lib.emu_banded_table.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3
         lib.emu_banded_table.restype = ctypes.c_int
+        lib.emu_patch_table.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3
+        lib.emu_patch_table.restype = ctypes.c_int
         lib.emu_pack_dn_word.argtypes = [ctypes.c_uint32]
         lib.emu_pack_dn_word.restype = ctypes.c_uint32
         lib.emu_dn_tap.argtypes = [ctypes.c_uint32, ctypes.c_float, ctypes.c_void_p]

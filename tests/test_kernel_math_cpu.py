@@ -203,3 +203,25 @@ def test_fast_path_is_taken_and_agrees_with_general_path(monkeypatch):
     emu.emu_prefilter_level(src.ctypes.data, ws, ws, level, levels, 256, b_w.ctypes.data, b_f.ctypes.data)
     assert emu.emu_last_fast_fraction() == 0.0
     assert oracle_lib.relative_error(a_f, b_f).max() < 2e-5
+
+
+@pytest.mark.parametrize("level,levels,samples", [(1, 8, 1024), (3, 8, 1024), (6, 8, 1024), (1, 12, 4096), (2, 5, 40)])
+def test_patch_table_is_a_reordering_of_the_ring_table_with_monotone_band_floors(level, levels, samples):
+    """ibl_tables.h order 1 (bands are compact patches of the lobe instead of rings): the same entries, the
+    short band still last, per-band smallest lz non-increasing (the kernel's same-face search relies on it)
+    and a true lower bound of every entry of the band and of all bands before it."""
+    emu = emu_lib.load()
+    band = 16
+    ring = np.zeros((samples, 4), np.float32)
+    patch = np.zeros((samples, 4), np.float32)
+    floor_ring, floor_patch = np.zeros(samples, np.float32), np.zeros(samples, np.float32)
+    nb0, nb1 = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    n0 = emu.emu_banded_table(level, levels, samples, band, ring.ctypes.data, floor_ring.ctypes.data, nb0.ctypes.data)
+    n1 = emu.emu_patch_table(level, levels, samples, band, patch.ctypes.data, floor_patch.ctypes.data, nb1.ctypes.data)
+    assert n0 == n1 and nb0[0] == nb1[0]
+    key = [("a", "f4"), ("b", "f4"), ("c", "f4"), ("d", "f4")]
+    assert np.array_equal(np.sort(ring[:n0].copy().view(key).ravel()), np.sort(patch[:n1].copy().view(key).ravel()))
+    floors = floor_patch[: nb1[0]]
+    assert np.all(np.diff(floors) <= 0)
+    for k in range(nb1[0]):
+        assert patch[k * band:min(n1, (k + 1) * band), 2].min() >= floors[k]

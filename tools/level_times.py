@@ -9,6 +9,7 @@ bits = synth.synthetic_chain(ws, ws, levels)
 offs = datum_b200.level_offsets(ws, ws, levels)
 d_bits = torch.from_numpy(bits.view(np.int32)).to("cuda:0")
 variants = [int(v) for v in os.environ.get("IBL_VARIANTS", "0,10000").split(",")]
+ctx.set_tuning("table_order", int(os.environ.get("IBL_TABLE_ORDER", "0")))
 ctx.set_prefilter_variant(0)
 ctx.buildmips_cube_ibl_device(ws, ws, levels, d_bits, samples); ctx.synchronize()
 for variant in variants:
