@@ -64,6 +64,7 @@ namespace
     double total_weight = 0;
     float4 *d_banded = nullptr;  // the entries in banded ring order (ibl_tables.h), scaled by kDnTableScale
     float4 *d_pairs = nullptr;   // the banded entries, last band filled up, interleaved two by two (build_paired_entries)
+    float4 *d_proj = nullptr;    // the same with (lx/lz, ly/lz) in place of (lx, ly): the pair kernel's projective form
     float *d_band_min = nullptr; // smallest lz per band
     int bands = 0;
   };
@@ -188,6 +189,7 @@ namespace
     if (t.d_banded) cudaFree(t.d_banded);
     if (t.d_band_min) cudaFree(t.d_band_min);
     if (t.d_pairs) cudaFree(t.d_pairs);
+    if (t.d_proj) cudaFree(t.d_proj);
     t = DeviceTable();
   }
 
@@ -224,6 +226,7 @@ namespace
         t.bands = (int)banded.band_min_lz.size();
 
         std::vector<float> paired = ibl::build_paired_entries(banded, ibl::kDnTableScale);
+        std::vector<float> proj = ibl::build_paired_entries(banded, ibl::kDnTableScale, true);
 
         for(auto &e : banded.level.entries)
         {
@@ -242,6 +245,10 @@ namespace
           err = cudaMalloc(&t.d_pairs, sizeof(float) * (paired.size() > 0 ? paired.size() : 4));
         if (err == cudaSuccess)
           err = cudaMemcpyAsync(t.d_pairs, paired.data(), sizeof(float) * paired.size(), cudaMemcpyHostToDevice, ctx->stream);
+        if (err == cudaSuccess)
+          err = cudaMalloc(&t.d_proj, sizeof(float) * (proj.size() > 0 ? proj.size() : 4));
+        if (err == cudaSuccess)
+          err = cudaMemcpyAsync(t.d_proj, proj.data(), sizeof(float) * proj.size(), cudaMemcpyHostToDevice, ctx->stream);
 
         if (err == cudaSuccess)
           err = cudaStreamSynchronize(ctx->stream); // `host` and `banded` die at the end of this iteration
@@ -340,6 +347,7 @@ namespace
     p.records = ctx->records.ptr;
     p.table = table.d_banded;
     p.table_pairs = table.d_pairs;
+    p.table_proj = table.d_proj;
     p.band_min_lz = table.d_band_min;
     p.table_count = table.count;
     p.bands = table.bands;

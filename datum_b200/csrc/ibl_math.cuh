@@ -139,6 +139,11 @@ namespace ibl
     float inv_hw, inv_hh;
     uint32_t face_size;  // ws*hs records per face
     uint32_t bias;       // kMagicBits*(ws+1) mod 2^32, removed from the raw index
+
+    // projective form (face_footprint_proj / cube_footprint_proj below)
+    float hwm_magic, hhm_magic;   // hwm + kMagic, hhm + kMagic: exact while ws and hs are even
+    float neg_ws;                 // -(float)ws
+    uint32_t bias_general;        // kMagicBits - hhm*ws: what cube_footprint_proj's raw index carries
   };
 
   IBL_HD LevelGeom make_level_geom(int ws, int hs)
@@ -150,6 +155,9 @@ namespace ibl
     g.inv_hw = 1.0f / g.hw; g.inv_hh = 1.0f / g.hh;
     g.face_size = (uint32_t)ws * (uint32_t)hs;
     g.bias = kMagicBits * (uint32_t)(ws + 1);
+    g.hwm_magic = g.hwm + kMagic; g.hhm_magic = g.hhm + kMagic;
+    g.neg_ws = -(float)ws;
+    g.bias_general = kMagicBits - (uint32_t)((hs - 2) / 2) * (uint32_t)ws;
     return g;
   }
 
@@ -270,6 +278,72 @@ namespace ibl
     dv = fv - (mv - kMagic);
 
     return f2u(mv) * (uint32_t)g.ws + f2u(mu) + face_base;
+  }
+
+  // ---- projective form of both footprints (prefilter_dp_kernel) ----
+  //
+  // The sample table holds (X, Y) = (lx/lz, ly/lz): a direction is scale invariant (the face choice and
+  // both quotients of ibl.cpp:51-85 are), so L' = X*T + Y*B + N costs two multiply-adds per component
+  // instead of three.  On the texel's own face the align-corners offset goes into the frame rows,
+  // a' = a*hw + hwm*m (fold_face_row), so that the texel coordinate is ONE product fu = a'/m that is
+  // never rounded by itself: i comes out of fma(a', r, magic), the fraction out of fma(a', r, -i) — one
+  // rounding each, three operations per coordinate instead of four.  The record index is formed in the
+  // fp32 adder too: magic + i + j*ws is exact below 2^24 (ws*hs <= 2^22), its bits are the 32-bit
+  // index with kMagicBits on top (the kernel moves the record pointer back by that once).
+  // All of this is what face_footprint / cube_footprint compute, up to fp32 rounding.
+  constexpr uint32_t kProjMaxFace = 1u << 22;
+
+  IBL_HD bool proj_usable(int ws, int hs)
+  {
+    return ws >= 2 && hs >= 2 && (ws & 1) == 0 && (hs & 1) == 0 && (uint64_t)ws * (uint64_t)hs <= kProjMaxFace;
+  }
+
+  IBL_HD Vec3f fold_face_row(LevelGeom const &g, Vec3f l)
+  {
+    return Vec3f{ fmaf(g.hwm, l.z, l.x * g.hw), fmaf(g.hhm, l.z, l.y * g.hh), l.z };
+  }
+
+  IBL_HD Vec3f unfold_face_row(LevelGeom const &g, Vec3f s)
+  {
+    return Vec3f{ fmaf(-g.hwm, s.z, s.x) * g.inv_hw, fmaf(-g.hhm, s.z, s.y) * g.inv_hh, s.z };
+  }
+
+  // la, lb, lm from folded rows; returns kMagicBits + i + j*ws (face offset not included)
+  IBL_HD uint32_t face_footprint_proj(LevelGeom const &g, float la, float lb, float lm, float &du, float &dv)
+  {
+    float r = rcp_fast(lm);
+    float mu = fmaf(la, r, kMagic);
+    float mv = fmaf(lb, r, kMagic);
+    float niu = fmaf(mu, -1.0f, kMagic);      // -i, exact
+    float niv = fmaf(mv, -1.0f, kMagic);
+    du = fmaf(la, r, niu);
+    dv = fmaf(lb, r, niv);
+    return f2u(fmaf(niv, g.neg_ws, mu));
+  }
+
+  // any direction; returns kMagicBits + i + (j - hhm)*ws (face offset not included: see g.bias_general)
+  IBL_HD uint32_t cube_footprint_proj(LevelGeom const &g, float Lx, float Ly, float Lz, float &du, float &dv, uint32_t &face)
+  {
+    float qu, qv;
+    cube_select(Lx, Ly, Lz, qu, qv, face);
+
+    float mu = fmaf(qu, g.hw, g.hwm_magic);
+    float mv = fmaf(qv, g.hh, g.hhm_magic);
+    float cu = fmaf(mu, -1.0f, g.hwm_magic);  // hwm - i, exact (hwm is an integer)
+    float cv = fmaf(mv, -1.0f, g.hhm_magic);
+    du = fmaf(qu, g.hw, cu);
+    dv = fmaf(qv, g.hh, cv);
+    return f2u(fmaf(cv, g.neg_ws, mu));
+  }
+
+  // footprint_weights with the right-hand column as a difference: w10 = v0 - w00 = (0.5 + du) * v0 up to
+  // one rounding of the size of ulp(v0); never negative because u0 <= 1
+  IBL_HD void footprint_weights_diff(float du, float dv, float wh, float nl, float w[4])
+  {
+    float u0 = 0.5f - du;
+    float v1 = fmaf(dv, nl, wh), v0 = fmaf(-dv, nl, wh);
+    w[0] = u0 * v0; w[2] = u0 * v1;
+    w[1] = v0 - w[0]; w[3] = v1 - w[2];
   }
 
   // ---- packed-texel accumulation ----

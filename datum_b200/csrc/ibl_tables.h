@@ -58,7 +58,9 @@ namespace ibl
   //     { lx_a, lx_b, ly_a, ly_b }  { lz_a, lz_b, wh_a, wh_b }
   // so that one 16-byte load yields two register pairs for the packed fp32x2 arithmetic.
   // Returns 4 floats per entry, band * ceil(count / band) entries.
-  std::vector<float> build_paired_entries(BandedSamples const &banded, float scale);
+  // projective: lx, ly are replaced by lx/lz, ly/lz (unscaled; ibl_math.cuh "projective form"), lz and wh
+  // keep the scale: they only weigh the taps then.
+  std::vector<float> build_paired_entries(BandedSamples const &banded, float scale, bool projective = false);
 
   // ibl.cpp:95-104
   float radicalinverse_VdC(uint32_t bits);

@@ -46,6 +46,7 @@ namespace ibl
     uint4 const *records;     // quad records of the SOURCE level, words re-laid by pack_dn_word (6*ws*hs)
     float4 const *table;      // banded sample table of this level, every entry scaled by kDnTableScale
     float4 const *table_pairs; // the same entries, last band filled up, two entries interleaved per 32 bytes (ibl_tables.h)
+    float4 const *table_proj; // table_pairs with (lx/lz, ly/lz) for (lx, ly): what the pair kernel reads unless the source level is odd-sized or above 2^22 texels per face (proj_usable)
     float const *band_min_lz; // smallest lz of each band (unscaled), decreasing
     int table_count;
     int bands;                // ceil(table_count / kSampleBand)

@@ -681,7 +681,121 @@ namespace ibl
     gather_pair<EXP_ALU, RHI>(p, base, fa * p.geom.face_size, fb * p.geom.face_size, fu, fv, e, acc);
   }
 
-  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false>
+
+  // ---- projective form (ibl_math.cuh: face_footprint_proj, cube_footprint_proj, footprint_weights_diff) ----
+  //
+  // Entries hold (lx/lz, ly/lz): a direction is two packed multiply-adds per component.  On the texel's
+  // own face the rows arrive folded (fold_face_row), so integer part and fraction of a texel coordinate
+  // are one FFMA2 each straight from the quotient; the record index is formed in the fp32 adder
+  // (magic + i + j*ws, exact) and its bits go into IMAD.WIDE as they are.  The right-hand taps' weights
+  // are differences.  Per pair of samples: 32 packed fp32 operations and 10 integer multiply-adds where
+  // the form above needs 37 and 12.
+
+  __device__ __forceinline__ void direction_pair_proj(Frame const &t, PairEntry const &e, f32x2 &x, f32x2 &y, f32x2 &z)
+  {
+    x = fma2(e.lx, bcast2(t.T.x), fma2(e.ly, bcast2(t.B.x), bcast2(t.N.x)));
+    y = fma2(e.lx, bcast2(t.T.y), fma2(e.ly, bcast2(t.B.y), bcast2(t.N.y)));
+    z = fma2(e.lx, bcast2(t.T.z), fma2(e.ly, bcast2(t.B.z), bcast2(t.N.z)));
+  }
+
+  // idx = raw index bits of both samples (what `base` has been moved back by), du/dv = fraction - 0.5
+  __device__ __forceinline__ void gather_pair_proj(PrefilterDnParams const &p, uint4 const *base, uint32_t idx_a, uint32_t idx_b, f32x2 du, f32x2 dv, PairEntry const &e, Sums &acc)
+  {
+    uint4 ra = load_record(base, idx_a);
+    uint4 rb = load_record(base, idx_b);
+
+    // tools/ibl.cpp:40 times the sample weight: (0.5 -+ du) * (wh -+ dv * nl), right-hand column by difference
+    f32x2 u0 = fma2(du, bcast2(-1.0f), bcast2(0.5f));
+    f32x2 v0 = fma2(neg2(dv), e.lz, e.wh);
+    f32x2 v1 = fma2(dv, e.lz, e.wh);
+    f32x2 p00 = mul2(u0, v0);
+    f32x2 p01 = mul2(u0, v1);
+
+    float w00a, w00b, w10a, w10b, w01a, w01b, w11a, w11b;
+    unpack2(p00, w00a, w00b);
+    unpack2(p01, w01a, w01b);
+    unpack2(fma2(p00, bcast2(-1.0f), v0), w10a, w10b);
+    unpack2(fma2(p01, bcast2(-1.0f), v1), w11a, w11b);
+
+    const uint32_t emul = p.exp_mul;
+    w00a = scale_by_exponent(w00a, ra.x & kDnMaskE, emul);
+    w10a = scale_by_exponent(w10a, ra.y & kDnMaskE, emul);
+    w01a = scale_by_exponent(w01a, ra.z & kDnMaskE, emul);
+    w11a = scale_by_exponent(w11a, ra.w & kDnMaskE, emul);
+    w00b = scale_by_exponent(w00b, rb.x & kDnMaskE, emul);
+    w10b = scale_by_exponent(w10b, rb.y & kDnMaskE, emul);
+    w01b = scale_by_exponent(w01b, rb.z & kDnMaskE, emul);
+    w11b = scale_by_exponent(w11b, rb.w & kDnMaskE, emul);
+
+    acc.rg = fma2(pack2(u2f(ra.x >> 23), u2f(ra.x & kDnMaskG)), bcast2(w00a), acc.rg);
+    acc.rg = fma2(pack2(u2f(ra.y >> 23), u2f(ra.y & kDnMaskG)), bcast2(w10a), acc.rg);
+    acc.rg = fma2(pack2(u2f(ra.z >> 23), u2f(ra.z & kDnMaskG)), bcast2(w01a), acc.rg);
+    acc.rg = fma2(pack2(u2f(ra.w >> 23), u2f(ra.w & kDnMaskG)), bcast2(w11a), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.x >> 23), u2f(rb.x & kDnMaskG)), bcast2(w00b), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.y >> 23), u2f(rb.y & kDnMaskG)), bcast2(w10b), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.z >> 23), u2f(rb.z & kDnMaskG)), bcast2(w01b), acc.rg);
+    acc.rg = fma2(pack2(u2f(rb.w >> 23), u2f(rb.w & kDnMaskG)), bcast2(w11b), acc.rg);
+
+    acc.bb = fma2(pack2(u2f(ra.x & kDnMaskB), u2f(rb.x & kDnMaskB)), pack2(w00a, w00b), acc.bb);
+    acc.bb = fma2(pack2(u2f(ra.y & kDnMaskB), u2f(rb.y & kDnMaskB)), pack2(w10a, w10b), acc.bb);
+    acc.bb = fma2(pack2(u2f(ra.z & kDnMaskB), u2f(rb.z & kDnMaskB)), pack2(w01a, w01b), acc.bb);
+    acc.bb = fma2(pack2(u2f(ra.w & kDnMaskB), u2f(rb.w & kDnMaskB)), pack2(w11a, w11b), acc.bb);
+  }
+
+  // frame rows face-local and folded; `base` = records of the texel's face, moved back by kMagicBits
+  __device__ __forceinline__ void pair_same_face_proj(PrefilterDnParams const &p, Frame const &t, uint4 const *base, PairEntry const &e, Sums &acc)
+  {
+    f32x2 la, lb, lm;
+    direction_pair_proj(t, e, la, lb, lm);
+
+    float ma, mb;
+    unpack2(lm, ma, mb);
+    f32x2 r = pack2(rcp_fast(ma), rcp_fast(mb));
+
+    f32x2 mu = fma2(la, r, bcast2(kMagic));
+    f32x2 mv = fma2(lb, r, bcast2(kMagic));
+    f32x2 niu = fma2(mu, bcast2(-1.0f), bcast2(kMagic));
+    f32x2 niv = fma2(mv, bcast2(-1.0f), bcast2(kMagic));
+    f32x2 du = fma2(la, r, niu);
+    f32x2 dv = fma2(lb, r, niv);
+
+    float ia, ib;
+    unpack2(fma2(niv, bcast2(p.geom.neg_ws), mu), ia, ib);
+
+    gather_pair_proj(p, base, f2u(ia), f2u(ib), du, dv, e, acc);
+  }
+
+  // frame rows in world coordinates; `base` = records moved back by geom.bias_general
+  __device__ __forceinline__ void pair_general_proj(PrefilterDnParams const &p, Frame const &t, uint4 const *base, PairEntry const &e, Sums &acc)
+  {
+    f32x2 x, y, z;
+    direction_pair_proj(t, e, x, y, z);
+
+    float xa, xb, ya, yb, za, zb;
+    unpack2(x, xa, xb);
+    unpack2(y, ya, yb);
+    unpack2(z, za, zb);
+
+    float qua, qva, qub, qvb;
+    uint32_t fa, fb;
+    cube_select(xa, ya, za, qua, qva, fa);
+    cube_select(xb, yb, zb, qub, qvb, fb);
+
+    f32x2 qu = pack2(qua, qub), qv = pack2(qva, qvb);
+    f32x2 mu = fma2(qu, bcast2(p.geom.hw), bcast2(p.geom.hwm_magic));
+    f32x2 mv = fma2(qv, bcast2(p.geom.hh), bcast2(p.geom.hhm_magic));
+    f32x2 cu = fma2(mu, bcast2(-1.0f), bcast2(p.geom.hwm_magic));
+    f32x2 cv = fma2(mv, bcast2(-1.0f), bcast2(p.geom.hhm_magic));
+    f32x2 du = fma2(qu, bcast2(p.geom.hw), cu);
+    f32x2 dv = fma2(qv, bcast2(p.geom.hh), cv);
+
+    float ia, ib;
+    unpack2(fma2(cv, bcast2(p.geom.neg_ws), mu), ia, ib);
+
+    gather_pair_proj(p, base, fa * p.geom.face_size + f2u(ia), fb * p.geom.face_size + f2u(ib), du, dv, e, acc);
+  }
+
+  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false, bool PROJ = true>
   __global__ void __launch_bounds__(32 * NW, MINB) prefilter_dp_kernel(PrefilterDnParams p)
   {
     extern __shared__ float4 smem[];
@@ -697,11 +811,11 @@ namespace ibl
     if (SMEM_TABLE)
     {
       for(int i = tid; i < padded; i += 32 * NW)
-        s_table[i] = __ldg(p.table_pairs + i);
+        s_table[i] = __ldg((PROJ ? p.table_proj : p.table_pairs) + i);
       __syncthreads();
     }
 
-    float4 const *table = SMEM_TABLE ? s_table : p.table_pairs;
+    float4 const *table = SMEM_TABLE ? s_table : (PROJ ? p.table_proj : p.table_pairs);
 
     uint32_t smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -711,8 +825,9 @@ namespace ibl
     static_assert(PER >= 2 && PER % 2 == 0, "a warp takes whole pairs of every band");
     constexpr int BAND_UNROLL = (PAIRS >= 2 ? 1 : 2) * DEPTH;     // DEPTH 2: twice the footprint loads in flight per warp (A/B)
 
-    // records, moved back by the bias of the magic-add integers
-    uint4 const *biased = opaque(p.records - (size_t)p.geom.bias);
+    // records, moved back by the bias of the magic-add integers (projective form: of the one fp32 index;
+    // the general path's index also carries -hhm*ws, see cube_footprint_proj)
+    uint4 const *biased = opaque(p.records - (size_t)(PROJ ? kMagicBits : p.geom.bias));
 
     for(int it = 0; ; ++it)
     {
@@ -786,9 +901,18 @@ namespace ibl
         float threshold = same_face_threshold(Nl);
         threshold = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(threshold)));
 
-        st.T = Vec3f{ Tl.x * p.geom.hw, Tl.y * p.geom.hh, Tl.z };
-        st.B = Vec3f{ Bl.x * p.geom.hw, Bl.y * p.geom.hh, Bl.z };
-        st.N = Vec3f{ Nl.x * p.geom.hw, Nl.y * p.geom.hh, Nl.z };
+        if (PROJ)
+        {
+          st.T = fold_face_row(p.geom, Tl);
+          st.B = fold_face_row(p.geom, Bl);
+          st.N = fold_face_row(p.geom, Nl);
+        }
+        else
+        {
+          st.T = Vec3f{ Tl.x * p.geom.hw, Tl.y * p.geom.hh, Tl.z };
+          st.B = Vec3f{ Bl.x * p.geom.hw, Bl.y * p.geom.hh, Bl.z };
+          st.N = Vec3f{ Nl.x * p.geom.hw, Nl.y * p.geom.hh, Nl.z };
+        }
 
         int lo = 0, hi = p.bands;
         while (lo < hi)
@@ -817,23 +941,45 @@ namespace ibl
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
-            pair_same_face<EXP_ALU, RHI>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+          {
+            if (PROJ)
+              pair_same_face_proj(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+            else
+              pair_same_face<EXP_ALU, RHI>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+          }
         }
       }
 
       if (band < p.bands)
       {
         // back to world coordinates for the samples that may cross a face edge
-        st.T = from_face_local(face, Vec3f{ st.T.x * p.geom.inv_hw, st.T.y * p.geom.inv_hh, st.T.z });
-        st.B = from_face_local(face, Vec3f{ st.B.x * p.geom.inv_hw, st.B.y * p.geom.inv_hh, st.B.z });
-        st.N = from_face_local(face, Vec3f{ st.N.x * p.geom.inv_hw, st.N.y * p.geom.inv_hh, st.N.z });
+        if (PROJ)
+        {
+          st.T = from_face_local(face, unfold_face_row(p.geom, st.T));
+          st.B = from_face_local(face, unfold_face_row(p.geom, st.B));
+          st.N = from_face_local(face, unfold_face_row(p.geom, st.N));
+        }
+        else
+        {
+          st.T = from_face_local(face, Vec3f{ st.T.x * p.geom.inv_hw, st.T.y * p.geom.inv_hh, st.T.z });
+          st.B = from_face_local(face, Vec3f{ st.B.x * p.geom.inv_hw, st.B.y * p.geom.inv_hh, st.B.z });
+          st.N = from_face_local(face, Vec3f{ st.N.x * p.geom.inv_hw, st.N.y * p.geom.inv_hh, st.N.z });
+        }
+
+        // the general path's index carries kMagicBits - hhm*ws instead of kMagicBits
+        uint4 const *general = PROJ ? opaque(biased_probe + (size_t)(kMagicBits - p.geom.bias_general)) : biased_probe;
 
         #pragma unroll BAND_UNROLL
         for(; band < p.bands; ++band)
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
-            pair_general<EXP_ALU, RHI>(p, st, biased_probe, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+          {
+            if (PROJ)
+              pair_general_proj(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+            else
+              pair_general<EXP_ALU, RHI>(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+          }
         }
       }
 
@@ -1172,10 +1318,10 @@ namespace ibl
 
   namespace
   {
-    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false>
+    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false, bool PROJ = true>
     cudaError_t launch_dp(PrefilterDnParams p, int sm_count, cudaStream_t stream, int *launched_grid)
     {
-      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU, DEPTH, RHI, PLAIN_QUEUE, LEAN>;
+      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU, DEPTH, RHI, PLAIN_QUEUE, LEAN, PROJ>;
 
       int rows = p.row_end - p.row_begin;
       int tiles_x = (p.wd + 7) / 8, tiles_y = (rows + 3) / 4;
@@ -1213,10 +1359,11 @@ namespace ibl
       return cudaGetLastError();
     }
 
-    // the pair kernel folds the magic-add bias into the record pointer: index + bias must not wrap
+    // the pair kernel forms the record index in the fp32 adder (ibl_math.cuh, projective form): even source
+    // sizes of at most 2^22 texels per face; everything else runs the one-sample kernel
     bool pair_kernel_usable(PrefilterDnParams const &p)
     {
-      return p.table_pairs != nullptr && (unsigned long long)p.geom.bias + 6ull * p.geom.face_size <= 0xFFFFFFFFull;
+      return p.table_proj != nullptr && proj_usable(p.geom.ws, p.geom.hs);
     }
   }
 
@@ -1227,7 +1374,7 @@ namespace ibl
   {
     PrefilterDnParams p = {};
     p.geom = make_level_geom(ws, hs);
-    p.table_pairs = reinterpret_cast<float4 const*>(&p);     // any non-null value: only the geometry decides
+    p.table_proj = reinterpret_cast<float4 const*>(&p);      // any non-null value: only the geometry decides
     return pair_kernel_usable(p);
   }
 
@@ -1298,6 +1445,9 @@ namespace ibl
       case 92: return launch_dp<4, 8, true, true, 0, 1, false, true>(p, sm_count, stream, launched_grid);   // round 1's tile hand-out (one thread, no stealing)
       case 93: return launch_dp<4, 8, true, true, 0, 1, false, true, true>(p, sm_count, stream, launched_grid);   // ... and no batch / peer-signal code
       case 94: return launch_dp<4, 8, true, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid);  // stealing hand-out, no batch / peer-signal code
+      // round 2's arithmetic (three-term directions, integer record index, four weight products) for A/B
+      case 95: return launch_dp<4, 8, true, true, 0, 1, false, false, true, false>(p, sm_count, stream, launched_grid);
+      case 96: return launch_dp<8, 4, true, false, 0, 1, false, false, true, false>(p, sm_count, stream, launched_grid);
       case 75: return launch_dp<4, 8, true, true, 1>(p, sm_count, stream, launched_grid);
       case 76: return launch_dp<4, 8, true, true, 2>(p, sm_count, stream, launched_grid);
       case 77: return launch_dp<4, 8, true, true, 3>(p, sm_count, stream, launched_grid);

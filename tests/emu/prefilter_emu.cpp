@@ -135,10 +135,10 @@ extern "C" void emu_prefilter_level(uint32_t const *src, int ws, int hs, int lev
 // per-band same-face decision, quad records re-laid by pack_dn_word, subnormal-mantissa taps with
 // the exponent folded into the weight, per-channel normalisation.
 //
-// pairs = true: the arithmetic of prefilter_dp_kernel instead — the pair-interleaved table with its
-// filled-up last band (build_paired_entries), footprint addresses taken relative to a record pointer
-// moved back by the magic-add bias (32-bit wrap-around index, 64-bit pointer), blue summed in one
-// partial per sample of a pair.
+// pairs = true: the arithmetic of prefilter_dp_kernel instead — the pair-interleaved PROJECTIVE table with
+// its filled-up last band (build_paired_entries), folded frame rows, the record index formed in the fp32
+// adder and taken relative to a record pointer moved back by its bias, right-hand weights by difference
+// (ibl_math.cuh "projective form"), blue summed in one partial per sample of a pair.
 static void emu_dn_impl(uint32_t const *src, int ws, int hs, int level, int levels, int samples, int band, uint32_t *words, float *f32, bool pairs)
 {
   BandedSamples banded = build_banded_samples(level, levels, samples, band);
@@ -150,7 +150,9 @@ static void emu_dn_impl(uint32_t const *src, int ws, int hs, int level, int leve
 
   if (pairs)
   {
-    std::vector<float> paired = build_paired_entries(banded, kDnTableScale);
+    if (!proj_usable(ws, hs))
+      __builtin_trap();   // the launcher never picks the pair kernel here
+    std::vector<float> paired = build_paired_entries(banded, kDnTableScale, true);
     table.assign(paired.size() / 4, SampleEntry{});
     for(size_t i = 0; i < table.size(); i += 2)
     {
@@ -210,6 +212,14 @@ static void emu_dn_impl(uint32_t const *src, int ws, int hs, int level, int leve
         Vec3f Bw = from_face_local(face, Vec3f{ Bs.x * geom.inv_hw, Bs.y * geom.inv_hh, Bs.z });
         Vec3f Nw = from_face_local(face, Vec3f{ Ns.x * geom.inv_hw, Ns.y * geom.inv_hh, Ns.z });
 
+        if (pairs)
+        {
+          Ts = fold_face_row(geom, Tl); Bs = fold_face_row(geom, Bl); Ns = fold_face_row(geom, Nl);
+          Tw = from_face_local(face, unfold_face_row(geom, Ts));
+          Bw = from_face_local(face, unfold_face_row(geom, Bs));
+          Nw = from_face_local(face, unfold_face_row(geom, Ns));
+        }
+
         float acc[3] = { 0, 0, 0 };
         float blue[2] = { 0, 0 };
 
@@ -221,7 +231,36 @@ static void emu_dn_impl(uint32_t const *src, int ws, int hs, int level, int leve
           float du, dv;
           uint32_t idx;
 
-          if (same)
+          if (pairs)
+          {
+            // e.lx, e.ly hold lx/lz, ly/lz here
+            uint32_t raw, bias;
+            if (same)
+            {
+              float la = fmaf(e.lx, Ts.x, fmaf(e.ly, Bs.x, Ns.x));
+              float lb = fmaf(e.lx, Ts.y, fmaf(e.ly, Bs.y, Ns.y));
+              float lm = fmaf(e.lx, Ts.z, fmaf(e.ly, Bs.z, Ns.z));
+              raw = face_footprint_proj(geom, la, lb, lm, du, dv) + (uint32_t)face * geom.face_size;
+              bias = kMagicBits;
+              ++fast;
+            }
+            else
+            {
+              float Lx = fmaf(e.lx, Tw.x, fmaf(e.ly, Bw.x, Nw.x));
+              float Ly = fmaf(e.lx, Tw.y, fmaf(e.ly, Bw.y, Nw.y));
+              float Lz = fmaf(e.lx, Tw.z, fmaf(e.ly, Bw.z, Nw.z));
+              uint32_t f;
+              raw = cube_footprint_proj(geom, Lx, Ly, Lz, du, dv, f);
+              raw += f * geom.face_size;
+              bias = geom.bias_general;
+            }
+            // the kernel's address: unsigned 32-bit index that still carries the bias, pointer moved back by it
+            long long element = (long long)raw - (long long)bias;
+            if (element < 0 || element >= (long long)records.size())
+              __builtin_trap();
+            idx = (uint32_t)element;
+          }
+          else if (same)
           {
             float la = fmaf(e.lz, Ns.x, fmaf(e.ly, Bs.x, e.lx * Ts.x));
             float lb = fmaf(e.lz, Ns.y, fmaf(e.ly, Bs.y, e.lx * Ts.y));
@@ -238,22 +277,14 @@ static void emu_dn_impl(uint32_t const *src, int ws, int hs, int level, int leve
           }
           ++total;
 
-          if (pairs)
-          {
-            // the kernel's address: 32-bit index that still carries the bias, pointer moved back by it
-            uint32_t raw = idx + geom.bias;
-            if ((unsigned long long)geom.bias + 6ull * geom.face_size > 0xFFFFFFFFull)
-              __builtin_trap();   // the launcher never picks the pair kernel here
-            long long element = (long long)raw - (long long)geom.bias;
-            if (element < 0 || (size_t)element != (size_t)idx)
-              __builtin_trap();
-          }
-
           if (idx >= records.size())
             __builtin_trap();
 
           float w[4];
-          footprint_weights(du, dv, e.wh, e.lz, w);
+          if (pairs)
+            footprint_weights_diff(du, dv, e.wh, e.lz, w);
+          else
+            footprint_weights(du, dv, e.wh, e.lz, w);
 
           Rec const &rec = records[idx];
           if (pairs)

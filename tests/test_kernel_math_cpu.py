@@ -105,9 +105,11 @@ def test_dn_kernel_math_matches_oracle(ws, levels, level, noise):
 
 @pytest.mark.parametrize("ws,levels,level,samples,noise", [(16, 5, 1, 1024, True), (32, 6, 2, 1024, True), (8, 4, 3, 1024, True), (16, 5, 2, 7, True), (24, 4, 1, 100, False)])
 def test_pair_kernel_math_matches_the_one_sample_kernel_and_the_oracle(ws, levels, level, samples, noise):
-    """prefilter_dp_kernel's arithmetic: the table with its filled-up last band read two entries at a
-    time, the record pointer moved back by the magic-add bias, blue summed per sample of a pair.
-    r and g are bit-identical to the one-sample kernel; blue differs by association only."""
+    """prefilter_dp_kernel's arithmetic (ibl_math.cuh "projective form"): the table of (lx/lz, ly/lz) with its
+    filled-up last band read two entries at a time, folded frame rows, the record index out of the fp32
+    adder with the pointer moved back by its bias, right-hand weights by difference, blue summed per sample
+    of a pair.  Same samples, same footprints as the one-sample kernel up to fp32 rounding of the
+    coordinates."""
     emu = emu_lib.load()
     src = synth.synthetic_chain(ws, ws, 1, probe=8, noise=noise, sun=False)
     wd = ws // 2
@@ -116,11 +118,13 @@ def test_pair_kernel_math_matches_the_one_sample_kernel_and_the_oracle(ws, level
     b_w, b_f = np.zeros(n, np.uint32), np.zeros((n, 3), np.float32)
     emu.emu_prefilter_level_dn(src.ctypes.data, ws, ws, level, levels, samples, 16, a_w.ctypes.data, a_f.ctypes.data)
     emu.emu_prefilter_level_dp(src.ctypes.data, ws, ws, level, levels, samples, 16, b_w.ctypes.data, b_f.ctypes.data)
-    assert np.array_equal(a_f[:, :2], b_f[:, :2])
-    assert np.allclose(a_f[:, 2], b_f[:, 2], rtol=2e-5, atol=0)   # ~sqrt(samples) * 2^-24
+    # texels with a sample within rounding of a cube edge may send it to either face (tests/parity.py)
+    clean = oracle_lib.edge_ambiguous_counts(wd, wd, level, levels, samples) == 0
+    peak = np.maximum(a_f.max(axis=1, keepdims=True), 1e-30)
+    assert (np.abs(a_f - b_f) / peak)[clean].max() <= 2e-5
+    assert (np.abs(a_f - b_f) / peak).max() <= 5e-2
 
     want_words, want_f32 = oracle_lib.prefilter_level(src, ws, ws, level, levels, samples)
-    clean = oracle_lib.edge_ambiguous_counts(wd, wd, level, levels, samples) == 0
     assert oracle_lib.relative_error(b_f, want_f32)[clean].max() <= 1e-4
     stats = oracle_lib.word_stats(b_w[clean], want_words[clean])
     assert stats["max_code"] <= 1 and stats["exp_mismatch"] == 0

@@ -214,10 +214,12 @@ def test_row_slabs_reproduce_the_full_level(ctx):
         assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 1e-4
         stats = oracle_lib.word_stats(slabs.cpu().numpy().view(np.uint32), full.cpu().numpy().view(np.uint32))
         assert oracle_lib.words_within_one_code(stats, 0.995), stats
-        # pinned variants (one-sample and pair kernel): same warp split; only the same-face sample count of the re-cut tiles differs
+        # pinned variants (one-sample and pair kernel): same warp split; only the same-face sample count of the
+        # re-cut tiles differs (the two paths round a footprint coordinate differently: up to 4e-5 when EVERY
+        # sample changes path, tests/emu with EMU_NOFAST)
         for variant in (53, 72):
             full, full_f, slabs, slabs_f = run(variant)
-            assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 5e-6
+            assert oracle_lib.relative_error(slabs_f.cpu().numpy(), full_f.cpu().numpy()).max() <= 5e-5
             assert (full == slabs).float().mean().item() >= 0.999
     finally:
         ctx.set_prefilter_variant(0)
