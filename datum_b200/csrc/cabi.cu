@@ -128,6 +128,7 @@ struct datum_ibl_ctx
   void *host_stage = nullptr;     // pinned staging between the device and a caller's PAGEABLE payload
   size_t host_stage_bytes = 0;
   DeviceBuffer<uint4> records;    // quad records of the current source level
+  std::map<std::pair<int, int>, float*> frames; // source size -> per-texel frames of the destination level (ibl::launch_build_frames)
   DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
   int prefilter_no_steal = 0;
   int sh9_kernel = 0, sh9_rows_per_item = 0;   // A/B: 0 = column strips / automatic run length
@@ -339,7 +340,31 @@ namespace
       return fail_cuda("build_dn_records", err);
     ctx->launches += 1;
 
+    // frames of the destination level: geometry only, computed on first use of a source size
+    float const *frames = nullptr;
+    if (ibl::proj_usable(ws, hs))
+    {
+      auto found = ctx->frames.find(std::make_pair(ws, hs));
+      if (found == ctx->frames.end())
+      {
+        float *built = nullptr;
+        err = cudaMalloc(&built, sizeof(float) * (size_t)ibl::kFrameFloats * 6 * wd * hd);
+        if (err == cudaSuccess)
+        {
+          err = ibl::launch_build_frames(built, ws, hs, ctx->quats, ctx->stream);
+          if (err != cudaSuccess)
+            cudaFree(built);
+        }
+        if (err != cudaSuccess)
+          return fail_cuda("build_frames", err);
+        ctx->launches += 1;
+        found = ctx->frames.emplace(std::make_pair(ws, hs), built).first;
+      }
+      frames = found->second;
+    }
+
     ibl::PrefilterDnParams p = {};
+    p.frames = frames;
     p.probes = batch.probes;
     p.record_stride = (size_t)6 * ws * hs;
     p.dst_stride = batch.stride;
@@ -1020,6 +1045,9 @@ extern "C"
     if (ctx->host_stage)
       cudaFreeHost(ctx->host_stage);
     ctx->records.release();
+    for(auto &entry : ctx->frames)
+      cudaFree(entry.second);
+    ctx->frames.clear();
     ctx->queue_heads.release();
     ctx->peer_ticket.release();
     ctx->sh_weights.release();

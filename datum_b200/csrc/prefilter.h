@@ -72,7 +72,17 @@ namespace ibl
     size_t record_stride, dst_stride;
 
     int no_steal;             // A/B: a group whose chunk and pool are empty leaves instead of helping other SMs
+
+    // per-texel frames of the DESTINATION level for the pair kernel (launch_build_frames): kFrameFloats
+    // planes of 6*hd*wd floats — the face-local folded rows T, B, N (fold_face_row) and the same-face
+    // threshold.  They depend on the level's geometry alone, so the library keeps them per source size.
+    float const *frames;
   };
+
+  constexpr int kFrameFloats = 10;
+
+  // frames of every texel of the wd x hd destination of a ws x hs source level (proj_usable sizes)
+  cudaError_t launch_build_frames(float *frames, int ws, int hs, Quatf const quats[6], cudaStream_t stream);
 
   // ---- tail levels (prefilter_dn.cu, prefilter_tail_kernel): a few hundred texels ----
   //

@@ -524,6 +524,53 @@ namespace ibl
     signal_peers_when_last(p.signal);
   }
 
+  // ---- per-texel frames of a destination level -----------------------------------------------
+  //
+  // Normal, tangent frame (exactly rounded divisions and square roots, ~300 instructions), the change to
+  // face-local coordinates and the fold depend on the level's geometry alone.  The pair kernel used to
+  // redo them per tile in every one of its warps (3.5 % of its instructions on the 512^2 -> 256^2 level);
+  // now they are computed once per (source size, context) and read back as ten coalesced planes.
+  struct FrameQuats { Quatf q[6]; };
+
+  __global__ void __launch_bounds__(256) build_frames_kernel(float *__restrict__ frames, int wd, int hd, LevelGeom geom, FrameQuats quats)
+  {
+    const int texels = 6 * wd * hd;
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= texels)
+      return;
+
+    int x = o % wd, row = o / wd;
+    int face = row / hd, y = row - face * hd;
+
+    Vec3f N = texel_normal(quats.q[face], x, y, wd, hd);
+    Vec3f T, B;
+    tangent_frame(N, T, B);
+
+    Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
+    Vec3f Tf = fold_face_row(geom, Tl), Bf = fold_face_row(geom, Bl), Nf = fold_face_row(geom, Nl);
+
+    size_t plane = (size_t)texels;
+    frames[0 * plane + o] = Tf.x; frames[1 * plane + o] = Tf.y; frames[2 * plane + o] = Tf.z;
+    frames[3 * plane + o] = Bf.x; frames[4 * plane + o] = Bf.y; frames[5 * plane + o] = Bf.z;
+    frames[6 * plane + o] = Nf.x; frames[7 * plane + o] = Nf.y; frames[8 * plane + o] = Nf.z;
+    frames[9 * plane + o] = same_face_threshold(Nl);
+  }
+
+  cudaError_t launch_build_frames(float *frames, int ws, int hs, Quatf const quats[6], cudaStream_t stream)
+  {
+    int wd = ws >> 1, hd = hs >> 1;
+    int texels = 6 * wd * hd;
+    if (texels <= 0)
+      return cudaSuccess;
+
+    FrameQuats q;
+    for(int f = 0; f < 6; ++f)
+      q.q[f] = quats[f];
+
+    build_frames_kernel<<<(texels + 255) / 256, 256, 0, stream>>>(frames, wd, hd, make_level_geom(ws, hs), q);
+    return cudaGetLastError();
+  }
+
   // ---- two samples at a time --------------------------------------------------------------
   //
   // The kernel above packs the (a, b) face coordinates of ONE sample into fp32x2 operations; the
@@ -699,6 +746,7 @@ namespace ibl
   }
 
   // idx = raw index bits of both samples (what `base` has been moved back by), du/dv = fraction - 0.5
+  template<int EXP_ALU>
   __device__ __forceinline__ void gather_pair_proj(PrefilterDnParams const &p, uint4 const *base, uint32_t idx_a, uint32_t idx_b, f32x2 du, f32x2 dv, PairEntry const &e, Sums &acc)
   {
     uint4 ra = load_record(base, idx_a);
@@ -718,14 +766,14 @@ namespace ibl
     unpack2(fma2(p01, bcast2(-1.0f), v1), w11a, w11b);
 
     const uint32_t emul = p.exp_mul;
-    w00a = scale_by_exponent(w00a, ra.x & kDnMaskE, emul);
-    w10a = scale_by_exponent(w10a, ra.y & kDnMaskE, emul);
-    w01a = scale_by_exponent(w01a, ra.z & kDnMaskE, emul);
-    w11a = scale_by_exponent(w11a, ra.w & kDnMaskE, emul);
-    w00b = scale_by_exponent(w00b, rb.x & kDnMaskE, emul);
-    w10b = scale_by_exponent(w10b, rb.y & kDnMaskE, emul);
-    w01b = scale_by_exponent(w01b, rb.z & kDnMaskE, emul);
-    w11b = scale_by_exponent(w11b, rb.w & kDnMaskE, emul);
+    w00a = scale_tap<(EXP_ALU > 0)>(w00a, ra.x, emul);
+    w10a = scale_tap<(EXP_ALU > 2)>(w10a, ra.y, emul);
+    w01a = scale_tap<(EXP_ALU > 1)>(w01a, ra.z, emul);
+    w11a = scale_tap<(EXP_ALU > 3)>(w11a, ra.w, emul);
+    w00b = scale_tap<(EXP_ALU > 0)>(w00b, rb.x, emul);
+    w10b = scale_tap<(EXP_ALU > 2)>(w10b, rb.y, emul);
+    w01b = scale_tap<(EXP_ALU > 1)>(w01b, rb.z, emul);
+    w11b = scale_tap<(EXP_ALU > 3)>(w11b, rb.w, emul);
 
     acc.rg = fma2(pack2(u2f(ra.x >> 23), u2f(ra.x & kDnMaskG)), bcast2(w00a), acc.rg);
     acc.rg = fma2(pack2(u2f(ra.y >> 23), u2f(ra.y & kDnMaskG)), bcast2(w10a), acc.rg);
@@ -743,6 +791,7 @@ namespace ibl
   }
 
   // frame rows face-local and folded; `base` = records of the texel's face, moved back by kMagicBits
+  template<int EXP_ALU>
   __device__ __forceinline__ void pair_same_face_proj(PrefilterDnParams const &p, Frame const &t, uint4 const *base, PairEntry const &e, Sums &acc)
   {
     f32x2 la, lb, lm;
@@ -762,10 +811,11 @@ namespace ibl
     float ia, ib;
     unpack2(fma2(niv, bcast2(p.geom.neg_ws), mu), ia, ib);
 
-    gather_pair_proj(p, base, f2u(ia), f2u(ib), du, dv, e, acc);
+    gather_pair_proj<EXP_ALU>(p, base, f2u(ia), f2u(ib), du, dv, e, acc);
   }
 
   // frame rows in world coordinates; `base` = records moved back by geom.bias_general
+  template<int EXP_ALU>
   __device__ __forceinline__ void pair_general_proj(PrefilterDnParams const &p, Frame const &t, uint4 const *base, PairEntry const &e, Sums &acc)
   {
     f32x2 x, y, z;
@@ -792,7 +842,7 @@ namespace ibl
     float ia, ib;
     unpack2(fma2(cv, bcast2(p.geom.neg_ws), mu), ia, ib);
 
-    gather_pair_proj(p, base, fa * p.geom.face_size + f2u(ia), fb * p.geom.face_size + f2u(ib), du, dv, e, acc);
+    gather_pair_proj<EXP_ALU>(p, base, fa * p.geom.face_size + f2u(ia), fb * p.geom.face_size + f2u(ib), du, dv, e, acc);
   }
 
   template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false, bool PROJ = true>
@@ -892,38 +942,46 @@ namespace ibl
       Frame st;
       int n_same;
       {
-        Vec3f N = texel_normal(p.quats[face], x, y, p.wd, p.hd);
-        Vec3f T, B;
-        tangent_frame(N, T, B);
-
-        Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
-
-        float threshold = same_face_threshold(Nl);
-        threshold = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(threshold)));
+        float threshold;
 
         if (PROJ)
         {
-          st.T = fold_face_row(p.geom, Tl);
-          st.B = fold_face_row(p.geom, Bl);
-          st.N = fold_face_row(p.geom, Nl);
+          // the texel's frame from the per-level planes (launch_build_frames)
+          float const *f = p.frames + ((size_t)row * p.wd + x);
+          const size_t plane = (size_t)6 * p.hd * p.wd;
+          st.T = Vec3f{ __ldg(f + 0 * plane), __ldg(f + 1 * plane), __ldg(f + 2 * plane) };
+          st.B = Vec3f{ __ldg(f + 3 * plane), __ldg(f + 4 * plane), __ldg(f + 5 * plane) };
+          st.N = Vec3f{ __ldg(f + 6 * plane), __ldg(f + 7 * plane), __ldg(f + 8 * plane) };
+          threshold = __ldg(f + 9 * plane);
         }
         else
         {
+          Vec3f N = texel_normal(p.quats[face], x, y, p.wd, p.hd);
+          Vec3f T, B;
+          tangent_frame(N, T, B);
+
+          Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
+
+          threshold = same_face_threshold(Nl);
+
           st.T = Vec3f{ Tl.x * p.geom.hw, Tl.y * p.geom.hh, Tl.z };
           st.B = Vec3f{ Bl.x * p.geom.hw, Bl.y * p.geom.hh, Bl.z };
           st.N = Vec3f{ Nl.x * p.geom.hw, Nl.y * p.geom.hh, Nl.z };
         }
 
-        int lo = 0, hi = p.bands;
-        while (lo < hi)
+        threshold = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(threshold)));
+
+        // number of leading bands whose smallest lz lies above the threshold (band_min_lz decreases): the
+        // lanes look at 32 bands at a time
+        n_same = 0;
+        for(int base = 0; base < p.bands; base += 32)
         {
-          int mid = (lo + hi) >> 1;
-          if (__ldg(p.band_min_lz + mid) > threshold)
-            lo = mid + 1;
-          else
-            hi = mid;
+          int k = base + lane;
+          unsigned above = __ballot_sync(0xffffffffu, k < p.bands && __ldg(p.band_min_lz + k) > threshold);
+          n_same += __popc(above);
+          if (above != 0xffffffffu)
+            break;
         }
-        n_same = lo;
       }
 
       Sums acc;
@@ -943,7 +1001,7 @@ namespace ibl
           for(int k = 0; k < PAIRS; ++k)
           {
             if (PROJ)
-              pair_same_face_proj(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+              pair_same_face_proj<EXP_ALU>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
             else
               pair_same_face<EXP_ALU, RHI>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
           }
@@ -976,7 +1034,7 @@ namespace ibl
           for(int k = 0; k < PAIRS; ++k)
           {
             if (PROJ)
-              pair_general_proj(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+              pair_general_proj<EXP_ALU>(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
             else
               pair_general<EXP_ALU, RHI>(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
           }
@@ -1363,7 +1421,7 @@ namespace ibl
     // sizes of at most 2^22 texels per face; everything else runs the one-sample kernel
     bool pair_kernel_usable(PrefilterDnParams const &p)
     {
-      return p.table_proj != nullptr && proj_usable(p.geom.ws, p.geom.hs);
+      return p.table_proj != nullptr && p.frames != nullptr && proj_usable(p.geom.ws, p.geom.hs);
     }
   }
 
@@ -1374,7 +1432,8 @@ namespace ibl
   {
     PrefilterDnParams p = {};
     p.geom = make_level_geom(ws, hs);
-    p.table_proj = reinterpret_cast<float4 const*>(&p);      // any non-null value: only the geometry decides
+    p.table_proj = reinterpret_cast<float4 const*>(&p);      // any non-null values: only the geometry decides
+    p.frames = reinterpret_cast<float const*>(&p);
     return pair_kernel_usable(p);
   }
 
@@ -1448,17 +1507,17 @@ namespace ibl
       // round 2's arithmetic (three-term directions, integer record index, four weight products) for A/B
       case 95: return launch_dp<4, 8, true, true, 0, 1, false, false, true, false>(p, sm_count, stream, launched_grid);
       case 96: return launch_dp<8, 4, true, false, 0, 1, false, false, true, false>(p, sm_count, stream, launched_grid);
-      case 75: return launch_dp<4, 8, true, true, 1>(p, sm_count, stream, launched_grid);
-      case 76: return launch_dp<4, 8, true, true, 2>(p, sm_count, stream, launched_grid);
-      case 77: return launch_dp<4, 8, true, true, 3>(p, sm_count, stream, launched_grid);
-      case 78: return launch_dp<4, 8, true, true, 4>(p, sm_count, stream, launched_grid);
+      case 75: return launch_dp<4, 8, true, true, 1, 1, false, false, true>(p, sm_count, stream, launched_grid);
+      case 76: return launch_dp<4, 8, true, true, 2, 1, false, false, true>(p, sm_count, stream, launched_grid);
+      case 77: return launch_dp<4, 8, true, true, 3, 1, false, false, true>(p, sm_count, stream, launched_grid);
+      case 78: return launch_dp<4, 8, true, true, 4, 1, false, false, true>(p, sm_count, stream, launched_grid);
       case 79: return launch_dp<8, 4, true, false, 2>(p, sm_count, stream, launched_grid);
-      case 81: return launch_dp<4, 9, true, true>(p, sm_count, stream, launched_grid);
-      case 82: return launch_dp<4, 10, true, true>(p, sm_count, stream, launched_grid);
+      case 81: return launch_dp<4, 9, true, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid);
+      case 82: return launch_dp<4, 10, true, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid);
       case 83: return launch_dp<8, 5, true, false>(p, sm_count, stream, launched_grid);
-      case 84: return launch_dp<4, 6, true, true, 0, 2>(p, sm_count, stream, launched_grid);
-      case 85: return launch_dp<4, 8, true, true, 0, 2>(p, sm_count, stream, launched_grid);
-      case 86: return launch_dp<4, 5, true, true, 0, 2>(p, sm_count, stream, launched_grid);
+      case 84: return launch_dp<4, 6, true, true, 0, 2, false, false, true>(p, sm_count, stream, launched_grid);
+      case 85: return launch_dp<4, 8, true, true, 0, 2, false, false, true>(p, sm_count, stream, launched_grid);
+      case 86: return launch_dp<4, 5, true, true, 0, 2, false, false, true>(p, sm_count, stream, launched_grid);
       case 50: return launch_dn<4, 4, 8, true, false>(p, sm_count, stream, launched_grid);
       case 55: return launch_dn<16, 1, 2, true, false>(p, sm_count, stream, launched_grid);
       case 56: return launch_dn<16, 1, 2, false, false>(p, sm_count, stream, launched_grid);

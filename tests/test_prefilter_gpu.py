@@ -227,9 +227,13 @@ def test_row_slabs_reproduce_the_full_level(ctx):
 
 def test_kernel_variants_agree(ctx):
     """Every tile shape / warp split computes the same level (fp32 sums differ only by
-    association order: compare through the packed-word criterion)."""
+    association order: compare through the packed-word criterion).  The pair kernel scales its
+    directions by 1/lz (projective form), so a sample within rounding of a cube edge may take the
+    other face there: texels the oracle marks edge-ambiguous get the looser bound of tests/parity.py."""
     w, levels = 64, 6
     bits = synth.synthetic_chain(w, w, levels, probe=14, sun=False)
+    offs = datum_b200.level_offsets(w, w, levels)
+    clean = np.concatenate([oracle_lib.edge_ambiguous_counts(w >> level, w >> level, level, levels, 1024) == 0 for level in range(1, levels)])
     base = None
     try:
         for variant in (0, 51, 52, 53, 54, 70, 71, 72, 73, 80):     # every kernel shape the product library ships
@@ -238,37 +242,43 @@ def test_kernel_variants_agree(ctx):
             if base is None:
                 base = (words, f32)
             else:
-                assert oracle_lib.relative_error(f32, base[1]).max() <= 2e-4   # one-code word flips of level L feed level L+1
-                assert (words == base[0]).mean() >= 0.995
+                rel = oracle_lib.relative_error(f32, base[1])
+                assert rel[clean].max() <= 2e-4, (variant, float(rel[clean].max()))   # one-code word flips of level L feed level L+1
+                assert rel.max() <= 2e-2, (variant, float(rel.max()), int(rel.argmax()))
+                assert (words == base[0]).mean() >= 0.995, (variant, float((words == base[0]).mean()))
     finally:
         ctx.set_prefilter_variant(0)
 
 
-def test_pair_kernel_hands_over_when_its_biased_index_would_wrap(ctx):
-    """The two-samples-at-a-time kernel folds the magic-add bias into the record pointer; for a
-    few source widths (1370 is the smallest) bias + index would wrap in 32 bits and the launcher
-    must take the one-sample kernel instead: same words as that kernel pinned, and oracle parity."""
-    ws, levels, samples = 1370, 3, 8
-    # smooth radiance: with 8 samples over 6-stop per-texel noise the 1e-7 coordinate rounding of a
-    # 1370-wide face alone flips 8 % of the words by one code (DESIGN.md "Conditioning")
-    src = synth.synthetic_chain(ws, ws, 1, probe=23, noise=False, sun=False)
-    d_src = torch.from_numpy(src.view(np.int32)).to(DEV)
-    wd = ws // 2
+def test_pair_kernel_hands_over_when_its_fp32_index_does_not_apply(ctx):
+    """The two-samples-at-a-time kernel forms the record index in the fp32 adder (ibl_math.cuh, projective
+    form): that needs an even source size (the align-corners offset must be an integer) of at most 2^22
+    texels per face.  For an odd source the launcher must take the one-sample kernel instead: same words
+    as that kernel pinned, and oracle parity.  1370 (even, not a power of two: round 2's integer index
+    wrapped there) stays on the pair kernel and must agree with the oracle too."""
+    levels, samples = 3, 8
     rows = (0, 16)
-    outs = []
-    for variant in (0, 51, 70, 53, 72):
-        ctx.set_prefilter_variant(variant)
-        try:
-            out = torch.zeros(6 * wd * wd, dtype=torch.int32, device=DEV)
-            f32 = torch.zeros(6 * wd * wd * 3, dtype=torch.float32, device=DEV)
-            ctx.prefilter_level_device(d_src, ws, ws, 1, levels, samples, rows[0], rows[1], out, f32)
-            ctx.synchronize()
-        finally:
-            ctx.set_prefilter_variant(0)
-        outs.append((out.cpu().numpy().view(np.uint32), f32.cpu().numpy().reshape(-1, 3)))
-    assert np.array_equal(outs[2][1], outs[1][1])     # 70 ran as 51
-    assert np.array_equal(outs[4][1], outs[3][1])     # 72 ran as 53
-    parity.check_level(outs[0][0], outs[0][1], src, ws, ws, 1, levels, samples, rows[0], rows[1])
+    for ws, handed_over in ((1371, True), (1370, False)):
+        # smooth radiance: with 8 samples over 6-stop per-texel noise the 1e-7 coordinate rounding of a
+        # 1370-wide face alone flips 8 % of the words by one code (DESIGN.md "Conditioning")
+        src = synth.synthetic_chain(ws, ws, 1, probe=23, noise=False, sun=False)
+        d_src = torch.from_numpy(src.view(np.int32)).to(DEV)
+        wd = ws // 2
+        outs = []
+        for variant in (0, 51, 70, 53, 72):
+            ctx.set_prefilter_variant(variant)
+            try:
+                out = torch.zeros(6 * wd * wd, dtype=torch.int32, device=DEV)
+                f32 = torch.zeros(6 * wd * wd * 3, dtype=torch.float32, device=DEV)
+                ctx.prefilter_level_device(d_src, ws, ws, 1, levels, samples, rows[0], rows[1], out, f32)
+                ctx.synchronize()
+            finally:
+                ctx.set_prefilter_variant(0)
+            outs.append((out.cpu().numpy().view(np.uint32), f32.cpu().numpy().reshape(-1, 3)))
+        assert np.array_equal(outs[2][1], outs[1][1]) == handed_over     # 70 ran as 51
+        assert np.array_equal(outs[4][1], outs[3][1]) == handed_over     # 72 ran as 53
+        for k in (0, 2, 4):
+            parity.check_level(outs[k][0], outs[k][1], src, ws, ws, 1, levels, samples, rows[0], rows[1])
 
 
 def test_directions_on_cube_edges_stay_inside_the_face(ctx):
