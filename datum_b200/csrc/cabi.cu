@@ -65,6 +65,7 @@ namespace
     float4 *d_banded = nullptr;  // the entries in banded ring order (ibl_tables.h), scaled by kDnTableScale
     float4 *d_pairs = nullptr;   // the banded entries, last band filled up, interleaved two by two (build_paired_entries)
     float4 *d_proj = nullptr;    // the same with (lx/lz, ly/lz) in place of (lx, ly): the pair kernel's projective form
+    float4 *d_banded_proj = nullptr; // d_banded with (lx/lz, ly/lz) in place of (lx, ly): the tail kernel's
     float *d_band_min = nullptr; // smallest lz per band
     int bands = 0;
   };
@@ -129,6 +130,7 @@ struct datum_ibl_ctx
   size_t host_stage_bytes = 0;
   DeviceBuffer<uint4> records;    // quad records of the current source level
   std::map<std::pair<int, int>, float*> frames; // source size -> per-texel frames of the destination level (ibl::launch_build_frames)
+  std::map<std::pair<int, int>, float*> world_frames; // destination size -> world-space T, B, N per texel (tail kernel; levels of at most kWorldFrameTexels)
   DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
   int prefilter_no_steal = 0;
   int sh9_kernel = 0, sh9_rows_per_item = 0;   // A/B: 0 = column strips / automatic run length
@@ -191,6 +193,7 @@ namespace
     if (t.d_band_min) cudaFree(t.d_band_min);
     if (t.d_pairs) cudaFree(t.d_pairs);
     if (t.d_proj) cudaFree(t.d_proj);
+    if (t.d_banded_proj) cudaFree(t.d_banded_proj);
     t = DeviceTable();
   }
 
@@ -229,6 +232,13 @@ namespace
         std::vector<float> paired = ibl::build_paired_entries(banded, ibl::kDnTableScale);
         std::vector<float> proj = ibl::build_paired_entries(banded, ibl::kDnTableScale, true);
 
+        std::vector<ibl::SampleEntry> banded_proj = banded.level.entries;
+        for(auto &e : banded_proj)
+        {
+          e.lx = (float)((double)e.lx / (double)e.lz); e.ly = (float)((double)e.ly / (double)e.lz);
+          e.lz *= ibl::kDnTableScale; e.wh *= ibl::kDnTableScale;
+        }
+
         for(auto &e : banded.level.entries)
         {
           e.lx *= ibl::kDnTableScale; e.ly *= ibl::kDnTableScale; e.lz *= ibl::kDnTableScale; e.wh *= ibl::kDnTableScale;
@@ -246,6 +256,10 @@ namespace
           err = cudaMalloc(&t.d_pairs, sizeof(float) * (paired.size() > 0 ? paired.size() : 4));
         if (err == cudaSuccess)
           err = cudaMemcpyAsync(t.d_pairs, paired.data(), sizeof(float) * paired.size(), cudaMemcpyHostToDevice, ctx->stream);
+        if (err == cudaSuccess)
+          err = cudaMalloc(&t.d_banded_proj, sizeof(float4) * (size_t)(t.count > 0 ? t.count : 1));
+        if (err == cudaSuccess)
+          err = cudaMemcpyAsync(t.d_banded_proj, banded_proj.data(), sizeof(float4) * (size_t)t.count, cudaMemcpyHostToDevice, ctx->stream);
         if (err == cudaSuccess)
           err = cudaMalloc(&t.d_proj, sizeof(float) * (proj.size() > 0 ? proj.size() : 4));
         if (err == cudaSuccess)
@@ -429,8 +443,35 @@ namespace
 
     if ((ctx->prefilter_variant == 0 && tail) || ctx->prefilter_variant == 80 || (ctx->prefilter_variant >= 50 && wd < 8))
     {
+      // world-space frames of the destination level: geometry only, kept per size (small levels only:
+      // this kernel runs slabs of at most kTailTexels texels, a bigger level is a shared probe's)
+      float const *world_frames = nullptr;
+      const size_t kWorldFrameTexels = (size_t)1 << 20;
+      if ((size_t)6 * wd * hd <= kWorldFrameTexels)
+      {
+        auto found = ctx->world_frames.find(std::make_pair(wd, hd));
+        if (found == ctx->world_frames.end())
+        {
+          float *built = nullptr;
+          cudaError_t err = cudaMalloc(&built, sizeof(float) * (size_t)ibl::kWorldFrameFloats * 6 * wd * hd);
+          if (err == cudaSuccess)
+          {
+            err = ibl::launch_build_world_frames(built, wd, hd, ctx->quats, ctx->stream);
+            if (err != cudaSuccess)
+              cudaFree(built);
+          }
+          if (err != cudaSuccess)
+            return fail_cuda("build_world_frames", err);
+          ctx->launches += 1;
+          found = ctx->world_frames.emplace(std::make_pair(wd, hd), built).first;
+        }
+        world_frames = found->second;
+      }
+
       ibl::PrefilterTailParams p = {};
       p.src = d_src;
+      p.world_frames = world_frames;
+      p.table_proj = table.d_banded_proj;
       p.table = table.d_banded;
       p.table_count = table.count;
       p.dst_words = d_dst_words;
@@ -1048,6 +1089,9 @@ extern "C"
     for(auto &entry : ctx->frames)
       cudaFree(entry.second);
     ctx->frames.clear();
+    for(auto &entry : ctx->world_frames)
+      cudaFree(entry.second);
+    ctx->world_frames.clear();
     ctx->queue_heads.release();
     ctx->peer_ticket.release();
     ctx->sh_weights.release();

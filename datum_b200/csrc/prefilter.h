@@ -80,6 +80,10 @@ namespace ibl
   };
 
   constexpr int kFrameFloats = 10;
+  constexpr int kWorldFrameFloats = 9;
+
+  // world-space T, B, N of every texel of the wd x hd destination level (what the tail kernel's CTAs need)
+  cudaError_t launch_build_world_frames(float *frames, int wd, int hd, Quatf const quats[6], cudaStream_t stream);
 
   // frames of every texel of the wd x hd destination of a ws x hs source level (proj_usable sizes)
   cudaError_t launch_build_frames(float *frames, int ws, int hs, Quatf const quats[6], cudaStream_t stream);
@@ -92,6 +96,8 @@ namespace ibl
   {
     uint32_t const *src;      // SOURCE level words (6*ws*hs), tools/ibl.cpp layout
     float4 const *table;      // banded sample table of this level scaled by kDnTableScale (any order works)
+    float4 const *table_proj; // the same entries as (lx/lz, ly/lz, lz, wh): read instead when proj_usable(ws, hs)
+    float const *world_frames; // kWorldFrameFloats planes of 6*hd*wd floats: T, B, N of every destination texel (launch_build_world_frames), or null: computed per CTA
     int table_count;
     uint32_t *dst_words;
     float *dst_f32;

@@ -556,6 +556,40 @@ namespace ibl
     frames[9 * plane + o] = same_face_threshold(Nl);
   }
 
+  __global__ void __launch_bounds__(256) build_world_frames_kernel(float *__restrict__ frames, int wd, int hd, FrameQuats quats)
+  {
+    const int texels = 6 * wd * hd;
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= texels)
+      return;
+
+    int x = o % wd, row = o / wd;
+    int face = row / hd, y = row - face * hd;
+
+    Vec3f N = texel_normal(quats.q[face], x, y, wd, hd);
+    Vec3f T, B;
+    tangent_frame(N, T, B);
+
+    size_t plane = (size_t)texels;
+    frames[0 * plane + o] = T.x; frames[1 * plane + o] = T.y; frames[2 * plane + o] = T.z;
+    frames[3 * plane + o] = B.x; frames[4 * plane + o] = B.y; frames[5 * plane + o] = B.z;
+    frames[6 * plane + o] = N.x; frames[7 * plane + o] = N.y; frames[8 * plane + o] = N.z;
+  }
+
+  cudaError_t launch_build_world_frames(float *frames, int wd, int hd, Quatf const quats[6], cudaStream_t stream)
+  {
+    int texels = 6 * wd * hd;
+    if (texels <= 0)
+      return cudaSuccess;
+
+    FrameQuats q;
+    for(int f = 0; f < 6; ++f)
+      q.q[f] = quats[f];
+
+    build_world_frames_kernel<<<(texels + 255) / 256, 256, 0, stream>>>(frames, wd, hd, q);
+    return cudaGetLastError();
+  }
+
   cudaError_t launch_build_frames(float *frames, int ws, int hs, Quatf const quats[6], cudaStream_t stream)
   {
     int wd = ws >> 1, hd = hs >> 1;
@@ -1108,7 +1142,7 @@ namespace ibl
   // the face anyway); the four words of a footprint are read from the source level itself (it fits in
   // L1/L2) in the reference's own bit layout (raw_accumulate_tap), so the level needs no record pass: one
   // launch instead of two.  Arithmetic per sample is the one-sample kernel's general path.
-  template<int NW>
+  template<int NW, bool PROJ>
   __global__ void __launch_bounds__(32 * NW) prefilter_tail_kernel(PrefilterTailParams p)
   {
     __shared__ float s_red[NW][3];
@@ -1128,8 +1162,14 @@ namespace ibl
     const int face = row / p.hd;
     const int y = row - face * p.hd;
 
-    // the texel's frame (exactly rounded divisions and square roots, ~200 instructions) once per CTA
-    if (threadIdx.x == 0)
+    // the texel's frame: from the per-level planes (launch_build_world_frames), else computed here once per
+    // CTA (exactly rounded divisions and square roots, ~200 dependent instructions by one thread)
+    if (p.world_frames)
+    {
+      if (threadIdx.x < 9)
+        s_frame[threadIdx.x] = __ldg(p.world_frames + (size_t)threadIdx.x * ((size_t)6 * p.hd * p.wd) + ((size_t)row * p.wd + x));
+    }
+    else if (threadIdx.x == 0)
     {
       Vec3f n = texel_normal(p.quats[face], x, y, p.wd, p.hd);
       Vec3f t, b;
@@ -1149,17 +1189,31 @@ namespace ibl
 
     for(int s = threadIdx.x; s < p.table_count; s += 32 * NW)
     {
-      float4 e = __ldg(p.table + s);
+      float4 e = __ldg((PROJ ? p.table_proj : p.table) + s);
 
-      float Lx = fmaf(e.z, N.x, fmaf(e.y, B.x, e.x * T.x));
-      float Ly = fmaf(e.z, N.y, fmaf(e.y, B.y, e.x * T.y));
-      float Lz = fmaf(e.z, N.z, fmaf(e.y, B.z, e.x * T.z));
+      float du, dv, w[4];
+      uint32_t idx;                 // top-left texel of the footprint; i <= ws-2, j <= hs-2
 
-      float du, dv;
-      uint32_t idx = cube_footprint(p.geom, Lx, Ly, Lz, du, dv);     // top-left texel of the footprint; i <= ws-2, j <= hs-2
+      if (PROJ)
+      {
+        // e.x, e.y hold lx/lz, ly/lz (ibl_math.cuh, projective form)
+        float Lx = fmaf(e.x, T.x, fmaf(e.y, B.x, N.x));
+        float Ly = fmaf(e.x, T.y, fmaf(e.y, B.y, N.y));
+        float Lz = fmaf(e.x, T.z, fmaf(e.y, B.z, N.z));
 
-      float w[4];
-      footprint_weights(du, dv, e.w, e.z, w);
+        uint32_t f;
+        idx = cube_footprint_proj(p.geom, Lx, Ly, Lz, du, dv, f) + f * p.geom.face_size - p.geom.bias_general;
+        footprint_weights_diff(du, dv, e.w, e.z, w);
+      }
+      else
+      {
+        float Lx = fmaf(e.z, N.x, fmaf(e.y, B.x, e.x * T.x));
+        float Ly = fmaf(e.z, N.y, fmaf(e.y, B.y, e.x * T.y));
+        float Lz = fmaf(e.z, N.z, fmaf(e.y, B.z, e.x * T.z));
+
+        idx = cube_footprint(p.geom, Lx, Ly, Lz, du, dv);
+        footprint_weights(du, dv, e.w, e.z, w);
+      }
 
       uint32_t const *t = p.src + (size_t)probe * p.src_stride + idx;
       raw_accumulate_tap(__ldg(t), w[0], p.exp_mul, acc);
@@ -1235,14 +1289,23 @@ namespace ibl
     // the sums, and a batch must give the words of single calls.
     (void)sm_count;
     int grid = texels * p.probes;
+    const bool proj = p.table_proj != nullptr && proj_usable(p.geom.ws, p.geom.hs);
     if (texels >= 4096 || p.table_count <= 128)
-      prefilter_tail_kernel<4><<<grid, 128, 0, stream>>>(p);
+    {
+      if (proj) prefilter_tail_kernel<4, true><<<grid, 128, 0, stream>>>(p); else prefilter_tail_kernel<4, false><<<grid, 128, 0, stream>>>(p);
+    }
     else if (texels >= 1024 || p.table_count <= 256)
-      prefilter_tail_kernel<8><<<grid, 256, 0, stream>>>(p);
+    {
+      if (proj) prefilter_tail_kernel<8, true><<<grid, 256, 0, stream>>>(p); else prefilter_tail_kernel<8, false><<<grid, 256, 0, stream>>>(p);
+    }
     else if (texels >= 256 || p.table_count <= 512)
-      prefilter_tail_kernel<16><<<grid, 512, 0, stream>>>(p);
+    {
+      if (proj) prefilter_tail_kernel<16, true><<<grid, 512, 0, stream>>>(p); else prefilter_tail_kernel<16, false><<<grid, 512, 0, stream>>>(p);
+    }
     else
-      prefilter_tail_kernel<32><<<grid, 1024, 0, stream>>>(p);
+    {
+      if (proj) prefilter_tail_kernel<32, true><<<grid, 1024, 0, stream>>>(p); else prefilter_tail_kernel<32, false><<<grid, 1024, 0, stream>>>(p);
+    }
 
     return cudaGetLastError();
   }
@@ -1507,6 +1570,7 @@ namespace ibl
       // round 2's arithmetic (three-term directions, integer record index, four weight products) for A/B
       case 95: return launch_dp<4, 8, true, true, 0, 1, false, false, true, false>(p, sm_count, stream, launched_grid);
       case 96: return launch_dp<8, 4, true, false, 0, 1, false, false, true, false>(p, sm_count, stream, launched_grid);
+      case 97: return launch_dp<8, 4, true, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid);      // 8 warps per tile with tile queues, lean
       case 75: return launch_dp<4, 8, true, true, 1, 1, false, false, true>(p, sm_count, stream, launched_grid);
       case 76: return launch_dp<4, 8, true, true, 2, 1, false, false, true>(p, sm_count, stream, launched_grid);
       case 77: return launch_dp<4, 8, true, true, 3, 1, false, false, true>(p, sm_count, stream, launched_grid);
