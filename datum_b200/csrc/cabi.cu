@@ -64,7 +64,9 @@ namespace
     double total_weight = 0;
     float4 *d_banded = nullptr;  // the entries in banded ring order (ibl_tables.h), scaled by kDnTableScale
     float4 *d_pairs = nullptr;   // the banded entries, last band filled up, interleaved two by two (build_paired_entries)
-    float4 *d_proj = nullptr;    // the same with (lx/lz, ly/lz) in place of (lx, ly): the pair kernel's projective form
+    float4 *d_sector[2] = { nullptr, nullptr };   // the pair kernel's tables, one azimuth sector per warp, for 4 and 8 warps per tile (ibl_tables.h)
+    float *d_sector_rho[2] = { nullptr, nullptr };
+    int sector_bands[2] = { 0, 0 };
     float4 *d_banded_proj = nullptr; // d_banded with (lx/lz, ly/lz) in place of (lx, ly): the tail kernel's
     float *d_band_min = nullptr; // smallest lz per band
     int bands = 0;
@@ -192,7 +194,11 @@ namespace
     if (t.d_banded) cudaFree(t.d_banded);
     if (t.d_band_min) cudaFree(t.d_band_min);
     if (t.d_pairs) cudaFree(t.d_pairs);
-    if (t.d_proj) cudaFree(t.d_proj);
+    for(int i = 0; i < 2; ++i)
+    {
+      if (t.d_sector[i]) cudaFree(t.d_sector[i]);
+      if (t.d_sector_rho[i]) cudaFree(t.d_sector_rho[i]);
+    }
     if (t.d_banded_proj) cudaFree(t.d_banded_proj);
     t = DeviceTable();
   }
@@ -230,7 +236,7 @@ namespace
         t.bands = (int)banded.band_min_lz.size();
 
         std::vector<float> paired = ibl::build_paired_entries(banded, ibl::kDnTableScale);
-        std::vector<float> proj = ibl::build_paired_entries(banded, ibl::kDnTableScale, true);
+        ibl::SectorTable sector[2] = { ibl::build_sector_entries(host, 4, ibl::kSampleBand, ibl::kDnTableScale), ibl::build_sector_entries(host, 8, ibl::kSampleBand, ibl::kDnTableScale) };
 
         std::vector<ibl::SampleEntry> banded_proj = banded.level.entries;
         for(auto &e : banded_proj)
@@ -260,10 +266,18 @@ namespace
           err = cudaMalloc(&t.d_banded_proj, sizeof(float4) * (size_t)(t.count > 0 ? t.count : 1));
         if (err == cudaSuccess)
           err = cudaMemcpyAsync(t.d_banded_proj, banded_proj.data(), sizeof(float4) * (size_t)t.count, cudaMemcpyHostToDevice, ctx->stream);
-        if (err == cudaSuccess)
-          err = cudaMalloc(&t.d_proj, sizeof(float) * (proj.size() > 0 ? proj.size() : 4));
-        if (err == cudaSuccess)
-          err = cudaMemcpyAsync(t.d_proj, proj.data(), sizeof(float) * proj.size(), cudaMemcpyHostToDevice, ctx->stream);
+        for(int i = 0; i < 2; ++i)
+        {
+          t.sector_bands[i] = sector[i].bands;
+          if (err == cudaSuccess)
+            err = cudaMalloc(&t.d_sector[i], sizeof(float) * sector[i].entries.size());
+          if (err == cudaSuccess)
+            err = cudaMemcpyAsync(t.d_sector[i], sector[i].entries.data(), sizeof(float) * sector[i].entries.size(), cudaMemcpyHostToDevice, ctx->stream);
+          if (err == cudaSuccess)
+            err = cudaMalloc(&t.d_sector_rho[i], sizeof(float) * sector[i].rho_max.size());
+          if (err == cudaSuccess)
+            err = cudaMemcpyAsync(t.d_sector_rho[i], sector[i].rho_max.data(), sizeof(float) * sector[i].rho_max.size(), cudaMemcpyHostToDevice, ctx->stream);
+        }
 
         if (err == cudaSuccess)
           err = cudaStreamSynchronize(ctx->stream); // `host` and `banded` die at the end of this iteration
@@ -386,7 +400,12 @@ namespace
     p.records = ctx->records.ptr;
     p.table = table.d_banded;
     p.table_pairs = table.d_pairs;
-    p.table_proj = table.d_proj;
+    for(int i = 0; i < 2; ++i)
+    {
+      p.table_sector[i] = table.d_sector[i];
+      p.sector_rho[i] = table.d_sector_rho[i];
+      p.sector_bands[i] = table.sector_bands[i];
+    }
     p.band_min_lz = table.d_band_min;
     p.table_count = table.count;
     p.bands = table.bands;

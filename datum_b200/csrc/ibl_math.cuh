@@ -346,6 +346,55 @@ namespace ibl
     w[1] = v0 - w[0]; w[3] = v1 - w[2];
   }
 
+  // ---- same-face limits per azimuth sector (prefilter_dp_kernel) ----
+  //
+  // same_face_threshold above bounds the lobe angle whatever the azimuth.  But a sample leaves through ONE
+  // edge, and only if it points towards it: with (X, Y) = (lx/lz, ly/lz) = rho * (cos phi, sin phi) — the
+  // tangent-plane coordinates the projective table holds — the unnormalised direction is X*T + Y*B + N and
+  //     a - m <= 0   <=>   X*(Ta - Tm) + Y*(Ba - Bm) <= Nm - Na          (edge +a; -a, +b, -b alike)
+  // in face-local coordinates: rho * (p cos phi + q sin phi) <= d.  Over an azimuth sector the bracket is at
+  // most |(p, q)| when (p, q) points into the sector, else its larger end value — often negative: no sample
+  // of that sector ever crosses that edge.  The pair kernel gives every warp of a tile ONE sector of every
+  // band (ibl_tables.h, build_sector_entries), so each warp gets its own count of same-face bands from the
+  // limit of its sector: rho <= min over edges of d / max(bracket).  With (p, q) inside the sector this is
+  // tan(angular distance to the edge plane), the isotropic bound; otherwise it is larger.
+  // Sector k of kFrameSectors = 8 spans the azimuths [-pi + k*pi/4, -pi + (k+1)*pi/4].
+  constexpr int kFrameSectors = 8;
+  constexpr float kSectorMargin = 1e-5f;   // fp32 slop of the frame, the direction and the sector bounds
+
+  IBL_HD void sector_rho_limits(Vec3f T, Vec3f B, Vec3f N, float out[kFrameSectors])
+  {
+    const float h = 0.70710678118654752f;
+    const float ex[kFrameSectors + 1] = { -1.0f, -h, 0.0f, h, 1.0f, h, 0.0f, -h, -1.0f };
+    const float ey[kFrameSectors + 1] = { 0.0f, -h, -1.0f, -h, 0.0f, h, 1.0f, h, 0.0f };
+
+    // edges +a, -a, +b, -b of the face |a| <= m, |b| <= m
+    const float p[4] = { T.x - T.z, -T.x - T.z, T.y - T.z, -T.y - T.z };
+    const float q[4] = { B.x - B.z, -B.x - B.z, B.y - B.z, -B.y - B.z };
+    const float d[4] = { N.z - N.x, N.z + N.x, N.z - N.y, N.z + N.y };
+
+    for(int k = 0; k < kFrameSectors; ++k)
+    {
+      float limit = 3.0e38f;
+
+      for(int e = 0; e < 4; ++e)
+      {
+        float c0 = ex[k] * p[e] + ey[k] * q[e];
+        float c1 = ex[k + 1] * p[e] + ey[k + 1] * q[e];
+        bool inside = (ex[k] * q[e] - ey[k] * p[e] >= 0.0f) && (ex[k + 1] * q[e] - ey[k + 1] * p[e] <= 0.0f);
+        float most = inside ? sqrtf(p[e] * p[e] + q[e] * q[e]) : fmaxf(c0, c1);
+        float room = d[e] - kSectorMargin;
+
+        if (room <= 0.0f)
+          limit = 0.0f;
+        else if (most > 0.0f)
+          limit = fminf(limit, room / (most * (1.0f + kSectorMargin)));
+      }
+
+      out[k] = limit * (1.0f - kSectorMargin);
+    }
+  }
+
   // ---- packed-texel accumulation ----
   //
   // A quad record holds the four rgbe words of a bilinear footprint, each rotated

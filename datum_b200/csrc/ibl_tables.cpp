@@ -194,4 +194,93 @@ namespace ibl
 
     return out;
   }
+
+  SectorTable build_sector_entries(LevelSamples const &level, int sectors, int band, float scale)
+  {
+    SectorTable out;
+    out.sectors = sectors;
+    out.band = band;
+
+    const int per = band / sectors;
+    const double kPi = 3.14159265358979323846;
+
+    struct Projective { float x, y, lz, wh; double phi; };
+    std::vector<std::vector<Projective>> cut(sectors);
+
+    for(auto const &e : level.entries)
+    {
+      Projective s;
+      s.x = (float)((double)e.lx / (double)e.lz);     // lz > 0 for every accepted sample (ibl.cpp:178)
+      s.y = (float)((double)e.ly / (double)e.lz);
+      s.lz = e.lz * scale;
+      s.wh = e.wh * scale;
+      s.phi = std::atan2((double)s.y, (double)s.x);   // of the values the kernel multiplies with
+
+      int k = (int)std::floor((s.phi + kPi) / (2 * kPi / sectors));
+      k = std::min(std::max(k, 0), sectors - 1);
+      cut[k].push_back(s);
+    }
+
+    size_t longest = 0;
+    for(auto &c : cut)
+    {
+      std::stable_sort(c.begin(), c.end(), [](Projective const &a, Projective const &b) { return a.lz > b.lz; });
+      longest = std::max(longest, c.size());
+    }
+
+    out.bands = (int)((longest + (size_t)per - 1) / (size_t)per);
+    if (out.bands < 1)
+      out.bands = 1;
+
+    const float tiny = std::ldexp(scale, -60);
+    std::vector<Projective> flat((size_t)out.bands * band);
+    out.rho_max.assign((size_t)sectors * out.bands, 0.0f);
+
+    for(int w = 0; w < sectors; ++w)
+    {
+      float running = 0.0f;    // shares are lz-sorted, so the maximum grows anyway; keep it monotone by construction
+
+      for(int k = 0; k < out.bands; ++k)
+      {
+        std::vector<Projective> share;
+        for(int i = 0; i < per; ++i)
+        {
+          size_t at = (size_t)k * per + i;
+          if (at < cut[w].size())
+            share.push_back(cut[w][at]);
+        }
+
+        for(auto const &s : share)
+        {
+          float rho = (float)std::hypot((double)s.x, (double)s.y);
+          running = std::max(running, std::nextafter(rho, 3.0e38f));
+        }
+        out.rho_max[(size_t)w * out.bands + k] = share.empty() ? 0.0f : running;
+
+        std::stable_sort(share.begin(), share.end(), [](Projective const &a, Projective const &b) { return a.phi < b.phi; });
+        while ((int)share.size() < per)
+          share.push_back(Projective{ 0.0f, 0.0f, tiny, 0.5f * tiny, 0.0 });
+
+        for(int i = 0; i < per; ++i)
+          flat[(size_t)k * band + (size_t)w * per + i] = share[i];
+      }
+
+      // a filled-up share costs nothing on either path: let it count as same-face whenever the one before does
+      for(int k = 1; k < out.bands; ++k)
+        if (out.rho_max[(size_t)w * out.bands + k] == 0.0f)
+          out.rho_max[(size_t)w * out.bands + k] = out.rho_max[(size_t)w * out.bands + k - 1];
+    }
+
+    out.entries.resize(4 * flat.size());
+    for(size_t i = 0; i < flat.size(); i += 2)
+    {
+      Projective const &a = flat[i];
+      Projective const &b = flat[i + 1];
+      float *o = out.entries.data() + 4 * i;
+      o[0] = a.x; o[1] = b.x; o[2] = a.y; o[3] = b.y;
+      o[4] = a.lz; o[5] = b.lz; o[6] = a.wh; o[7] = b.wh;
+    }
+
+    return out;
+  }
 }

@@ -62,6 +62,23 @@ namespace ibl
   // keep the scale: they only weigh the taps then.
   std::vector<float> build_paired_entries(BandedSamples const &banded, float scale, bool projective = false);
 
+  // The pair kernel's table with one AZIMUTH SECTOR per warp (ibl_math.cuh, sector_rho_limits): the accepted
+  // samples are cut into `sectors` (4 or 8) equal azimuth sectors of the tangent plane, each sorted by
+  // decreasing lz; band k holds entries [k*per, (k+1)*per) of every sector, sector w at position w*per of
+  // the band (per = band / sectors: what warp w of a tile reads), ordered by azimuth inside.  Sectors that
+  // run out are filled up with samples of no effect (direction = the normal, weight 2^-60 of a real one).
+  // Entries are projective, (lx/lz, ly/lz, lz*scale, wh*scale), pair-interleaved like build_paired_entries.
+  // rho_max[w*bands + k] = largest |(lx/lz, ly/lz)| of sector w's share of band k (rounded up; 0 for a
+  // filled-up share), increasing in k: the kernel counts a warp's same-face bands against it.
+  struct SectorTable
+  {
+    int sectors = 0, band = 0, bands = 0;
+    std::vector<float> entries;    // 4 floats per entry, band * bands entries
+    std::vector<float> rho_max;    // sectors * bands
+  };
+
+  SectorTable build_sector_entries(LevelSamples const &level, int sectors, int band, float scale);
+
   // ibl.cpp:95-104
   float radicalinverse_VdC(uint32_t bits);
 }

@@ -46,7 +46,13 @@ namespace ibl
     uint4 const *records;     // quad records of the SOURCE level, words re-laid by pack_dn_word (6*ws*hs)
     float4 const *table;      // banded sample table of this level, every entry scaled by kDnTableScale
     float4 const *table_pairs; // the same entries, last band filled up, two entries interleaved per 32 bytes (ibl_tables.h)
-    float4 const *table_proj; // table_pairs with (lx/lz, ly/lz) for (lx, ly): what the pair kernel reads unless the source level is odd-sized or above 2^22 texels per face (proj_usable)
+    // the pair kernel's tables, one azimuth sector per warp (ibl_tables.h, build_sector_entries): [0] for 4 warps
+    // per tile, [1] for 8.  Projective entries (lx/lz, ly/lz, lz, wh), pair-interleaved; sector_rho[i][w*bands + k] =
+    // largest |(lx/lz, ly/lz)| of warp w's share of band k.  Used unless the source level is odd-sized or above
+    // 2^22 texels per face (proj_usable): then the one-sample kernel runs.
+    float4 const *table_sector[2];
+    float const *sector_rho[2];
+    int sector_bands[2];
     float const *band_min_lz; // smallest lz of each band (unscaled), decreasing
     int table_count;
     int bands;                // ceil(table_count / kSampleBand)
@@ -75,11 +81,12 @@ namespace ibl
 
     // per-texel frames of the DESTINATION level for the pair kernel (launch_build_frames): kFrameFloats
     // planes of 6*hd*wd floats — the face-local folded rows T, B, N (fold_face_row) and the same-face
-    // threshold.  They depend on the level's geometry alone, so the library keeps them per source size.
+    // limits of the eight azimuth sectors (sector_rho_limits).  They depend on the level's geometry alone,
+    // so the library keeps them per source size.
     float const *frames;
   };
 
-  constexpr int kFrameFloats = 10;
+  constexpr int kFrameFloats = 9 + kFrameSectors;
   constexpr int kWorldFrameFloats = 9;
 
   // world-space T, B, N of every texel of the wd x hd destination level (what the tail kernel's CTAs need)

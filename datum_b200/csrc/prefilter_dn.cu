@@ -553,7 +553,12 @@ namespace ibl
     frames[0 * plane + o] = Tf.x; frames[1 * plane + o] = Tf.y; frames[2 * plane + o] = Tf.z;
     frames[3 * plane + o] = Bf.x; frames[4 * plane + o] = Bf.y; frames[5 * plane + o] = Bf.z;
     frames[6 * plane + o] = Nf.x; frames[7 * plane + o] = Nf.y; frames[8 * plane + o] = Nf.z;
-    frames[9 * plane + o] = same_face_threshold(Nl);
+
+    float limits[kFrameSectors];
+    sector_rho_limits(Tl, Bl, Nl, limits);
+    #pragma unroll
+    for(int k = 0; k < kFrameSectors; ++k)
+      frames[(size_t)(9 + k) * plane + o] = limits[k];
   }
 
   __global__ void __launch_bounds__(256) build_world_frames_kernel(float *__restrict__ frames, int wd, int hd, FrameQuats quats)
@@ -883,7 +888,9 @@ namespace ibl
   __global__ void __launch_bounds__(32 * NW, MINB) prefilter_dp_kernel(PrefilterDnParams p)
   {
     extern __shared__ float4 smem[];
-    const int padded = p.bands * kSampleBand;
+    constexpr int SECTORS = NW == 8 ? 1 : 0;                       // which of the two sector tables
+    const int bands = PROJ ? p.sector_bands[SECTORS] : p.bands;
+    const int padded = bands * kSampleBand;
     float4 *s_table = smem;
     float *s_red = reinterpret_cast<float*>(smem + (SMEM_TABLE ? padded : 0));
     int *s_tile = reinterpret_cast<int*>(s_red + NW * 3 * 32);
@@ -895,11 +902,11 @@ namespace ibl
     if (SMEM_TABLE)
     {
       for(int i = tid; i < padded; i += 32 * NW)
-        s_table[i] = __ldg((PROJ ? p.table_proj : p.table_pairs) + i);
+        s_table[i] = __ldg((PROJ ? p.table_sector[SECTORS] : p.table_pairs) + i);
       __syncthreads();
     }
 
-    float4 const *table = SMEM_TABLE ? s_table : (PROJ ? p.table_proj : p.table_pairs);
+    float4 const *table = SMEM_TABLE ? s_table : (PROJ ? p.table_sector[SECTORS] : p.table_pairs);
 
     uint32_t smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -976,8 +983,6 @@ namespace ibl
       Frame st;
       int n_same;
       {
-        float threshold;
-
         if (PROJ)
         {
           // the texel's frame from the per-level planes (launch_build_frames)
@@ -986,7 +991,28 @@ namespace ibl
           st.T = Vec3f{ __ldg(f + 0 * plane), __ldg(f + 1 * plane), __ldg(f + 2 * plane) };
           st.B = Vec3f{ __ldg(f + 3 * plane), __ldg(f + 4 * plane), __ldg(f + 5 * plane) };
           st.N = Vec3f{ __ldg(f + 6 * plane), __ldg(f + 7 * plane), __ldg(f + 8 * plane) };
-          threshold = __ldg(f + 9 * plane);
+
+          // this warp reads ONE azimuth sector of every band: how far out its samples may lie before one of them
+          // can leave some texel's face (sector_rho_limits; the eight 45-degree sectors pair up for four warps)
+          float limit;
+          if (NW == 8)
+            limit = __ldg(f + (size_t)(9 + warp) * plane);
+          else
+            limit = fminf(__ldg(f + (size_t)(9 + 2 * warp) * plane), __ldg(f + (size_t)(10 + 2 * warp) * plane));
+          limit = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(limit)));   // limits are >= 0: bit order = value order
+
+          // leading bands whose share of this sector stays inside it (sector_rho increases with the band): the lanes
+          // look at 32 bands at a time
+          float const *rho = p.sector_rho[SECTORS] + warp * bands;
+          n_same = 0;
+          for(int base = 0; base < bands; base += 32)
+          {
+            int k = base + lane;
+            unsigned within = __ballot_sync(0xffffffffu, k < bands && __ldg(rho + k) <= limit);
+            n_same += __popc(within);
+            if (within != 0xffffffffu)
+              break;
+          }
         }
         else
         {
@@ -996,25 +1022,23 @@ namespace ibl
 
           Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
 
-          threshold = same_face_threshold(Nl);
+          float threshold = same_face_threshold(Nl);
+          threshold = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(threshold)));
 
           st.T = Vec3f{ Tl.x * p.geom.hw, Tl.y * p.geom.hh, Tl.z };
           st.B = Vec3f{ Bl.x * p.geom.hw, Bl.y * p.geom.hh, Bl.z };
           st.N = Vec3f{ Nl.x * p.geom.hw, Nl.y * p.geom.hh, Nl.z };
-        }
 
-        threshold = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(threshold)));
-
-        // number of leading bands whose smallest lz lies above the threshold (band_min_lz decreases): the
-        // lanes look at 32 bands at a time
-        n_same = 0;
-        for(int base = 0; base < p.bands; base += 32)
-        {
-          int k = base + lane;
-          unsigned above = __ballot_sync(0xffffffffu, k < p.bands && __ldg(p.band_min_lz + k) > threshold);
-          n_same += __popc(above);
-          if (above != 0xffffffffu)
-            break;
+          int lo = 0, hi = p.bands;
+          while (lo < hi)
+          {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(p.band_min_lz + mid) > threshold)
+              lo = mid + 1;
+            else
+              hi = mid;
+          }
+          n_same = lo;
         }
       }
 
@@ -1042,7 +1066,7 @@ namespace ibl
         }
       }
 
-      if (band < p.bands)
+      if (band < bands)
       {
         // back to world coordinates for the samples that may cross a face edge
         if (PROJ)
@@ -1062,7 +1086,7 @@ namespace ibl
         uint4 const *general = PROJ ? opaque(biased_probe + (size_t)(kMagicBits - p.geom.bias_general)) : biased_probe;
 
         #pragma unroll BAND_UNROLL
-        for(; band < p.bands; ++band)
+        for(; band < bands; ++band)
         {
           #pragma unroll
           for(int k = 0; k < PAIRS; ++k)
@@ -1452,7 +1476,8 @@ namespace ibl
         p.probes = 1;
       p.tiles = p.tiles_per_probe * p.probes;
 
-      size_t smem = (SMEM_TABLE ? (size_t)p.bands * kSampleBand * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
+      const int table_bands = PROJ ? p.sector_bands[NW == 8 ? 1 : 0] : p.bands;
+      size_t smem = (SMEM_TABLE ? (size_t)table_bands * kSampleBand * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
 
       int resident = 0;
       cudaError_t err = resident_ctas(kernel, 32 * NW, smem, &resident);
@@ -1484,7 +1509,7 @@ namespace ibl
     // sizes of at most 2^22 texels per face; everything else runs the one-sample kernel
     bool pair_kernel_usable(PrefilterDnParams const &p)
     {
-      return p.table_proj != nullptr && p.frames != nullptr && proj_usable(p.geom.ws, p.geom.hs);
+      return p.table_sector[0] != nullptr && p.table_sector[1] != nullptr && p.frames != nullptr && proj_usable(p.geom.ws, p.geom.hs);
     }
   }
 
@@ -1495,7 +1520,7 @@ namespace ibl
   {
     PrefilterDnParams p = {};
     p.geom = make_level_geom(ws, hs);
-    p.table_proj = reinterpret_cast<float4 const*>(&p);      // any non-null values: only the geometry decides
+    p.table_sector[0] = p.table_sector[1] = reinterpret_cast<float4 const*>(&p);      // any non-null values: only the geometry decides
     p.frames = reinterpret_cast<float const*>(&p);
     return pair_kernel_usable(p);
   }

@@ -136,7 +136,8 @@ extern "C" void emu_prefilter_level(uint32_t const *src, int ws, int hs, int lev
 // the exponent folded into the weight, per-channel normalisation.
 //
 // pairs = true: the arithmetic of prefilter_dp_kernel instead — the pair-interleaved PROJECTIVE table with
-// its filled-up last band (build_paired_entries), folded frame rows, the record index formed in the fp32
+// one azimuth sector per warp (build_sector_entries), the same-face decision from the sector's limit
+// (sector_rho_limits), folded frame rows, the record index formed in the fp32
 // adder and taken relative to a record pointer moved back by its bias, right-hand weights by difference
 // (ibl_math.cuh "projective form"), blue summed in one partial per sample of a pair.
 static void emu_dn_impl(uint32_t const *src, int ws, int hs, int level, int levels, int samples, int band, uint32_t *words, float *f32, bool pairs)
@@ -148,19 +149,21 @@ static void emu_dn_impl(uint32_t const *src, int ws, int hs, int level, int leve
     e.lx *= kDnTableScale; e.ly *= kDnTableScale; e.lz *= kDnTableScale; e.wh *= kDnTableScale;
   }
 
+  SectorTable sectors;
+  const int kSectors = 4;     // the kernel's shape for big levels: 4 warps per tile, one 90-degree sector each
   if (pairs)
   {
     if (!proj_usable(ws, hs))
       __builtin_trap();   // the launcher never picks the pair kernel here
-    std::vector<float> paired = build_paired_entries(banded, kDnTableScale, true);
-    table.assign(paired.size() / 4, SampleEntry{});
+    sectors = build_sector_entries(banded.level, kSectors, band, kDnTableScale);
+    table.assign(sectors.entries.size() / 4, SampleEntry{});
     for(size_t i = 0; i < table.size(); i += 2)
     {
-      float const *q = paired.data() + 4 * i;
+      float const *q = sectors.entries.data() + 4 * i;
       table[i] = SampleEntry{ q[0], q[2], q[4], q[6] };
       table[i + 1] = SampleEntry{ q[1], q[3], q[5], q[7] };
     }
-    if (table.size() != banded.band_min_lz.size() * (size_t)band)
+    if (table.size() != (size_t)sectors.bands * (size_t)band)
       __builtin_trap();
   }
   LevelGeom geom = make_level_geom(ws, hs);
@@ -223,10 +226,22 @@ static void emu_dn_impl(uint32_t const *src, int ws, int hs, int level, int leve
         float acc[3] = { 0, 0, 0 };
         float blue[2] = { 0, 0 };
 
+        // the pair kernel decides per warp (= azimuth sector) and tile; here per sector and texel
+        float limits[kFrameSectors];
+        sector_rho_limits(Tl, Bl, Nl, limits);
+
         for(size_t i = 0; i < table.size(); ++i)
         {
           SampleEntry const &e = table[i];
-          bool same = banded.band_min_lz[i / (size_t)band] > threshold;
+          bool same = !pairs && banded.band_min_lz[i / (size_t)band] > threshold;
+          if (pairs && !getenv("EMU_NOFAST"))
+          {
+            int w = (int)((i % (size_t)band) / (size_t)(band / kSectors));
+            float limit = 3.0e38f;
+            for(int k = w * kFrameSectors / kSectors; k < (w + 1) * kFrameSectors / kSectors; ++k)
+              limit = std::min(limit, limits[k]);
+            same = sectors.rho_max[(size_t)w * sectors.bands + i / (size_t)band] <= limit;
+          }
 
           float du, dv;
           uint32_t idx;
@@ -457,4 +472,115 @@ extern "C" int emu_table(int level, int levels, int samples, float *entries, dou
   }
   *total = table.total_weight;
   return table.accepted;
+}
+
+// ---- per-sector same-face limits (ibl_math.cuh sector_rho_limits, ibl_tables.h build_sector_entries) ----
+//
+// For the destination level of a ws x ws source: out[0] = share of the warp-samples the pair kernel sends
+// through the cube-face selection with ONE isotropic band count per tile (round 2's rule), out[1] = the
+// same with one count per warp from its sector's limit, out[2] = violations: samples a texel's own sector
+// limit admits to the same-face path whose direction (evaluated in double precision) is not strictly
+// inside the texel's face.  `sectors` = warps per tile (4 or 8).
+extern "C" void emu_sector_study(int ws, int level, int levels, int samples, int sectors, double *out)
+{
+  const int band = 16;
+  LevelSamples ls = build_level_samples(level, levels, samples);
+  BandedSamples banded = build_banded_samples(level, levels, samples, band);
+  SectorTable st = build_sector_entries(ls, sectors, band, 1.0f);
+  const int per = band / sectors;
+
+  const float kPi = 3.14159265358979323846f;
+  float angles[6] = { -kPi/2, kPi/2, -kPi/2, kPi/2, 0.0f, kPi };
+  int axes[6] = { 1, 1, 0, 0, 1, 1 };
+  Quatf quats[6];
+  for(int f = 0; f < 6; ++f)
+  {
+    float c = std::cos(angles[f]/2), s = std::sin(angles[f]/2);
+    quats[f] = Quatf{ c, axes[f] == 0 ? s : 0.0f, axes[f] == 1 ? s : 0.0f, 0.0f };
+  }
+
+  int wd = ws >> 1, hd = ws >> 1;
+  double old_general = 0, new_general = 0, old_total = 0, new_total = 0, violations = 0;
+
+  std::vector<float> limits((size_t)wd * hd * kFrameSectors);
+  std::vector<float> thresholds((size_t)wd * hd);
+
+  for(int face = 0; face < 6; ++face)
+  {
+    for(int y = 0; y < hd; ++y)
+      for(int x = 0; x < wd; ++x)
+      {
+        Vec3f N = texel_normal(quats[face], x, y, wd, hd);
+        Vec3f T, B;
+        tangent_frame(N, T, B);
+        Vec3f Tl = to_face_local(face, T), Bl = to_face_local(face, B), Nl = to_face_local(face, N);
+        float *lim = limits.data() + ((size_t)y * wd + x) * kFrameSectors;
+        sector_rho_limits(Tl, Bl, Nl, lim);
+        thresholds[(size_t)y * wd + x] = same_face_threshold(Nl);
+
+        // safety of the texel's own limits
+        for(int w = 0; w < sectors; ++w)
+        {
+          float rho_lane = 3.0e38f;
+          for(int k = w * kFrameSectors / sectors; k < (w + 1) * kFrameSectors / sectors; ++k)
+            rho_lane = std::min(rho_lane, lim[k]);
+
+          for(int k = 0; k < st.bands; ++k)
+          {
+            if (!(st.rho_max[(size_t)w * st.bands + k] <= rho_lane))
+              break;
+            for(int i = 0; i < per; ++i)
+            {
+              size_t e = (size_t)k * band + (size_t)w * per + i;
+              float const *q = st.entries.data() + 4 * (e & ~(size_t)1);
+              double X = q[0 + (e & 1)], Y = q[2 + (e & 1)];
+              double a = X * Tl.x + Y * Bl.x + Nl.x, b = X * Tl.y + Y * Bl.y + Nl.y, m = X * Tl.z + Y * Bl.z + Nl.z;
+              if (!(m > 0 && std::fabs(a) < m && std::fabs(b) < m))
+                violations += 1;
+            }
+          }
+        }
+      }
+
+    // tiles of 8x4 texels
+    for(int ty = 0; ty < hd; ty += 4)
+      for(int tx = 0; tx < wd; tx += 8)
+      {
+        float threshold = 0.0f;
+        float rho_tile[8];
+        for(int w = 0; w < sectors; ++w)
+          rho_tile[w] = 3.0e38f;
+
+        for(int y = ty; y < std::min(hd, ty + 4); ++y)
+          for(int x = tx; x < std::min(wd, tx + 8); ++x)
+          {
+            threshold = std::max(threshold, thresholds[(size_t)y * wd + x]);
+            float const *lim = limits.data() + ((size_t)y * wd + x) * kFrameSectors;
+            for(int w = 0; w < sectors; ++w)
+              for(int k = w * kFrameSectors / sectors; k < (w + 1) * kFrameSectors / sectors; ++k)
+                rho_tile[w] = std::min(rho_tile[w], lim[k]);
+          }
+
+        int bands_old = (int)banded.band_min_lz.size();
+        int n_same = 0;
+        while (n_same < bands_old && banded.band_min_lz[n_same] > threshold)
+          ++n_same;
+        old_general += bands_old - n_same;
+        old_total += bands_old;
+
+        for(int w = 0; w < sectors; ++w)
+        {
+          int n = 0;
+          while (n < st.bands && st.rho_max[(size_t)w * st.bands + n] <= rho_tile[w])
+            ++n;
+          new_general += st.bands - n;
+          new_total += st.bands;
+        }
+      }
+  }
+
+  out[0] = old_general / old_total;
+  out[1] = new_general / new_total;
+  out[2] = violations;
+  out[3] = (double)st.bands * band / (double)(banded.band_min_lz.size() * band);   // table growth through filling up
 }

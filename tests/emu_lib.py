@@ -26,6 +26,7 @@ def load():
         lib.emu_prefilter_level_dp.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2
         lib.emu_paired_table.argtypes = [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p, ctypes.c_int]
         lib.emu_paired_table.restype = ctypes.c_int
+        lib.emu_sector_study.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p]
         lib.emu_banded_table.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3
         lib.emu_banded_table.restype = ctypes.c_int
         lib.emu_patch_table.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3

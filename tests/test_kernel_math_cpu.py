@@ -151,6 +151,22 @@ def test_paired_table_is_the_banded_table_filled_up_and_interleaved(level, level
     assert np.all(fill[:, :2] == 0) and np.all(fill[:, 2] == scale * np.float32(2.0 ** -60)) and np.all(fill[:, 3] == 0.5 * fill[:, 2])
 
 
+@pytest.mark.parametrize("ws,level,levels,samples,sectors", [
+    (128, 1, 8, 1024, 4), (128, 2, 8, 1024, 4), (64, 3, 8, 1024, 8), (32, 6, 8, 1024, 8), (64, 1, 12, 4096, 4), (48, 2, 5, 100, 8), (16, 7, 8, 1024, 4)])
+def test_sector_limits_never_admit_a_sample_that_leaves_the_face(ws, level, levels, samples, sectors):
+    """The pair kernel's same-face decision (ibl_math.cuh sector_rho_limits + ibl_tables.h build_sector_entries):
+    every sample a texel's sector limit sends down the path WITHOUT cube-face selection must lie strictly
+    inside the texel's own face (checked in double precision for every texel, sector and sample); and the
+    per-warp rule sends fewer warp-samples through the face selection than one isotropic count per tile."""
+    emu = emu_lib.load()
+    out = np.zeros(4)
+    emu.emu_sector_study(ws, level, levels, samples, sectors, out.ctypes.data)
+    general_per_tile, general_per_sector, violations, growth = out
+    assert violations == 0
+    assert general_per_sector <= general_per_tile
+    assert 1.0 <= growth <= 1.2      # sectors hold (almost) equal shares of the accepted samples
+
+
 def test_dn_tap_decodes_every_field_exactly():
     """One tap of weight w through the subnormal-mantissa path == w * rgbe decode, for the
     extreme exponents, mantissas and weights (products must stay in the normal range)."""
