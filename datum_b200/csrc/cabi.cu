@@ -376,7 +376,7 @@ namespace
       if (found == ctx->frames.end())
       {
         float *built = nullptr;
-        err = cudaMalloc(&built, sizeof(float) * (size_t)ibl::kFrameFloats * 6 * wd * hd);
+        err = cudaMalloc(&built, sizeof(float) * ibl::frame_floats(wd, hd));
         if (err == cudaSuccess)
         {
           err = ibl::launch_build_frames(built, ws, hs, ctx->quats, ctx->stream);

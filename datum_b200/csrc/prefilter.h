@@ -79,14 +79,18 @@ namespace ibl
 
     int no_steal;             // A/B: a group whose chunk and pool are empty leaves instead of helping other SMs
 
-    // per-texel frames of the DESTINATION level for the pair kernel (launch_build_frames): kFrameFloats
-    // planes of 6*hd*wd floats — the face-local folded rows T, B, N (fold_face_row) and the same-face
-    // limits of the eight azimuth sectors (sector_rho_limits).  They depend on the level's geometry alone,
-    // so the library keeps them per source size.
+    // frames of the DESTINATION level for the pair kernel (launch_build_frames): nine planes of 6*hd*wd floats
+    // — the face-local folded rows T, B, N of every texel (fold_face_row) — followed by the same-face limits
+    // of the eight azimuth sectors (sector_rho_limits) per TILE of 8x4 texels: kFrameSectors planes of
+    // frame_tile_rows(hd) * frame_tiles_x(wd) floats, each the minimum over the tile's texels.  They depend
+    // on the level's geometry alone, so the library keeps them per source size.
     float const *frames;
   };
 
-  constexpr int kFrameFloats = 9 + kFrameSectors;
+  inline int frame_tiles_x(int wd) { return (wd + 7) / 8; }
+  inline int frame_tile_rows(int hd) { return (6 * hd + 3) / 4; }
+  inline size_t frame_floats(int wd, int hd) { return (size_t)9 * 6 * hd * wd + (size_t)kFrameSectors * frame_tile_rows(hd) * frame_tiles_x(wd); }
+
   constexpr int kWorldFrameFloats = 9;
 
   // world-space T, B, N of every texel of the wd x hd destination level (what the tail kernel's CTAs need)

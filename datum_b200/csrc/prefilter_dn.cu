@@ -554,11 +554,16 @@ namespace ibl
     frames[3 * plane + o] = Bf.x; frames[4 * plane + o] = Bf.y; frames[5 * plane + o] = Bf.z;
     frames[6 * plane + o] = Nf.x; frames[7 * plane + o] = Nf.y; frames[8 * plane + o] = Nf.z;
 
+    // sector limits: minimum over the texels of the 8x4 tile (limits are >= 0: bit order = value order;
+    // the planes start out as 0x7f7f7f7f = 3.4e38)
     float limits[kFrameSectors];
     sector_rho_limits(Tl, Bl, Nl, limits);
+
+    const int tiles_x = (wd + 7) / 8, tile_rows = (6 * hd + 3) / 4;
+    unsigned int *tile = reinterpret_cast<unsigned int*>(frames + 9 * plane) + (size_t)(row >> 2) * tiles_x + (x >> 3);
     #pragma unroll
     for(int k = 0; k < kFrameSectors; ++k)
-      frames[(size_t)(9 + k) * plane + o] = limits[k];
+      atomicMin(tile + (size_t)k * tile_rows * tiles_x, __float_as_uint(limits[k]));
   }
 
   __global__ void __launch_bounds__(256) build_world_frames_kernel(float *__restrict__ frames, int wd, int hd, FrameQuats quats)
@@ -605,6 +610,10 @@ namespace ibl
     FrameQuats q;
     for(int f = 0; f < 6; ++f)
       q.q[f] = quats[f];
+
+    cudaError_t err = cudaMemsetAsync(frames + (size_t)9 * texels, 0x7f, sizeof(float) * (size_t)kFrameSectors * frame_tile_rows(hd) * frame_tiles_x(wd), stream);
+    if (err != cudaSuccess)
+      return err;
 
     build_frames_kernel<<<(texels + 255) / 256, 256, 0, stream>>>(frames, wd, hd, make_level_geom(ws, hs), q);
     return cudaGetLastError();
@@ -993,13 +1002,22 @@ namespace ibl
           st.N = Vec3f{ __ldg(f + 6 * plane), __ldg(f + 7 * plane), __ldg(f + 8 * plane) };
 
           // this warp reads ONE azimuth sector of every band: how far out its samples may lie before one of them
-          // can leave some texel's face (sector_rho_limits; the eight 45-degree sectors pair up for four warps)
+          // can leave some texel's face (sector_rho_limits, kept as the minimum over the texels of every 8x4 tile
+          // of the level; a slab that starts between two such tile rows looks at both; the eight 45-degree sectors
+          // pair up for four warps)
           float limit;
-          if (NW == 8)
-            limit = __ldg(f + (size_t)(9 + warp) * plane);
-          else
-            limit = fminf(__ldg(f + (size_t)(9 + 2 * warp) * plane), __ldg(f + (size_t)(10 + 2 * warp) * plane));
-          limit = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(limit)));   // limits are >= 0: bit order = value order
+          {
+            const int tiles_x = (p.wd + 7) >> 3, tile_rows = (6 * p.hd + 3) >> 2;
+            const int top = __shfl_sync(0xffffffffu, row, 0), left = __shfl_sync(0xffffffffu, x, 0);     // lane 0 is always inside the slab
+            const int t0 = top >> 2, t1 = min((top + 3) >> 2, tile_rows - 1);
+            float const *tile = p.frames + 9 * plane + (left >> 3);
+            const size_t sector = (size_t)tile_rows * tiles_x;
+            const int first = NW == 8 ? warp : 2 * warp;
+
+            limit = fminf(__ldg(tile + first * sector + (size_t)t0 * tiles_x), __ldg(tile + first * sector + (size_t)t1 * tiles_x));
+            if (NW != 8)
+              limit = fminf(limit, fminf(__ldg(tile + (first + 1) * sector + (size_t)t0 * tiles_x), __ldg(tile + (first + 1) * sector + (size_t)t1 * tiles_x)));
+          }
 
           // leading bands whose share of this sector stays inside it (sector_rho increases with the band): the lanes
           // look at 32 bands at a time
