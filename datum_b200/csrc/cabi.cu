@@ -132,6 +132,7 @@ struct datum_ibl_ctx
   size_t host_stage_bytes = 0;
   DeviceBuffer<uint4> records;    // quad records of the current source level
   std::map<std::pair<int, int>, float*> frames; // source size -> per-texel frames of the destination level (ibl::launch_build_frames)
+  size_t frames_bytes = 0;
   std::map<std::pair<int, int>, float*> world_frames; // destination size -> world-space T, B, N per texel (tail kernel; levels of at most kWorldFrameTexels)
   DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
   int prefilter_no_steal = 0;
@@ -375,6 +376,18 @@ namespace
       auto found = ctx->frames.find(std::make_pair(ws, hs));
       if (found == ctx->frames.end())
       {
+        // a process that bakes many different sizes must not collect planes for ever: start over above 1 GiB
+        const size_t bytes = sizeof(float) * ibl::frame_floats(wd, hd);
+        if (ctx->frames_bytes + bytes > ((size_t)1 << 30) && !ctx->frames.empty())
+        {
+          cudaStreamSynchronize(ctx->stream);
+          for(auto &entry : ctx->frames)
+            cudaFree(entry.second);
+          ctx->frames.clear();
+          ctx->frames_bytes = 0;
+        }
+        ctx->frames_bytes += bytes;
+
         float *built = nullptr;
         err = cudaMalloc(&built, sizeof(float) * ibl::frame_floats(wd, hd));
         if (err == cudaSuccess)
@@ -1108,6 +1121,7 @@ extern "C"
     for(auto &entry : ctx->frames)
       cudaFree(entry.second);
     ctx->frames.clear();
+    ctx->frames_bytes = 0;
     for(auto &entry : ctx->world_frames)
       cudaFree(entry.second);
     ctx->world_frames.clear();

@@ -155,22 +155,12 @@ namespace ibl
     return out;
   }
 
-  std::vector<float> build_paired_entries(BandedSamples const &banded, float scale, bool projective)
+  std::vector<float> build_paired_entries(BandedSamples const &banded, float scale)
   {
     std::vector<SampleEntry> e = banded.level.entries;
     for(auto &s : e)
     {
-      if (projective)
-      {
-        // lz > 0 for every accepted sample (ibl.cpp:178)
-        s.lx = (float)((double)s.lx / (double)s.lz);
-        s.ly = (float)((double)s.ly / (double)s.lz);
-      }
-      else
-      {
-        s.lx *= scale; s.ly *= scale;
-      }
-      s.lz *= scale; s.wh *= scale;
+      s.lx *= scale; s.ly *= scale; s.lz *= scale; s.wh *= scale;
     }
 
     // fill the last band: direction (0, 0, 1) in the tangent frame, i.e. the normal itself (always on

@@ -57,10 +57,9 @@ namespace ibl
   // every fp32 sum), and consecutive entries (a, b) interleaved as
   //     { lx_a, lx_b, ly_a, ly_b }  { lz_a, lz_b, wh_a, wh_b }
   // so that one 16-byte load yields two register pairs for the packed fp32x2 arithmetic.
-  // Returns 4 floats per entry, band * ceil(count / band) entries.
-  // projective: lx, ly are replaced by lx/lz, ly/lz (unscaled; ibl_math.cuh "projective form"), lz and wh
-  // keep the scale: they only weigh the taps then.
-  std::vector<float> build_paired_entries(BandedSamples const &banded, float scale, bool projective = false);
+  // Returns 4 floats per entry, band * ceil(count / band) entries.  (Round 2's pair kernel read this table; it
+  // is kept for the A/B variants of the tools build.  The shipped kernel reads build_sector_entries' below.)
+  std::vector<float> build_paired_entries(BandedSamples const &banded, float scale);
 
   // The pair kernel's table with one AZIMUTH SECTOR per warp (ibl_math.cuh, sector_rho_limits): the accepted
   // samples are cut into `sectors` (4 or 8) equal azimuth sectors of the tangent plane, each sorted by

@@ -893,11 +893,14 @@ namespace ibl
     gather_pair_proj<EXP_ALU>(p, base, fa * p.geom.face_size + f2u(ia), fb * p.geom.face_size + f2u(ib), du, dv, e, acc);
   }
 
-  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false, bool PROJ = true>
+  template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false, bool PROJ = true, int VW = 1>
   __global__ void __launch_bounds__(32 * NW, MINB) prefilter_dp_kernel(PrefilterDnParams p)
   {
     extern __shared__ float4 smem[];
-    constexpr int SECTORS = NW == 8 ? 1 : 0;                       // which of the two sector tables
+    // VW = 2: a warp takes TWO 45-degree sectors of the 8-sector table one after the other, each with its own
+    // count of same-face bands, instead of one 90-degree sector of the 4-sector table
+    static_assert(VW == 1 || (VW == 2 && NW == 4 && PROJ), "two sectors per warp: four warps per tile, projective form");
+    constexpr int SECTORS = NW * VW == 8 ? 1 : 0;                  // which of the two sector tables
     const int bands = PROJ ? p.sector_bands[SECTORS] : p.bands;
     const int padded = bands * kSampleBand;
     float4 *s_table = smem;
@@ -920,7 +923,7 @@ namespace ibl
     uint32_t smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
 
-    constexpr int PER = kSampleBand / NW;        // entries of a band per warp: an arc of the ring
+    constexpr int PER = kSampleBand / (NW * VW); // entries of a band per warp and pass: an arc of the ring
     constexpr int PAIRS = PER / 2;
     static_assert(PER >= 2 && PER % 2 == 0, "a warp takes whole pairs of every band");
     constexpr int BAND_UNROLL = (PAIRS >= 2 ? 1 : 2) * DEPTH;     // DEPTH 2: twice the footprint loads in flight per warp (A/B)
@@ -990,7 +993,7 @@ namespace ibl
       uint4 const *biased_probe = LEAN ? biased : opaque(biased + (size_t)probe * p.record_stride);
 
       Frame st;
-      int n_same;
+      int n_same, n_same_second = 0;
       {
         if (PROJ)
         {
@@ -1005,7 +1008,7 @@ namespace ibl
           // can leave some texel's face (sector_rho_limits, kept as the minimum over the texels of every 8x4 tile
           // of the level; a slab that starts between two such tile rows looks at both; the eight 45-degree sectors
           // pair up for four warps)
-          float limit;
+          float limit, limit_second = 0.0f;
           {
             const int tiles_x = (p.wd + 7) >> 3, tile_rows = (6 * p.hd + 3) >> 2;
             const int top = __shfl_sync(0xffffffffu, row, 0), left = __shfl_sync(0xffffffffu, x, 0);     // lane 0 is always inside the slab
@@ -1016,20 +1019,35 @@ namespace ibl
 
             limit = fminf(__ldg(tile + first * sector + (size_t)t0 * tiles_x), __ldg(tile + first * sector + (size_t)t1 * tiles_x));
             if (NW != 8)
-              limit = fminf(limit, fminf(__ldg(tile + (first + 1) * sector + (size_t)t0 * tiles_x), __ldg(tile + (first + 1) * sector + (size_t)t1 * tiles_x)));
+            {
+              float second = fminf(__ldg(tile + (first + 1) * sector + (size_t)t0 * tiles_x), __ldg(tile + (first + 1) * sector + (size_t)t1 * tiles_x));
+              if (VW == 2)
+                limit_second = second;
+              else
+                limit = fminf(limit, second);
+            }
           }
 
           // leading bands whose share of this sector stays inside it (sector_rho increases with the band): the lanes
           // look at 32 bands at a time
-          float const *rho = p.sector_rho[SECTORS] + warp * bands;
-          n_same = 0;
-          for(int base = 0; base < bands; base += 32)
+          #pragma unroll
+          for(int pass = 0; pass < VW; ++pass)
           {
-            int k = base + lane;
-            unsigned within = __ballot_sync(0xffffffffu, k < bands && __ldg(rho + k) <= limit);
-            n_same += __popc(within);
-            if (within != 0xffffffffu)
-              break;
+            float const *rho = p.sector_rho[SECTORS] + (VW * warp + pass) * bands;
+            const float within_limit = pass == 0 ? limit : limit_second;
+            int count = 0;
+            for(int base = 0; base < bands; base += 32)
+            {
+              int k = base + lane;
+              unsigned within = __ballot_sync(0xffffffffu, k < bands && __ldg(rho + k) <= within_limit);
+              count += __popc(within);
+              if (within != 0xffffffffu)
+                break;
+            }
+            if (pass == 0)
+              n_same = count;
+            else
+              n_same_second = count;
           }
         }
         else
@@ -1064,27 +1082,32 @@ namespace ibl
       acc.rg = 0ull;
       acc.bb = 0ull;
 
-      float4 const *tw = table + warp * PER;   // entry index == float4 index in the pair-interleaved table
-      int band = 0;
-
+      // entry index == float4 index in the pair-interleaved table
       {
         uint4 const *base = opaque(biased_probe + (size_t)face * p.geom.face_size);
 
-        #pragma unroll BAND_UNROLL
-        for(; band < n_same; ++band)
+        #pragma unroll 1
+        for(int pass = 0; pass < VW; ++pass)
         {
-          #pragma unroll
-          for(int k = 0; k < PAIRS; ++k)
+          float4 const *tw = table + (VW * warp + pass) * PER;
+          const int count = pass == 0 ? n_same : n_same_second;
+
+          #pragma unroll BAND_UNROLL
+          for(int band = 0; band < count; ++band)
           {
-            if (PROJ)
-              pair_same_face_proj<EXP_ALU>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
-            else
-              pair_same_face<EXP_ALU, RHI>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+            #pragma unroll
+            for(int k = 0; k < PAIRS; ++k)
+            {
+              if (PROJ)
+                pair_same_face_proj<EXP_ALU>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+              else
+                pair_same_face<EXP_ALU, RHI>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+            }
           }
         }
       }
 
-      if (band < bands)
+      if (n_same < bands || (VW == 2 && n_same_second < bands))
       {
         // back to world coordinates for the samples that may cross a face edge
         if (PROJ)
@@ -1103,16 +1126,22 @@ namespace ibl
         // the general path's index carries kMagicBits - hhm*ws instead of kMagicBits
         uint4 const *general = PROJ ? opaque(biased_probe + (size_t)(kMagicBits - p.geom.bias_general)) : biased_probe;
 
-        #pragma unroll BAND_UNROLL
-        for(; band < bands; ++band)
+        #pragma unroll 1
+        for(int pass = 0; pass < VW; ++pass)
         {
-          #pragma unroll
-          for(int k = 0; k < PAIRS; ++k)
+          float4 const *tw = table + (VW * warp + pass) * PER;
+
+          #pragma unroll BAND_UNROLL
+          for(int band = pass == 0 ? n_same : n_same_second; band < bands; ++band)
           {
-            if (PROJ)
-              pair_general_proj<EXP_ALU>(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
-            else
-              pair_general<EXP_ALU, RHI>(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+            #pragma unroll
+            for(int k = 0; k < PAIRS; ++k)
+            {
+              if (PROJ)
+                pair_general_proj<EXP_ALU>(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+              else
+                pair_general<EXP_ALU, RHI>(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+            }
           }
         }
       }
@@ -1481,10 +1510,10 @@ namespace ibl
 
   namespace
   {
-    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false, bool PROJ = true>
+    template<int NW, int MINB, bool SMEM_TABLE, bool QUEUES, int EXP_ALU = 0, int DEPTH = 1, bool RHI = false, bool PLAIN_QUEUE = false, bool LEAN = false, bool PROJ = true, int VW = 1>
     cudaError_t launch_dp(PrefilterDnParams p, int sm_count, cudaStream_t stream, int *launched_grid)
     {
-      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU, DEPTH, RHI, PLAIN_QUEUE, LEAN, PROJ>;
+      auto kernel = prefilter_dp_kernel<NW, MINB, SMEM_TABLE, QUEUES, EXP_ALU, DEPTH, RHI, PLAIN_QUEUE, LEAN, PROJ, VW>;
 
       int rows = p.row_end - p.row_begin;
       int tiles_x = (p.wd + 7) / 8, tiles_y = (rows + 3) / 4;
@@ -1494,7 +1523,7 @@ namespace ibl
         p.probes = 1;
       p.tiles = p.tiles_per_probe * p.probes;
 
-      const int table_bands = PROJ ? p.sector_bands[NW == 8 ? 1 : 0] : p.bands;
+      const int table_bands = PROJ ? p.sector_bands[NW * VW == 8 ? 1 : 0] : p.bands;
       size_t smem = (SMEM_TABLE ? (size_t)table_bands * kSampleBand * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
 
       int resident = 0;
@@ -1614,6 +1643,7 @@ namespace ibl
       case 95: return launch_dp<4, 8, true, true, 0, 1, false, false, true, false>(p, sm_count, stream, launched_grid);
       case 96: return launch_dp<8, 4, true, false, 0, 1, false, false, true, false>(p, sm_count, stream, launched_grid);
       case 97: return launch_dp<8, 4, true, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid);      // 8 warps per tile with tile queues, lean
+      case 98: return launch_dp<4, 8, true, true, 0, 1, false, false, true, true, 2>(p, sm_count, stream, launched_grid);   // two 45-degree sectors per warp, one after the other
       case 75: return launch_dp<4, 8, true, true, 1, 1, false, false, true>(p, sm_count, stream, launched_grid);
       case 76: return launch_dp<4, 8, true, true, 2, 1, false, false, true>(p, sm_count, stream, launched_grid);
       case 77: return launch_dp<4, 8, true, true, 3, 1, false, false, true>(p, sm_count, stream, launched_grid);
