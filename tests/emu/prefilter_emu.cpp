@@ -500,7 +500,7 @@ extern "C" void emu_sector_study(int ws, int level, int levels, int samples, int
   }
 
   int wd = ws >> 1, hd = ws >> 1;
-  double old_general = 0, new_general = 0, old_total = 0, new_total = 0, violations = 0;
+  double old_general = 0, new_general = 0, old_total = 0, new_total = 0, violations = 0, interior_tiles = 0, tiles = 0;
 
   std::vector<float> limits((size_t)wd * hd * kFrameSectors);
   std::vector<float> thresholds((size_t)wd * hd);
@@ -568,6 +568,7 @@ extern "C" void emu_sector_study(int ws, int level, int levels, int samples, int
         old_general += bands_old - n_same;
         old_total += bands_old;
 
+        bool interior = true;
         for(int w = 0; w < sectors; ++w)
         {
           int n = 0;
@@ -575,7 +576,10 @@ extern "C" void emu_sector_study(int ws, int level, int levels, int samples, int
             ++n;
           new_general += st.bands - n;
           new_total += st.bands;
+          interior = interior && n == st.bands;
         }
+        interior_tiles += interior ? 1 : 0;
+        tiles += 1;
       }
   }
 
@@ -583,4 +587,5 @@ extern "C" void emu_sector_study(int ws, int level, int levels, int samples, int
   out[1] = new_general / new_total;
   out[2] = violations;
   out[3] = (double)st.bands * band / (double)(banded.band_min_lz.size() * band);   // table growth through filling up
+  out[4] = interior_tiles / tiles;   // tiles none of whose samples can leave the face
 }

@@ -159,9 +159,9 @@ def test_sector_limits_never_admit_a_sample_that_leaves_the_face(ws, level, leve
     inside the texel's own face (checked in double precision for every texel, sector and sample); and the
     per-warp rule sends fewer warp-samples through the face selection than one isotropic count per tile."""
     emu = emu_lib.load()
-    out = np.zeros(4)
+    out = np.zeros(8)
     emu.emu_sector_study(ws, level, levels, samples, sectors, out.ctypes.data)
-    general_per_tile, general_per_sector, violations, growth = out
+    general_per_tile, general_per_sector, violations, growth = out[:4]
     assert violations == 0
     assert general_per_sector <= general_per_tile
     assert 1.0 <= growth <= 1.2      # sectors hold (almost) equal shares of the accepted samples
