@@ -18,5 +18,6 @@ for tool in "$@"; do
   $S $D chain 256 256 8 gpurun_out/sanitize/l0_256.bin gpurun_out/sanitize/out_256.bin 2>&1 | grep -E "SUMMARY|Error|hazard|error" | head -5; echo "chain 256^2 x 8 (pair kernels with and without tile queues, tail kernel, pageable staging): exit ${PIPESTATUS[0]}"
   $S $D faces 64 64 5 gpurun_out/sanitize/argb_64.bin gpurun_out/sanitize/out_faces.bin 2>&1 | grep -E "SUMMARY|Error|hazard|error" | head -5; echo "six-image ingest + chain: exit ${PIPESTATUS[0]}"
   $S $D irradiance 64 64 8 8 gpurun_out/sanitize/argb_64.bin gpurun_out/sanitize/out_irr.bin 2>&1 | grep -E "SUMMARY|Error|hazard|error" | head -5; echo "SH9 projection + irradiance cube: exit ${PIPESTATUS[0]}"
-  DATUM_IBL_DEVICES=0,0 DATUM_IBL_SPLIT_MIN_FACE=1 $S $D chain 192 192 7 gpurun_out/sanitize/l0_192.bin gpurun_out/sanitize/out_192.bin 2>&1 | grep -E "SUMMARY|Error|hazard|error" | head -5; echo "one probe shared by two contexts (peer stores, last-CTA signal, stream waits): exit ${PIPESTATUS[0]}"
+  # stream memory operations (cuStreamWaitValue32) do not complete under compute-sanitizer: SANITIZE_SHARED=1 to try anyway
+  [ "${SANITIZE_SHARED:-0}" = "1" ] && DATUM_IBL_DEVICES=0,0 DATUM_IBL_SPLIT_MIN_FACE=1 $S $D chain 192 192 7 gpurun_out/sanitize/l0_192.bin gpurun_out/sanitize/out_192.bin 2>&1 | grep -E "SUMMARY|Error|hazard|error" | head -5&& echo "one probe shared by two contexts (peer stores, last-CTA signal, stream waits): exit ${PIPESTATUS[0]}"
 done
