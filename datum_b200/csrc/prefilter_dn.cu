@@ -801,7 +801,7 @@ namespace ibl
     uint4 rb = load_record(base, idx_b);
 
     // tools/ibl.cpp:40 times the sample weight: (0.5 -+ du) * (wh -+ dv * nl), right-hand column by difference
-    f32x2 u0 = fma2(du, bcast2(-1.0f), bcast2(0.5f));
+    f32x2 u0 = add2(neg2(du), bcast2(0.5f));
     f32x2 v0 = fma2(neg2(dv), e.lz, e.wh);
     f32x2 v1 = fma2(dv, e.lz, e.wh);
     f32x2 p00 = mul2(u0, v0);
@@ -810,8 +810,8 @@ namespace ibl
     float w00a, w00b, w10a, w10b, w01a, w01b, w11a, w11b;
     unpack2(p00, w00a, w00b);
     unpack2(p01, w01a, w01b);
-    unpack2(fma2(p00, bcast2(-1.0f), v0), w10a, w10b);
-    unpack2(fma2(p01, bcast2(-1.0f), v1), w11a, w11b);
+    unpack2(add2(v0, neg2(p00)), w10a, w10b);
+    unpack2(add2(v1, neg2(p01)), w11a, w11b);
 
     const uint32_t emul = p.exp_mul;
     w00a = scale_tap<(EXP_ALU > 0)>(w00a, ra.x, emul);
@@ -851,8 +851,8 @@ namespace ibl
 
     f32x2 mu = fma2(la, r, bcast2(kMagic));
     f32x2 mv = fma2(lb, r, bcast2(kMagic));
-    f32x2 niu = fma2(mu, bcast2(-1.0f), bcast2(kMagic));
-    f32x2 niv = fma2(mv, bcast2(-1.0f), bcast2(kMagic));
+    f32x2 niu = add2(neg2(mu), bcast2(kMagic));
+    f32x2 niv = add2(neg2(mv), bcast2(kMagic));
     f32x2 du = fma2(la, r, niu);
     f32x2 dv = fma2(lb, r, niv);
 
@@ -882,8 +882,8 @@ namespace ibl
     f32x2 qu = pack2(qua, qub), qv = pack2(qva, qvb);
     f32x2 mu = fma2(qu, bcast2(p.geom.hw), bcast2(p.geom.hwm_magic));
     f32x2 mv = fma2(qv, bcast2(p.geom.hh), bcast2(p.geom.hhm_magic));
-    f32x2 cu = fma2(mu, bcast2(-1.0f), bcast2(p.geom.hwm_magic));
-    f32x2 cv = fma2(mv, bcast2(-1.0f), bcast2(p.geom.hhm_magic));
+    f32x2 cu = add2(neg2(mu), bcast2(p.geom.hwm_magic));
+    f32x2 cv = add2(neg2(mv), bcast2(p.geom.hhm_magic));
     f32x2 du = fma2(qu, bcast2(p.geom.hw), cu);
     f32x2 dv = fma2(qv, bcast2(p.geom.hh), cv);
 
