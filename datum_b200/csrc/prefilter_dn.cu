@@ -23,11 +23,16 @@
 //
 // Around that loop:
 //   * the sample table is banded (ibl_tables.h): bands of kSampleBand entries of the lobe-angle
-//     order, ring-ordered inside; the warps of a tile each take a quarter arc of every band.  The
-//     same-face test (no cube-face selection needed) is made per band;
+//     order; the warps of a tile each take their share of every band.  For the one-sample kernel
+//     (prefilter_dn_kernel) a band is a ring of the lobe walked by azimuth and the same-face test (no
+//     cube-face selection needed) is one angle per band and tile; the pair kernel
+//     (prefilter_dp_kernel, what the library runs) gives every warp ONE azimuth sector of every band
+//     and its own count of same-face bands (ibl_math.cuh, sector_rho_limits);
 //   * tiles are numbered in 4x4 blocks and, for big levels, handed out from per-SM queues so that
 //     the CTAs resident on one SM work on neighbouring tiles and share the lobe's footprint in L1
-//     (measured: L1 hit rate 38 % -> 68 % on the 512^2 -> 256^2 level).
+//     (measured: L1 hit rate 38 % -> 68 % on the 512^2 -> 256^2 level);
+//   * the pair kernel reads a texel's frame and its tile's sector limits from per-level planes
+//     (build_frames_kernel) instead of computing them per tile.
 
 #include "prefilter.h"
 #include "ibl_math.cuh"
@@ -624,17 +629,16 @@ namespace ibl
   // The kernel above packs the (a, b) face coordinates of ONE sample into fp32x2 operations; the
   // third coordinate, the bilinear weights and half of the magic-add floor stay scalar.  Packing
   // the SAME quantity of TWO consecutive samples instead makes every per-sample fp32 operation a
-  // half-instruction: direction 9 packed ops per pair (was 6 per sample), weights 9 per pair (was
-  // 6 per sample), and the general (cube-face-selecting) path gets the packed direction and floor
-  // it never had.  Per element the operations and their order are the ones of the kernel above,
-  // so r and g sums are bit-identical to it; the two b partial sums now belong to the two samples
-  // of a pair instead of to the tap columns.  The table arrives pair-interleaved with its last
-  // band filled up (build_paired_entries), so there is no short-band code.
+  // half-instruction, and the general (cube-face-selecting) path gets the packed direction and floor
+  // it never had.  The two b partial sums belong to the two samples of a pair instead of to the tap
+  // columns.  The table arrives pair-interleaved with its short shares filled up, so there is no
+  // short-band code.
   //
-  // Footprint address: the magic-add integers carry kMagicBits each, kMagicBits*(ws+1) in the
-  // index.  Instead of subtracting that per sample the record pointer is moved back by it once
-  // (the launcher checks that index + bias cannot wrap in 32 bits, else it uses the kernel above):
-  // one IMAD + one IMAD.WIDE per footprint.
+  // Two statements of the per-pair arithmetic follow.  The first (direction_pair, gather_pair,
+  // pair_same_face, pair_general: PROJ = false) is round 2's first cut — three-term directions, an
+  // integer record index whose bias kMagicBits*(ws+1) is folded into the record pointer, four weight
+  // products — kept for the A/B variants of the tools build.  The second (…_proj: what ships) is the
+  // projective form described at its head.
 
   struct PairEntry
   {
