@@ -143,6 +143,7 @@ namespace ibl
     // projective form (face_footprint_proj / cube_footprint_proj below)
     float hwm_magic, hhm_magic;   // hwm + kMagic, hhm + kMagic: exact while ws and hs are even
     float neg_ws;                 // -(float)ws
+    float hw_shrunk, hh_shrunk;   // hw, hh times kRcpShrink: the scale of cube_select_unshrunk's quotients
     uint32_t bias_general;        // kMagicBits - hhm*ws: what cube_footprint_proj's raw index carries
   };
 
@@ -157,6 +158,7 @@ namespace ibl
     g.bias = kMagicBits * (uint32_t)(ws + 1);
     g.hwm_magic = g.hwm + kMagic; g.hhm_magic = g.hhm + kMagic;
     g.neg_ws = -(float)ws;
+    g.hw_shrunk = g.hw * kRcpShrink; g.hh_shrunk = g.hh * kRcpShrink;
     g.bias_general = kMagicBits - (uint32_t)((hs - 2) / 2) * (uint32_t)ws;
     return g;
   }
@@ -175,7 +177,8 @@ namespace ibl
   // integer this may pick i-1 with frac 1, which addresses the same bilinear
   // value.  |q| <= 1 keeps i in [0, ws-2], so the footprint never leaves the face.
   // face selection and the two face coordinates in [-1, 1] (qu = 2u - 1, qv = 2v - 1)
-  IBL_HD void cube_select(float Lx, float Ly, float Lz, float &qu, float &qv, uint32_t &face)
+  template<bool SHRINK>
+  IBL_HD void cube_select_impl(float Lx, float Ly, float Lz, float &qu, float &qv, uint32_t &face)
   {
     float ax = fabsf(Lx), ay = fabsf(Ly), az = fabsf(Lz);
     bool px = ax >= fmaxf(ay, az);
@@ -188,8 +191,8 @@ namespace ibl
     // rcp.approx may round up by one ulp: on an exact tie |un| == |major| (a direction on a cube
     // edge) the quotient would then exceed 1 and the footprint would start one texel outside the
     // face.  Shrinking the reciprocal by two ulps keeps |q| <= 1; it moves a footprint by at most
-    // 2.4e-7 of the face width.
-    float r = rcp_fast(major) * kRcpShrink;
+    // 2.4e-7 of the face width.  (SHRINK = false: the caller multiplies by a shrunk scale instead.)
+    float r = SHRINK ? rcp_fast(major) * kRcpShrink : rcp_fast(major);
     float ar = fabsf(r);
     float ru = px ? r : (py ? ar : -r);
     float rv = py ? r : ar;
@@ -200,6 +203,17 @@ namespace ibl
 
     qu = un * ru;
     qv = vn * rv;
+  }
+
+  IBL_HD void cube_select(float Lx, float Ly, float Lz, float &qu, float &qv, uint32_t &face)
+  {
+    cube_select_impl<true>(Lx, Ly, Lz, qu, qv, face);
+  }
+
+  // |qu|, |qv| <= 1 + 2^-23 here: to be scaled by LevelGeom::hw_shrunk / hh_shrunk
+  IBL_HD void cube_select_unshrunk(float Lx, float Ly, float Lz, float &qu, float &qv, uint32_t &face)
+  {
+    cube_select_impl<false>(Lx, Ly, Lz, qu, qv, face);
   }
 
   IBL_HD uint32_t cube_footprint(LevelGeom const &g, float Lx, float Ly, float Lz, float &du, float &dv)
@@ -325,14 +339,14 @@ namespace ibl
   IBL_HD uint32_t cube_footprint_proj(LevelGeom const &g, float Lx, float Ly, float Lz, float &du, float &dv, uint32_t &face)
   {
     float qu, qv;
-    cube_select(Lx, Ly, Lz, qu, qv, face);
+    cube_select_unshrunk(Lx, Ly, Lz, qu, qv, face);
 
-    float mu = fmaf(qu, g.hw, g.hwm_magic);
-    float mv = fmaf(qv, g.hh, g.hhm_magic);
+    float mu = fmaf(qu, g.hw_shrunk, g.hwm_magic);
+    float mv = fmaf(qv, g.hh_shrunk, g.hhm_magic);
     float cu = fmaf(mu, -1.0f, g.hwm_magic);  // hwm - i, exact (hwm is an integer)
     float cv = fmaf(mv, -1.0f, g.hhm_magic);
-    du = fmaf(qu, g.hw, cu);
-    dv = fmaf(qv, g.hh, cv);
+    du = fmaf(qu, g.hw_shrunk, cu);
+    dv = fmaf(qv, g.hh_shrunk, cv);
     return f2u(fmaf(cv, g.neg_ws, mu));
   }
 

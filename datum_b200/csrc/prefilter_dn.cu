@@ -880,16 +880,17 @@ namespace ibl
 
     float qua, qva, qub, qvb;
     uint32_t fa, fb;
-    cube_select(xa, ya, za, qua, qva, fa);
-    cube_select(xb, yb, zb, qub, qvb, fb);
+    cube_select_unshrunk(xa, ya, za, qua, qva, fa);
+    cube_select_unshrunk(xb, yb, zb, qub, qvb, fb);
 
+    // the two-ulp shrink of the reciprocal (cube_select) rides in the scale
     f32x2 qu = pack2(qua, qub), qv = pack2(qva, qvb);
-    f32x2 mu = fma2(qu, bcast2(p.geom.hw), bcast2(p.geom.hwm_magic));
-    f32x2 mv = fma2(qv, bcast2(p.geom.hh), bcast2(p.geom.hhm_magic));
+    f32x2 mu = fma2(qu, bcast2(p.geom.hw_shrunk), bcast2(p.geom.hwm_magic));
+    f32x2 mv = fma2(qv, bcast2(p.geom.hh_shrunk), bcast2(p.geom.hhm_magic));
     f32x2 cu = add2(neg2(mu), bcast2(p.geom.hwm_magic));
     f32x2 cv = add2(neg2(mv), bcast2(p.geom.hhm_magic));
-    f32x2 du = fma2(qu, bcast2(p.geom.hw), cu);
-    f32x2 dv = fma2(qv, bcast2(p.geom.hh), cv);
+    f32x2 du = fma2(qu, bcast2(p.geom.hw_shrunk), cu);
+    f32x2 dv = fma2(qv, bcast2(p.geom.hh_shrunk), cv);
 
     float ia, ib;
     unpack2(fma2(cv, bcast2(p.geom.neg_ws), mu), ia, ib);
