@@ -589,3 +589,63 @@ extern "C" void emu_sector_study(int ws, int level, int levels, int samples, int
   out[3] = (double)st.bands * band / (double)(banded.band_min_lz.size() * band);   // table growth through filling up
   out[4] = interior_tiles / tiles;   // tiles none of whose samples can leave the face
 }
+
+// Per row of 8x4 tiles of the destination level of a ws x ws source: how many (warp, band) shares the pair kernel
+// sends through the cube-face selection (out_general[tile_row]) of how many in all (out_total[tile_row]).
+// For studies of how evenly row slabs of a level load the GPUs that share a probe.
+extern "C" void emu_row_costs(int ws, int level, int levels, int samples, int sectors, double *out_general, double *out_total)
+{
+  const int band = 16;
+  LevelSamples ls = build_level_samples(level, levels, samples);
+  SectorTable st = build_sector_entries(ls, sectors, band, 1.0f);
+
+  const float kPi = 3.14159265358979323846f;
+  float angles[6] = { -kPi/2, kPi/2, -kPi/2, kPi/2, 0.0f, kPi };
+  int axes[6] = { 1, 1, 0, 0, 1, 1 };
+  Quatf quats[6];
+  for(int f = 0; f < 6; ++f)
+  {
+    float c = std::cos(angles[f]/2), s = std::sin(angles[f]/2);
+    quats[f] = Quatf{ c, axes[f] == 0 ? s : 0.0f, axes[f] == 1 ? s : 0.0f, 0.0f };
+  }
+
+  int wd = ws >> 1, hd = ws >> 1;
+  std::vector<float> limits((size_t)wd * kFrameSectors);
+
+  for(int face = 0; face < 6; ++face)
+    for(int ty = 0; ty < hd; ty += 4)
+    {
+      int tile_row = (face * hd + ty) / 4;
+      out_general[tile_row] = 0;
+      out_total[tile_row] = 0;
+
+      for(int tx = 0; tx < wd; tx += 8)
+      {
+        float rho_tile[8];
+        for(int w = 0; w < sectors; ++w)
+          rho_tile[w] = 3.0e38f;
+
+        for(int y = ty; y < std::min(hd, ty + 4); ++y)
+          for(int x = tx; x < std::min(wd, tx + 8); ++x)
+          {
+            Vec3f N = texel_normal(quats[face], x, y, wd, hd);
+            Vec3f T, B;
+            tangent_frame(N, T, B);
+            float lim[kFrameSectors];
+            sector_rho_limits(to_face_local(face, T), to_face_local(face, B), to_face_local(face, N), lim);
+            for(int w = 0; w < sectors; ++w)
+              for(int k = w * kFrameSectors / sectors; k < (w + 1) * kFrameSectors / sectors; ++k)
+                rho_tile[w] = std::min(rho_tile[w], lim[k]);
+          }
+
+        for(int w = 0; w < sectors; ++w)
+        {
+          int n = 0;
+          while (n < st.bands && st.rho_max[(size_t)w * st.bands + n] <= rho_tile[w])
+            ++n;
+          out_general[tile_row] += st.bands - n;
+          out_total[tile_row] += st.bands;
+        }
+      }
+    }
+}
