@@ -1567,6 +1567,8 @@ namespace ibl
 
   // slabs of at least this many texels take their tiles from per-SM queues
   constexpr size_t kQueuedTexels = 32u * 148u * 8u;
+  // ... and of at least this many run 4 warps per tile instead of 8
+  constexpr size_t kFourWarpTexels = 160000u;
 
   bool prefilter_batchable(int ws, int hs)
   {
@@ -1595,20 +1597,28 @@ namespace ibl
       // the one-sample kernel when the biased record index could wrap
       // Warps per tile follow ONE probe's slab (they decide the order of the sums: a batch must give the
       // words of single calls), the tile queues follow the whole launch.
-      if (texels >= kQueuedTexels)
+      // Slabs between the two bounds take 8 warps per tile AND the tile queues: eight 45-degree sectors send fewer
+      // warp-samples through the face selection than four of 90 (level 2 of C2: 32 % instead of 38 %; 247 -> 241 us),
+      // which on the biggest slabs does not pay for the one-pair loop of that shape (level 1: 780 -> 805 us)
+      if (texels >= kFourWarpTexels)
         variant = big_table ? 71 : 70;
+      else if (texels >= kQueuedTexels)
+        variant = big_table ? 67 : 66;
       else if (texels * (size_t)(p.probes > 1 ? p.probes : 1) >= kQueuedTexels)
         variant = big_table ? 91 : 90;
       else
         variant = big_table ? 73 : 72;      // slabs of at most kTailTexels never get here (prefilter_tail_kernel)
     }
 
-    if (p.probes > 1 && !(variant >= 70 && variant <= 99 && pair_kernel_usable(p)))
+    if (p.probes > 1 && !(((variant >= 70 && variant <= 99) || variant == 66 || variant == 67) && pair_kernel_usable(p)))
       return cudaErrorNotSupported;         // batches run on the pair kernel only (the caller checks prefilter_batchable)
 
     // two samples at a time; when the biased index could wrap, the same shape one sample at a time
     if (variant >= 81 && variant <= 86 && !pair_kernel_usable(p))
       variant = variant == 83 ? 53 : 51;
+
+    if ((variant == 66 || variant == 67) && !pair_kernel_usable(p))
+      variant = variant == 66 ? 53 : 54;
 
     if (variant >= 70 && variant <= 79 && !pair_kernel_usable(p))
     {
@@ -1628,6 +1638,8 @@ namespace ibl
       case 71: return lean ? launch_dp<4, 8, false, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid) : launch_dp<4, 8, false, true>(p, sm_count, stream, launched_grid);
       case 72: return lean ? launch_dp<8, 4, true, false, 0, 1, false, false, true>(p, sm_count, stream, launched_grid) : launch_dp<8, 4, true, false>(p, sm_count, stream, launched_grid);
       case 73: return lean ? launch_dp<8, 4, false, false, 0, 1, false, false, true>(p, sm_count, stream, launched_grid) : launch_dp<8, 4, false, false>(p, sm_count, stream, launched_grid);
+      case 66: return lean ? launch_dp<8, 4, true, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid) : launch_dp<8, 4, true, true>(p, sm_count, stream, launched_grid);
+      case 67: return lean ? launch_dp<8, 4, false, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid) : launch_dp<8, 4, false, true>(p, sm_count, stream, launched_grid);
       case 90: return launch_dp<8, 4, true, true>(p, sm_count, stream, launched_grid);     // several probes' small slabs in one launch
       case 91: return launch_dp<8, 4, false, true>(p, sm_count, stream, launched_grid);
       //                        NW UNR MINB SMEM  QUEUES
@@ -1647,7 +1659,6 @@ namespace ibl
       // round 2's arithmetic (three-term directions, integer record index, four weight products) for A/B
       case 95: return launch_dp<4, 8, true, true, 0, 1, false, false, true, false>(p, sm_count, stream, launched_grid);
       case 96: return launch_dp<8, 4, true, false, 0, 1, false, false, true, false>(p, sm_count, stream, launched_grid);
-      case 97: return launch_dp<8, 4, true, true, 0, 1, false, false, true>(p, sm_count, stream, launched_grid);      // 8 warps per tile with tile queues, lean
       case 98: return launch_dp<4, 8, true, true, 0, 1, false, false, true, true, 2>(p, sm_count, stream, launched_grid);   // two 45-degree sectors per warp, one after the other
       case 75: return launch_dp<4, 8, true, true, 1, 1, false, false, true>(p, sm_count, stream, launched_grid);
       case 76: return launch_dp<4, 8, true, true, 2, 1, false, false, true>(p, sm_count, stream, launched_grid);

@@ -236,7 +236,7 @@ def test_kernel_variants_agree(ctx):
     clean = np.concatenate([oracle_lib.edge_ambiguous_counts(w >> level, w >> level, level, levels, 1024) == 0 for level in range(1, levels)])
     base = None
     try:
-        for variant in (0, 51, 52, 53, 54, 70, 71, 72, 73, 80):     # every kernel shape the product library ships
+        for variant in (0, 51, 52, 53, 54, 66, 67, 70, 71, 72, 73, 80):     # every kernel shape the product library ships
             ctx.set_prefilter_variant(variant)
             words, f32 = run_chain_device(ctx, bits, w, w, levels, 1024)
             if base is None:
