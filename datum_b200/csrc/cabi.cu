@@ -237,7 +237,7 @@ namespace
         t.bands = (int)banded.band_min_lz.size();
 
         std::vector<float> paired = ibl::build_paired_entries(banded, ibl::kDnTableScale);
-        ibl::SectorTable sector[2] = { ibl::build_sector_entries(host, 4, ibl::kSampleBand, ibl::kDnTableScale), ibl::build_sector_entries(host, 8, ibl::kSampleBand, ibl::kDnTableScale) };
+        ibl::SectorTable sector[2] = { ibl::build_sector_entries(host, 4, 4 * ibl::kSectorShare, ibl::kDnTableScale), ibl::build_sector_entries(host, 8, 8 * ibl::kSectorShare, ibl::kDnTableScale) };
 
         std::vector<ibl::SampleEntry> banded_proj = banded.level.entries;
         for(auto &e : banded_proj)

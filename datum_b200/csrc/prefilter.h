@@ -40,6 +40,7 @@ namespace ibl
     unsigned int *ticket;    // "CTAs done" counter of this context, zero between launches
   };
   constexpr int kSampleBand = 16;   // entries per band of the banded sample table (ibl_tables.h)
+  constexpr int kSectorShare = 4;   // entries per sector and band of the pair kernel's sector tables: bands of 16 (4 sectors) or 32 (8)
 
   struct PrefilterDnParams
   {

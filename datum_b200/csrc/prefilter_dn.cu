@@ -907,7 +907,11 @@ namespace ibl
     static_assert(VW == 1 || (VW == 2 && NW == 4 && PROJ), "two sectors per warp: four warps per tile, projective form");
     constexpr int SECTORS = NW * VW == 8 ? 1 : 0;                  // which of the two sector tables
     const int bands = PROJ ? p.sector_bands[SECTORS] : p.bands;
-    const int padded = bands * kSampleBand;
+    // entries per band: the sector tables hold FOUR entries (two pairs) per sector and band, whatever the number of
+    // sectors, so that a round of the sample loops is always two pairs of one band (a loop over one pair of two
+    // bands measured 3 % slower); round 2's table for the A/B variants has kSampleBand
+    constexpr int BAND = PROJ ? kSectorShare * NW * VW : kSampleBand;
+    const int padded = bands * BAND;
     float4 *s_table = smem;
     float *s_red = reinterpret_cast<float*>(smem + (SMEM_TABLE ? padded : 0));
     int *s_tile = reinterpret_cast<int*>(s_red + NW * 3 * 32);
@@ -928,7 +932,7 @@ namespace ibl
     uint32_t smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
 
-    constexpr int PER = kSampleBand / (NW * VW); // entries of a band per warp and pass: an arc of the ring
+    constexpr int PER = BAND / (NW * VW);        // entries of a band per warp and pass
     constexpr int PAIRS = PER / 2;
     static_assert(PER >= 2 && PER % 2 == 0, "a warp takes whole pairs of every band");
     constexpr int BAND_UNROLL = (PAIRS >= 2 ? 1 : 2) * DEPTH;     // DEPTH 2: twice the footprint loads in flight per warp (A/B)
@@ -1104,9 +1108,9 @@ namespace ibl
             for(int k = 0; k < PAIRS; ++k)
             {
               if (PROJ)
-                pair_same_face_proj<EXP_ALU>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+                pair_same_face_proj<EXP_ALU>(p, st, base, load_pair<SMEM_TABLE>(tw + band * BAND + 2 * k), acc);
               else
-                pair_same_face<EXP_ALU, RHI>(p, st, base, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+                pair_same_face<EXP_ALU, RHI>(p, st, base, load_pair<SMEM_TABLE>(tw + band * BAND + 2 * k), acc);
             }
           }
         }
@@ -1143,9 +1147,9 @@ namespace ibl
             for(int k = 0; k < PAIRS; ++k)
             {
               if (PROJ)
-                pair_general_proj<EXP_ALU>(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+                pair_general_proj<EXP_ALU>(p, st, general, load_pair<SMEM_TABLE>(tw + band * BAND + 2 * k), acc);
               else
-                pair_general<EXP_ALU, RHI>(p, st, general, load_pair<SMEM_TABLE>(tw + band * kSampleBand + 2 * k), acc);
+                pair_general<EXP_ALU, RHI>(p, st, general, load_pair<SMEM_TABLE>(tw + band * BAND + 2 * k), acc);
             }
           }
         }
@@ -1529,7 +1533,8 @@ namespace ibl
       p.tiles = p.tiles_per_probe * p.probes;
 
       const int table_bands = PROJ ? p.sector_bands[NW * VW == 8 ? 1 : 0] : p.bands;
-      size_t smem = (SMEM_TABLE ? (size_t)table_bands * kSampleBand * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
+      const int band_entries = PROJ ? kSectorShare * NW * VW : kSampleBand;
+      size_t smem = (SMEM_TABLE ? (size_t)table_bands * band_entries * sizeof(float4) : 0) + (size_t)NW * 3 * 32 * sizeof(float) + sizeof(int);
 
       int resident = 0;
       cudaError_t err = resident_ctas(kernel, 32 * NW, smem, &resident);

@@ -483,9 +483,9 @@ extern "C" int emu_table(int level, int levels, int samples, float *entries, dou
 // inside the texel's face.  `sectors` = warps per tile (4 or 8).
 extern "C" void emu_sector_study(int ws, int level, int levels, int samples, int sectors, double *out)
 {
-  const int band = 16;
+  const int band = 4 * sectors;      // the kernel's sector tables: four entries per sector and band
   LevelSamples ls = build_level_samples(level, levels, samples);
-  BandedSamples banded = build_banded_samples(level, levels, samples, band);
+  BandedSamples banded = build_banded_samples(level, levels, samples, 16);
   SectorTable st = build_sector_entries(ls, sectors, band, 1.0f);
   const int per = band / sectors;
 
@@ -586,7 +586,7 @@ extern "C" void emu_sector_study(int ws, int level, int levels, int samples, int
   out[0] = old_general / old_total;
   out[1] = new_general / new_total;
   out[2] = violations;
-  out[3] = (double)st.bands * band / (double)(banded.band_min_lz.size() * band);   // table growth through filling up
+  out[3] = (double)st.bands * band / (double)(banded.band_min_lz.size() * 16);   // table growth through filling up
   out[4] = interior_tiles / tiles;   // tiles none of whose samples can leave the face
 }
 
@@ -595,7 +595,7 @@ extern "C" void emu_sector_study(int ws, int level, int levels, int samples, int
 // For studies of how evenly row slabs of a level load the GPUs that share a probe.
 extern "C" void emu_row_costs(int ws, int level, int levels, int samples, int sectors, double *out_general, double *out_total)
 {
-  const int band = 16;
+  const int band = 4 * sectors;
   LevelSamples ls = build_level_samples(level, levels, samples);
   SectorTable st = build_sector_entries(ls, sectors, band, 1.0f);
 

@@ -164,7 +164,8 @@ def test_sector_limits_never_admit_a_sample_that_leaves_the_face(ws, level, leve
     general_per_tile, general_per_sector, violations, growth = out[:4]
     assert violations == 0
     assert general_per_sector <= general_per_tile
-    assert 1.0 <= growth <= 1.2      # sectors hold (almost) equal shares of the accepted samples
+    # sectors hold (almost) equal shares of the accepted samples; a short table pays for whole shares of four
+    assert 1.0 <= growth <= (1.2 if samples >= 1024 else 1.5)
 
 
 def test_dn_tap_decodes_every_field_exactly():
