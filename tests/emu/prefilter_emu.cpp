@@ -649,3 +649,71 @@ extern "C" void emu_row_costs(int ws, int level, int levels, int samples, int se
       }
     }
 }
+
+// ---- the projective footprints against the plain ones (ibl_math.cuh) ----
+//
+// n pseudo-random directions (and the exact cube diagonals / edge ties) through cube_footprint and
+// cube_footprint_proj for a ws x hs source: out[0] = largest difference of the texel coordinates the two
+// forms address (i + fraction, j + fraction), out[1] = footprints of the projective form outside
+// [0, ws-2] x [0, hs-2] or on another face than the plain form's, out[2] = directions tested.
+extern "C" void emu_footprint_compare(int ws, int hs, int n, unsigned seed, double *out)
+{
+  LevelGeom g = make_level_geom(ws, hs);
+  double worst = 0, bad = 0, count = 0;
+  unsigned state = seed * 2654435761u + 12345u;
+  auto rnd = [&]() { state = state * 1664525u + 1013904223u; return (float)((state >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+
+  for(int k = 0; k < n + 26; ++k)
+  {
+    float x, y, z;
+    if (k < 26)
+    {
+      // axes, edge and corner diagonals: exact ties of the face selection
+      int t = k + (k >= 13 ? 1 : 0);
+      x = (float)(t % 3 - 1); y = (float)((t / 3) % 3 - 1); z = (float)((t / 9) % 3 - 1);
+      if (x == 0 && y == 0 && z == 0)
+        continue;
+    }
+    else
+    {
+      x = rnd(); y = rnd(); z = rnd();
+      if (fabsf(x) + fabsf(y) + fabsf(z) < 1e-3f)
+        continue;
+    }
+
+    float du0, dv0, du1, dv1;
+    uint32_t idx0 = cube_footprint(g, x, y, z, du0, dv0);
+    uint32_t face1;
+    uint32_t raw = cube_footprint_proj(g, x, y, z, du1, dv1, face1);
+    uint32_t idx1 = raw - g.bias_general + face1 * g.face_size;
+
+    uint32_t face0 = idx0 / g.face_size;
+    int i0 = (int)((idx0 % g.face_size) % (uint32_t)ws), j0 = (int)((idx0 % g.face_size) / (uint32_t)ws);
+    long long local = (long long)idx1 - (long long)face1 * g.face_size;
+    int i1 = (int)(local % ws), j1 = (int)(local / ws);
+
+    count += 1;
+    if (face0 != face1 || local < 0 || i1 < 0 || i1 > ws - 2 || j1 < 0 || j1 > hs - 2)
+    {
+      bad += 1;
+      continue;
+    }
+    worst = std::max(worst, std::fabs(((double)i0 + du0) - ((double)i1 + du1)));
+    worst = std::max(worst, std::fabs(((double)j0 + dv0) - ((double)j1 + dv1)));
+  }
+
+  out[0] = worst; out[1] = bad; out[2] = count;
+}
+
+// the pair kernel's sector table: entries (4 floats each, pair-interleaved) and rho_max; returns bands or -1
+extern "C" int emu_sector_table(int level, int levels, int samples, int sectors, float scale, float *entries, int capacity, float *rho_max)
+{
+  SectorTable st = build_sector_entries(build_level_samples(level, levels, samples), sectors, 4 * sectors, scale);
+  if ((int)st.entries.size() > capacity)
+    return -1;
+  for(size_t i = 0; i < st.entries.size(); ++i)
+    entries[i] = st.entries[i];
+  for(size_t i = 0; i < st.rho_max.size(); ++i)
+    rho_max[i] = st.rho_max[i];
+  return st.bands;
+}

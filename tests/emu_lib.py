@@ -27,6 +27,9 @@ def load():
         lib.emu_paired_table.argtypes = [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p, ctypes.c_int]
         lib.emu_paired_table.restype = ctypes.c_int
         lib.emu_sector_study.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p]
+        lib.emu_footprint_compare.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_void_p]
+        lib.emu_sector_table.argtypes = [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        lib.emu_sector_table.restype = ctypes.c_int
         lib.emu_banded_table.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3
         lib.emu_banded_table.restype = ctypes.c_int
         lib.emu_patch_table.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3

@@ -168,6 +168,58 @@ def test_sector_limits_never_admit_a_sample_that_leaves_the_face(ws, level, leve
     assert 1.0 <= growth <= (1.2 if samples >= 1024 else 1.5)
 
 
+@pytest.mark.parametrize("ws,hs", [(2, 2), (4, 4), (8, 8), (24, 12), (64, 64), (512, 512), (1370, 1370), (2048, 2048)])
+def test_projective_footprint_addresses_the_plain_footprint(ws, hs):
+    """cube_footprint_proj (index out of the fp32 adder, shrink folded into the scale, fraction as fma(q, hw, hwm - i))
+    against cube_footprint on random directions and on the exact ties of the face selection: same face, inside
+    the face, same texel coordinate to fp32 rounding — up to the largest size proj_usable admits (2048^2)."""
+    emu = emu_lib.load()
+    out = np.zeros(4)
+    emu.emu_footprint_compare(ws, hs, 200000, 7, out.ctypes.data)
+    worst, bad, count = out[:3]
+    assert count > 190000 and bad == 0
+    assert worst <= 4e-7 * max(ws, hs) + 1e-6          # a few ulps of a coordinate of that size
+
+
+@pytest.mark.parametrize("level,levels,samples,sectors", [(1, 8, 1024, 4), (1, 8, 1024, 8), (7, 8, 1024, 8), (2, 5, 100, 4), (1, 12, 4096, 4), (3, 4, 7, 8)])
+def test_sector_table_holds_every_accepted_sample_once(level, levels, samples, sectors):
+    """build_sector_entries: the accepted samples of the level, each exactly once as (lx/lz, ly/lz, lz, wh) in its
+    azimuth sector's place of a band, filled up with no-effect entries; rho_max covers every share and grows."""
+    emu = emu_lib.load()
+    band = 4 * sectors
+    entries = np.zeros((samples, 4), np.float32)
+    band_min = np.zeros(samples, np.float32)
+    bands_plain = np.zeros(1, np.int32)
+    m = emu.emu_banded_table(level, levels, samples, 16, entries.ctypes.data, band_min.ctypes.data, bands_plain.ctypes.data)
+    out = np.zeros(4 * (2 * samples + 8 * band), np.float32)
+    rho = np.zeros(sectors * (samples + 8), np.float32)
+    scale = np.float32(2.0 ** 64)
+    bands = emu.emu_sector_table(level, levels, samples, sectors, scale, out.ctypes.data, out.size, rho.ctypes.data)
+    assert bands > 0
+    q = out[: 4 * bands * band].reshape(bands * band // 2, 2, 2, 2)
+    flat = np.zeros((bands * band, 4), np.float32)
+    flat[0::2] = np.stack([q[:, 0, 0, 0], q[:, 0, 1, 0], q[:, 1, 0, 0], q[:, 1, 1, 0]], axis=1)
+    flat[1::2] = np.stack([q[:, 0, 0, 1], q[:, 0, 1, 1], q[:, 1, 0, 1], q[:, 1, 1, 1]], axis=1)
+    real = flat[flat[:, 2] > scale * np.float32(2.0 ** -30)]
+    fill = flat[flat[:, 2] <= scale * np.float32(2.0 ** -30)]
+    assert len(real) == m and np.all(fill[:, :2] == 0) and np.all(fill[:, 2] == scale * np.float32(2.0 ** -60))
+    want = np.stack([(entries[:m, 0].astype(np.float64) / entries[:m, 2]).astype(np.float32), (entries[:m, 1].astype(np.float64) / entries[:m, 2]).astype(np.float32),
+                     entries[:m, 2] * scale, entries[:m, 3] * scale], axis=1)
+    key = lambda a: a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]
+    assert np.array_equal(key(real), key(want))
+    # every entry sits in its sector's share, and rho_max bounds it
+    per = band // sectors
+    for i, e in enumerate(flat):
+        if e[2] <= scale * np.float32(2.0 ** -30):
+            continue
+        k, w = i // band, (i % band) // per
+        phi = np.arctan2(np.float64(e[1]), np.float64(e[0]))
+        assert int(min(max(np.floor((phi + np.pi) / (2 * np.pi / sectors)), 0), sectors - 1)) == w
+        assert np.hypot(np.float64(e[0]), np.float64(e[1])) <= rho[w * bands + k]
+    r = rho[: sectors * bands].reshape(sectors, bands)
+    assert np.all(np.diff(r, axis=1) >= 0)
+
+
 def test_dn_tap_decodes_every_field_exactly():
     """One tap of weight w through the subnormal-mantissa path == w * rgbe decode, for the
     extreme exponents, mantissas and weights (products must stay in the normal range)."""
