@@ -132,7 +132,7 @@ struct datum_ibl_ctx
   size_t host_stage_bytes = 0;
   DeviceBuffer<uint4> records;    // quad records of the current source level
   std::map<std::pair<int, int>, float*> frames; // source size -> per-texel frames of the destination level (ibl::launch_build_frames)
-  size_t frames_bytes = 0;
+  size_t frames_bytes = 0, world_frames_bytes = 0;
   std::map<std::pair<int, int>, float*> world_frames; // destination size -> world-space T, B, N per texel (tail kernel; levels of at most kWorldFrameTexels)
   DeviceBuffer<int> queue_heads;  // per-SM tile queue heads of the prefilter kernel
   int prefilter_no_steal = 0;
@@ -386,10 +386,9 @@ namespace
           ctx->frames.clear();
           ctx->frames_bytes = 0;
         }
-        ctx->frames_bytes += bytes;
 
         float *built = nullptr;
-        err = cudaMalloc(&built, sizeof(float) * ibl::frame_floats(wd, hd));
+        err = cudaMalloc(&built, bytes);
         if (err == cudaSuccess)
         {
           err = ibl::launch_build_frames(built, ws, hs, ctx->quats, ctx->stream);
@@ -399,6 +398,7 @@ namespace
         if (err != cudaSuccess)
           return fail_cuda("build_frames", err);
         ctx->launches += 1;
+        ctx->frames_bytes += bytes;
         found = ctx->frames.emplace(std::make_pair(ws, hs), built).first;
       }
       frames = found->second;
@@ -484,8 +484,20 @@ namespace
         auto found = ctx->world_frames.find(std::make_pair(wd, hd));
         if (found == ctx->world_frames.end())
         {
+          // the same bound as for the pair kernel's planes: start over above 256 MiB
+          const size_t bytes = sizeof(float) * (size_t)ibl::kWorldFrameFloats * 6 * wd * hd;
+          if (ctx->world_frames_bytes + bytes > ((size_t)1 << 28) && !ctx->world_frames.empty())
+          {
+            cudaStreamSynchronize(ctx->stream);
+            for(auto &entry : ctx->world_frames)
+              cudaFree(entry.second);
+            ctx->world_frames.clear();
+    ctx->world_frames_bytes = 0;
+            ctx->world_frames_bytes = 0;
+          }
+
           float *built = nullptr;
-          cudaError_t err = cudaMalloc(&built, sizeof(float) * (size_t)ibl::kWorldFrameFloats * 6 * wd * hd);
+          cudaError_t err = cudaMalloc(&built, bytes);
           if (err == cudaSuccess)
           {
             err = ibl::launch_build_world_frames(built, wd, hd, ctx->quats, ctx->stream);
@@ -495,6 +507,7 @@ namespace
           if (err != cudaSuccess)
             return fail_cuda("build_world_frames", err);
           ctx->launches += 1;
+          ctx->world_frames_bytes += bytes;
           found = ctx->world_frames.emplace(std::make_pair(wd, hd), built).first;
         }
         world_frames = found->second;
@@ -1125,6 +1138,7 @@ extern "C"
     for(auto &entry : ctx->world_frames)
       cudaFree(entry.second);
     ctx->world_frames.clear();
+    ctx->world_frames_bytes = 0;
     ctx->queue_heads.release();
     ctx->peer_ticket.release();
     ctx->sh_weights.release();
