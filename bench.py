@@ -410,7 +410,8 @@ def config_c3(job, ctx, engine, stream):
 def config_c3_one_process(job, ctx):
     """Config 3 through the device-list entry point: ONE process (this rank, after the others have left)
     drives all the GPUs of the job — what DATUM_IBL_DEVICES gives a single-process assetbuilder.  End to end
-    from a pinned host payload: level 0 up once and copied GPU to GPU, the chain back from the first GPU."""
+    from a pinned host payload: every GPU uploads one slice of level 0 and fetches the rest from its peers, every GPU
+    sends one slice of the baked chain back."""
     import datum_b200
     from datum_b200 import synth
 
