@@ -492,7 +492,6 @@ namespace
             for(auto &entry : ctx->world_frames)
               cudaFree(entry.second);
             ctx->world_frames.clear();
-    ctx->world_frames_bytes = 0;
             ctx->world_frames_bytes = 0;
           }
 
