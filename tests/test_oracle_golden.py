@@ -128,6 +128,30 @@ def test_oracle_vs_compiled_reference_fresh_input():
 
 # ---- properties of the bake the GPU tests reuse at full size ----
 
+@pytest.mark.skipif(not (oracle_lib.have_ref() and oracle_lib.have_ref(fast=True)), reason="oracle/_ref not built (needs /root/reference)")
+def test_the_reference_differs_from_itself_by_more_than_the_gpu_tolerance():
+    """Why "identical to the reference" is a tolerance and not a bit pattern (tests/parity.py): the UNMODIFIED
+    tools/ibl.cpp built with its own flags (-O2 -ffast-math, what assetbuilder ships) and built strictly (the
+    build the oracle is word-identical to) disagree on level 1 of the same level 0 — on a few per cent of the
+    words of a noisy HDR source, by up to two mantissa codes, also on texels without any sample near a cube
+    edge.  The CUDA path is held to >= 99 % identical words and <= 1 code against the oracle
+    (tests/test_prefilter_gpu.py); it measures >= 99.8 %."""
+    import datum_b200
+
+    w, levels = 64, 7
+    offs = datum_b200.level_offsets(w, w, levels)
+    src = synth.synthetic_chain(w, w, levels, probe=5, noise=True, sun=False)
+    strict, fast = src.copy(), src.copy()
+    oracle_lib.ref(False).ref_image_buildmips_cube_ibl(w, w, levels, strict.ctypes.data)
+    oracle_lib.ref(True).ref_image_buildmips_cube_ibl(w, w, levels, fast.ctypes.data)
+    assert np.array_equal(strict[: offs[1]], fast[: offs[1]])              # the same level 0 ...
+    a, b = strict[offs[1]:offs[2]], fast[offs[1]:offs[2]]                  # ... and the first level computed from it
+    clean = oracle_lib.edge_ambiguous_counts(w // 2, w // 2, 1, levels, 1024) == 0
+    stats = oracle_lib.word_stats(a[clean], b[clean])
+    assert stats["identical"] < 0.99 and stats["max_code"] >= 1, stats     # measured: 97.9 % identical, 2 codes
+    assert stats["identical"] > 0.9 and stats["max_code"] <= 4, stats      # still the same image
+
+
 def test_constant_environment_stays_constant():
     w, levels = 16, 5
     offs = [0]
