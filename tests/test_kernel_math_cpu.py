@@ -103,7 +103,8 @@ def test_dn_kernel_math_matches_oracle(ws, levels, level, noise):
     assert stats["max_code"] <= 1 and stats["exp_mismatch"] == 0 and stats["identical"] >= 0.99
 
 
-@pytest.mark.parametrize("ws,levels,level,samples,noise", [(16, 5, 1, 1024, True), (32, 6, 2, 1024, True), (8, 4, 3, 1024, True), (16, 5, 2, 7, True), (24, 4, 1, 100, False)])
+@pytest.mark.parametrize("ws,levels,level,samples,noise", [(16, 5, 1, 1024, True), (32, 6, 2, 1024, True), (8, 4, 3, 1024, True), (16, 5, 2, 7, True), (24, 4, 1, 100, False),
+                                                           (64, 8, 1, 1024, True), (32, 12, 1, 4096, True)])
 def test_pair_kernel_math_matches_the_one_sample_kernel_and_the_oracle(ws, levels, level, samples, noise):
     """prefilter_dp_kernel's arithmetic (ibl_math.cuh "projective form"): the table of (lx/lz, ly/lz) with its
     filled-up last band read two entries at a time, folded frame rows, the record index out of the fp32
