@@ -128,7 +128,8 @@ def test_pair_kernel_math_matches_the_one_sample_kernel_and_the_oracle(ws, level
     want_words, want_f32 = oracle_lib.prefilter_level(src, ws, ws, level, levels, samples)
     assert oracle_lib.relative_error(b_f, want_f32)[clean].max() <= 1e-4
     stats = oracle_lib.word_stats(b_w[clean], want_words[clean])
-    assert stats["max_code"] <= 1 and stats["exp_mismatch"] == 0
+    assert stats["max_code"] <= 1
+    assert stats["exp_mismatch"] == 0 or stats["max_value_rel"] <= 4e-3      # a value that straddles a power of two: one code apart in value (tests/parity.py)
 
 
 @pytest.mark.parametrize("level,levels,samples", [(1, 8, 1024), (7, 8, 1024), (2, 5, 16), (3, 4, 7), (1, 12, 4096)])
